@@ -1,0 +1,73 @@
+"""ctypes binding of libbgmm.so (the C ABI declared in include/bgmm.h).
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libbgmm.so")
+
+# constants mirrored from include/bgmm.h (checked against bgmm_abi_version at load time)
+ABI_VERSION = 1
+F64, F32 = 0, 1
+PASS_AUTO, PASS_SIMPLE, PASS_DMMA = 0, 1, 2
+SMALL_FEATURES, SMALL_ITERATE, SMALL_STATS = 0, 1, 2
+
+OFF_NAMES = ("center", "alpha0", "kappa0", "nu0", "m0", "w0inv", "lnb0", "lnc0", "params0", "params1", "stats",
+             "ns", "xbar", "smats", "vlk", "vlterms", "vlhist", "ctrl", "total", "stats_len", "params_len", "pitch")
+POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb", "coef")
+CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR = range(7)
+N_CTRL = 16
+
+_lib = None
+
+
+def load():
+    """Load libbgmm.so once; raises RuntimeError (no CPU fallback) when it cannot be loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA library is required (no CPU fallback). "
+            "Build it with `python -m bayesml_b200.build`.")
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, f64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    lib.bgmm_abi_version.restype = i32
+    lib.bgmm_abi_version.argtypes = []
+    lib.bgmm_last_error.restype = ctypes.c_char_p
+    lib.bgmm_last_error.argtypes = []
+    lib.bgmm_layout.restype = i32
+    lib.bgmm_layout.argtypes = [i32, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+    lib.bgmm_workspace_doubles.restype = i64
+    lib.bgmm_workspace_doubles.argtypes = [i32, i32]
+    lib.bgmm_colsum.restype = i32
+    lib.bgmm_colsum.argtypes = [vp, i64, i32, i32, vp, vp, vp]
+    lib.bgmm_center.restype = i32
+    lib.bgmm_center.argtypes = [vp, i32, vp, i32, i64, i32, vp, vp]
+    lib.bgmm_pass.restype = i32
+    lib.bgmm_pass.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.bgmm_pass_supported.restype = i32
+    lib.bgmm_pass_supported.argtypes = [i32, i32, i32, i32]
+    lib.bgmm_small.restype = i32
+    lib.bgmm_small.argtypes = [i32, i32, vp, i32, i32, f64, i32, vp]
+    if lib.bgmm_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libbgmm ABI {lib.bgmm_abi_version()} != binding ABI {ABI_VERSION}; rebuild the library")
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().bgmm_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def layout(K, D, hist_len):
+    """Offsets (in doubles) of the device state block; see include/bgmm.h."""
+    lib = load()
+    off = (ctypes.c_int64 * len(OFF_NAMES))()
+    poff = (ctypes.c_int64 * len(POFF_NAMES))()
+    check(lib.bgmm_layout(K, D, hist_len, off, poff), "bgmm_layout")
+    return dict(zip(OFF_NAMES, off)), dict(zip(POFF_NAMES, poff))

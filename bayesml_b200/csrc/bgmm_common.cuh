@@ -1,0 +1,101 @@
+// Shared device/host helpers for libbgmm (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/bgmm.h"
+
+namespace bgmm {
+
+__host__ __device__ inline int feat_count(int D) { return 1 + D + D * (D + 1) / 2; }
+__host__ __device__ inline int feat_pitch(int D) { return (feat_count(D) + 7) & ~7; }
+
+// State-block layout (units: doubles).  Mirrors bgmm_layout(); kept in one place so kernels and host agree.
+struct Layout {
+    int K, D, P, pitch, hist_len;
+    int64_t center, alpha0, kappa0, nu0, m0, w0inv, lnb0, lnc0, params[2], stats, ns, xbar, smats, vlk, vlterms,
+        vlhist, ctrl, total, stats_len, params_len;
+    // offsets inside one parameter set
+    int64_t p_alpha, p_kappa, p_nu, p_m, p_winv, p_w, p_elnpi, p_elndet, p_lnb, p_coef;
+};
+
+__host__ __device__ inline int64_t align8(int64_t v) { return (v + 7) & ~int64_t(7); }
+
+__host__ __device__ inline Layout make_layout(int K, int D, int hist_len) {
+    Layout L;
+    L.K = K; L.D = D; L.P = feat_count(D); L.pitch = feat_pitch(D); L.hist_len = hist_len;
+    const int64_t KD = (int64_t)K * D, KDD = KD * D;
+    int64_t o = 0;
+    L.p_alpha = o;  o += align8(K);
+    L.p_kappa = o;  o += align8(K);
+    L.p_nu = o;     o += align8(K);
+    L.p_m = o;      o += align8(KD);
+    L.p_winv = o;   o += align8(KDD);
+    L.p_w = o;      o += align8(KDD);
+    L.p_elnpi = o;  o += align8(K);
+    L.p_elndet = o; o += align8(K);
+    L.p_lnb = o;    o += align8(K);
+    L.p_coef = o;   o += (int64_t)K * L.pitch;
+    L.params_len = o;
+    o = 0;
+    L.center = o;  o += align8(D);
+    L.alpha0 = o;  o += align8(K);
+    L.kappa0 = o;  o += align8(K);
+    L.nu0 = o;     o += align8(K);
+    L.m0 = o;      o += align8(KD);
+    L.w0inv = o;   o += align8(KDD);
+    L.lnb0 = o;    o += align8(K);
+    L.lnc0 = o;    o += 8;
+    L.params[0] = o; o += L.params_len;
+    L.params[1] = o; o += L.params_len;
+    L.stats_len = (int64_t)K * L.pitch + 8;
+    L.stats = o;   o += L.stats_len;
+    L.ns = o;      o += align8(K);
+    L.xbar = o;    o += align8(KD);
+    L.smats = o;   o += align8(KDD);
+    L.vlk = o;     o += (int64_t)K * 8;
+    L.vlterms = o; o += 8;
+    L.ctrl = o;    o += BGMM_N_CTRL / 2;  // int32[16]
+    L.vlhist = o;  o += align8(hist_len); // variable length: keep it LAST so no other offset depends on hist_len
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum; result valid in every thread.  `scratch` holds >= 33 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();  // protect scratch from a previous call
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = (lane < nwarp) ? scratch[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// Arguments of one pass launch (see bgmm_pass in include/bgmm.h).
+struct PassArgs {
+    const void* x;
+    int64_t n;
+    double* state;
+    double* workspace;
+    double* r_out;
+    double* lnrho_out;
+    int32_t* argmax_out;
+    const double* r_in;
+    int force, accumulate;
+};
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+}  // namespace bgmm

@@ -1,0 +1,300 @@
+// bgmm_small: the O(K D^3) part of one VB iteration, one CTA per mixture component.
+//
+// Replaces, in /root/reference/bayesml/gaussianmixture/_gaussianmixture.py:
+//   _update_q_mu_lambda :758-770   kappa, m, nu, W^-1 from (N_k, x_bar_k, S_k); W = inv(W^-1)
+//   _update_q_pi        :741-743   alpha = alpha0 + N
+//   _calc_q_pi_features :738-739   E[ln pi_k] = psi(alpha_k) - psi(sum alpha)
+//   _calc_q_lambda_features :745-756   E[ln|Lambda|], ln B(W, nu)   (E[Lambda] = nu W is folded into coef)
+//   _calc_vl            :671-723   all K-sized ELBO terms (the O(N K) term sum r ln r comes from bgmm_pass)
+//   update_posterior    :869       the convergence test, on the device (no host sync in the loop)
+// The reference inverts with LAPACK LU (`np.linalg.inv`, `slogdet`); W^-1 is SPD so this kernel uses one
+// Cholesky factorisation for the inverse and the log-determinant (agrees to cond*eps, tested vs the oracle).
+#include "bgmm_common.cuh"
+#include <math.h>
+
+namespace bgmm {
+
+// psi(x), x > 0: upward recurrence to x >= 10 then the asymptotic series (error < 1e-16 relative there).
+__device__ double digamma_pos(double x) {
+    double r = 0.0;
+    while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+    const double inv = 1.0 / x, inv2 = inv * inv;
+    double s = 691.0 / 32760.0 - inv2 * (1.0 / 12.0);
+    s = 1.0 / 132.0 - inv2 * s;
+    s = 1.0 / 240.0 - inv2 * s;
+    s = 1.0 / 252.0 - inv2 * s;
+    s = 1.0 / 120.0 - inv2 * s;
+    s = 1.0 / 12.0 - inv2 * s;
+    return r + log(x) - 0.5 * inv - inv2 * s;
+}
+
+constexpr double LN2 = 0.693147180559945309417232121458;
+constexpr double LNPI = 1.144729885849400174143427351353;
+constexpr double LN2PI = 1.837877066409345483560659472811;
+
+__global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, const Layout L, const int mode,
+                                                    const int max_itr, const double tol) {
+    extern __shared__ double sm[];
+    const int K = L.K, D = L.D, DD = D * D, k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
+    const bool iterate = (mode == BGMM_SMALL_ITERATE), stats_only = (mode == BGMM_SMALL_STATS);
+    if (iterate && ctrl[BGMM_CTRL_DONE]) return;  // every CTA reads this before any CTA can take the last ticket
+    const int cur = ctrl[BGMM_CTRL_CUR];
+    double* Pc = st + L.params[cur];
+    double* Pn = iterate ? st + L.params[cur ^ 1] : Pc;
+
+    double* A = sm;             // [D][D]  W^-1 -> L -> L^-1
+    double* xbar = A + DD;      // [D]
+    double* dev = xbar + D;     // [D]
+    double* mnew = dev + D;     // [D]
+    double* lin = mnew + D;     // [D]
+    double* scratch = lin + D;  // [40]
+
+    const double* center = st + L.center;
+    const double* m0 = st + L.m0 + (int64_t)k * D;
+    const double* w0inv = st + L.w0inv + (int64_t)k * DD;
+    const double alpha0 = st[L.alpha0 + k], kappa0 = st[L.kappa0 + k], nu0 = st[L.nu0 + k];
+
+    double kn, nun, an, alpha_sum_new;
+
+    if (iterate || stats_only) {
+        // ---- statistics of component k from the raw moments (about the centre) ----
+        const double* raw = st + L.stats + (int64_t)k * L.pitch;
+        const double N = raw[0];
+        double* S = st + L.smats + (int64_t)k * DD;
+        if (N > 0.0) {
+            for (int i = tid; i < D; i += nt) xbar[i] = raw[1 + i] / N;
+            __syncthreads();
+            for (int e = tid; e < DD; e += nt) {
+                const int i = e / D, j = e - i * D, hi = max(i, j), lo = min(i, j);
+                S[e] = raw[1 + D + hi * (hi + 1) / 2 + lo] / N - xbar[i] * xbar[j];
+            }
+        } else {
+            // reference :729 — x_bar_vecs[k] keeps the un-normalised sum (0 in the original frame), s_mats[k] stale
+            for (int i = tid; i < D; i += nt) xbar[i] = -center[i];
+        }
+        __syncthreads();
+        for (int i = tid; i < D; i += nt) st[L.xbar + (int64_t)k * D + i] = xbar[i];
+        if (tid == 0) st[L.ns + k] = N;
+        if (stats_only) return;
+
+        // ---- ELBO terms of component k under the CURRENT parameters (those the pass used) ----
+        const double kappa = Pc[L.p_kappa + k], nu = Pc[L.p_nu + k], alpha = Pc[L.p_alpha + k];
+        const double elnpi = Pc[L.p_elnpi + k], elndet = Pc[L.p_elndet + k], lnb = Pc[L.p_lnb + k];
+        const double* W = Pc + L.p_w + (int64_t)k * DD;
+        const double* m = Pc + L.p_m + (int64_t)k * D;
+        double t_trs = 0.0, t_q1 = 0.0, t_q2 = 0.0, t_tr0 = 0.0;
+        for (int e = tid; e < DD; e += nt) {
+            const int i = e / D, j = e - i * D;
+            const double w = W[e];
+            t_trs += S[e] * w;
+            t_q1 += (xbar[i] - m[i]) * w * (xbar[j] - m[j]);
+            t_q2 += (m[i] - m0[i]) * w * (m[j] - m0[j]);
+            t_tr0 += w0inv[e] * w;
+        }
+        t_trs = block_sum(t_trs, scratch);
+        t_q1 = block_sum(t_q1, scratch);
+        t_q2 = block_sum(t_q2, scratch);
+        t_tr0 = block_sum(t_tr0, scratch);
+        if (tid == 0) {
+            double* vk = st + L.vlk + (int64_t)k * 8;
+            const double lnb0 = st[L.lnb0 + k];
+            vk[0] = N * (elndet - D / kappa - nu * t_trs - nu * t_q1 - D * LN2PI) / 2.0;          // :673-683
+            vk[1] = N * elnpi;                                                                     // :686
+            vk[2] = (alpha0 - 1.0) * elnpi;                                                        // :689
+            vk[3] = (D * (log(kappa0) - LN2PI - kappa0 / kappa) - kappa0 * nu * t_q2 + 2.0 * lnb0
+                     + (nu0 - D) * elndet - nu * t_tr0) / 2.0;                                     // :692-701
+            vk[4] = lgamma(alpha) - (alpha - 1.0) * digamma_pos(alpha);                            // :707 (per-k part)
+            vk[5] = (D * (1.0 + LN2PI - log(kappa)) - 2.0 * lnb - (nu - D) * elndet + nu * D) / 2.0;  // :710-715
+            vk[6] = alpha;
+            vk[7] = 0.0;
+        }
+
+        // ---- M-step (:758-768, :742) into the other parameter set ----
+        kn = kappa0 + N; nun = nu0 + N; an = alpha0 + N;
+        for (int i = tid; i < D; i += nt) {
+            mnew[i] = (kappa0 * m0[i] + N * xbar[i]) / kn;
+            dev[i] = xbar[i] - m0[i];
+        }
+        __syncthreads();
+        const double c2 = kappa0 * N / kn;
+        double* winv_out = Pn + L.p_winv + (int64_t)k * DD;
+        for (int e = tid; e < DD; e += nt) {
+            const int i = e / D, j = e - i * D;
+            const double v = w0inv[e] + N * S[e] + c2 * (dev[i] * dev[j]);
+            A[e] = v;
+            winv_out[e] = v;
+        }
+        double asum = 0.0;
+        for (int j = tid; j < K; j += nt) asum += st[L.alpha0 + j] + st[L.stats + (int64_t)j * L.pitch];
+        alpha_sum_new = block_sum(asum, scratch);
+        if (tid == 0) { Pn[L.p_kappa + k] = kn; Pn[L.p_nu + k] = nun; Pn[L.p_alpha + k] = an; }
+        for (int i = tid; i < D; i += nt) Pn[L.p_m + (int64_t)k * D + i] = mnew[i];
+    } else {
+        kn = Pc[L.p_kappa + k]; nun = Pc[L.p_nu + k]; an = Pc[L.p_alpha + k];
+        for (int i = tid; i < D; i += nt) mnew[i] = Pc[L.p_m + (int64_t)k * D + i];
+        for (int e = tid; e < DD; e += nt) A[e] = Pc[L.p_winv + (int64_t)k * DD + e];
+        double asum = 0.0;
+        for (int j = tid; j < K; j += nt) asum += Pc[L.p_alpha + j];
+        alpha_sum_new = block_sum(asum, scratch);
+    }
+    __syncthreads();
+
+    // ---- Cholesky A = L L^T (lower, in place, right-looking) ----
+    bool spd = true;
+    for (int j = 0; j < D; ++j) {
+        const double ajj = A[j * D + j];
+        if (!(ajj > 0.0)) spd = false;
+        const double ljj = sqrt(ajj);
+        __syncthreads();
+        if (tid == 0) A[j * D + j] = ljj;
+        for (int i = j + 1 + tid; i < D; i += nt) A[i * D + j] /= ljj;
+        __syncthreads();
+        const int rem = D - j - 1;
+        for (int e = tid; e < rem * rem; e += nt) {
+            const int i = j + 1 + e / rem, l = j + 1 + e % rem;
+            if (l <= i) A[i * D + l] -= A[i * D + j] * A[l * D + j];
+        }
+        __syncthreads();
+    }
+    double ld = 0.0;
+    for (int i = tid; i < D; i += nt) ld += log(A[i * D + i]);
+    const double logdet = 2.0 * block_sum(ld, scratch);  // ln|W^-1|
+    if (!spd && tid == 0) ctrl[BGMM_CTRL_ERROR] = 1;
+
+    // ---- L <- L^-1 in place (column sweep from the last column; lower triangular) ----
+    for (int j = D - 1; j >= 0; --j) {
+        const double inv_jj = 1.0 / A[j * D + j];
+        // x = L[j+1:, j]; new x_i = -inv_jj * sum_{l=j+1..i} Linv[i][l] * x_l
+        for (int i = j + 1 + tid; i < D; i += nt) lin[i] = A[i * D + j];
+        __syncthreads();
+        for (int i = j + 1 + tid; i < D; i += nt) {
+            double acc = 0.0;
+            for (int l = j + 1; l <= i; ++l) acc += A[i * D + l] * lin[l];
+            A[i * D + j] = -inv_jj * acc;
+        }
+        if (tid == 0) A[j * D + j] = inv_jj;
+        __syncthreads();
+    }
+
+    // ---- W = L^-T L^-1 ----
+    double* Wout = Pn + L.p_w + (int64_t)k * DD;
+    for (int e = tid; e < DD; e += nt) {
+        const int i = e / D, j = e - i * D;
+        double acc = 0.0;
+        for (int l = max(i, j); l < D; ++l) acc += A[l * D + i] * A[l * D + j];
+        Wout[e] = acc;
+    }
+
+    // ---- features (:738-739, :745-756) ----
+    double ps = 0.0, gs = 0.0;
+    for (int i = tid; i < D; i += nt) {
+        const double a = (nun - i) / 2.0;
+        ps += digamma_pos(a);
+        gs += lgamma(a);
+    }
+    ps = block_sum(ps, scratch);
+    gs = block_sum(gs, scratch);
+    const double elndet_n = ps + D * LN2 - logdet;
+    const double lnb_n = (nun * logdet - nun * D * LN2 - D * (D - 1) / 2.0 * LNPI - gs * 2.0) / 2.0;
+    const double elnpi_n = digamma_pos(an) - digamma_pos(alpha_sum_new);
+    if (tid == 0) {
+        Pn[L.p_elndet + k] = elndet_n;
+        Pn[L.p_lnb + k] = lnb_n;
+        Pn[L.p_elnpi + k] = elnpi_n;
+    }
+    __syncthreads();  // Wout visible to the whole CTA
+
+    // ---- E-step coefficient row: ln rho = coef . phi(x'), Lambda = nu W ----
+    for (int i = tid; i < D; i += nt) {
+        double acc = 0.0;
+        for (int j = 0; j < D; ++j) acc += Wout[i * D + j] * mnew[j];
+        lin[i] = nun * acc;
+    }
+    __syncthreads();
+    double mq = 0.0;
+    for (int i = tid; i < D; i += nt) mq += mnew[i] * lin[i];
+    mq = block_sum(mq, scratch);
+    double* coef = Pn + L.p_coef + (int64_t)k * L.pitch;
+    if (tid == 0) coef[0] = elnpi_n + (elndet_n - D * LN2PI - D / kn) / 2.0 - 0.5 * mq;
+    for (int i = tid; i < D; i += nt) coef[1 + i] = lin[i];
+    const int nq = D * (D + 1) / 2;
+    for (int q = tid; q < nq; q += nt) {
+        int i = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
+        while (i * (i + 1) / 2 > q) --i;
+        while ((i + 1) * (i + 2) / 2 <= q) ++i;
+        const int j = q - i * (i + 1) / 2;
+        coef[1 + D + q] = (i == j) ? -0.5 * nun * Wout[i * D + i] : -nun * Wout[i * D + j];
+    }
+    for (int q = L.P + tid; q < L.pitch; q += nt) coef[q] = 0.0;
+
+    if (!iterate) return;
+
+    // ---- last CTA: sum the ELBO, convergence test (:869), flip the parameter sets ----
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int t = atomicAdd(const_cast<int*>(&ctrl[BGMM_CTRL_TICKET]), 1);
+        is_last = (t == K - 1);
+    }
+    __syncthreads();
+    if (!is_last || tid != 0) return;
+    __threadfence();
+    volatile const double* vk = st + L.vlk;
+    double px = 0, pz = 0, ppi = 0, pml = 0, qpi = 0, qml = 0, asum = 0;
+    for (int j = 0; j < K; ++j) {
+        px += vk[j * 8 + 0]; pz += vk[j * 8 + 1]; ppi += vk[j * 8 + 2]; pml += vk[j * 8 + 3];
+        qpi += vk[j * 8 + 4]; qml += vk[j * 8 + 5]; asum += vk[j * 8 + 6];
+    }
+    ppi += st[L.lnc0];
+    const double qz = -st[L.stats + (int64_t)K * L.pitch];                    // -sum r ln r (:704)
+    qpi += -lgamma(asum) + (asum - K) * digamma_pos(asum);                    // dirichlet entropy (:707)
+    const double vl = px + pz + ppi + pml + qz + qpi + qml;                   // :717-723
+    double* vt = st + L.vlterms;
+    vt[0] = px; vt[1] = pz; vt[2] = ppi; vt[3] = pml; vt[4] = qz; vt[5] = qpi; vt[6] = qml; vt[7] = vl;
+    const int iter = ctrl[BGMM_CTRL_ITER];
+    double* hist = st + L.vlhist;
+    if (iter < L.hist_len) hist[iter] = vl;
+    bool conv = false;
+    if (iter >= 1 && iter - 1 < L.hist_len) {
+        const double vb = hist[iter - 1];
+        conv = fabs((vl - vb) / vb) < tol;
+    }
+    if (conv) { ctrl[BGMM_CTRL_CONVERGED] = 1; ctrl[BGMM_CTRL_DONE] = 1; }
+    else if (iter >= max_itr) { ctrl[BGMM_CTRL_DONE] = 1; }
+    else { ctrl[BGMM_CTRL_CUR] = cur ^ 1; }
+    ctrl[BGMM_CTRL_ITER] = iter + 1;
+    ctrl[BGMM_CTRL_TICKET] = 0;
+}
+
+}  // namespace bgmm
+
+extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, double tol, int hist_len,
+                          void* stream) {
+    using namespace bgmm;
+    if (K <= 0 || D <= 0 || state == nullptr || hist_len < 1) {
+        set_error("bgmm_small: bad argument (K=%d D=%d state=%p hist_len=%d)", K, D, (void*)state, hist_len);
+        return BGMM_EINVAL;
+    }
+    if (mode != BGMM_SMALL_FEATURES && mode != BGMM_SMALL_ITERATE && mode != BGMM_SMALL_STATS) {
+        set_error("bgmm_small: unknown mode %d", mode);
+        return BGMM_EINVAL;
+    }
+    const Layout L = make_layout(K, D, hist_len);
+    const size_t smem = sizeof(double) * ((size_t)D * D + 4 * (size_t)D + 40);
+    if (smem > 227 * 1024) {
+        set_error("bgmm_small: D=%d needs %zu B of shared memory (> 227 KiB)", D, smem);
+        return BGMM_ENOSUP;
+    }
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        int rc = check_cuda(cudaFuncSetAttribute(small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(small_kernel)");
+        if (rc) return rc;
+        configured = smem;
+    }
+    const int nt = D <= 8 ? 64 : (D <= 32 ? 128 : 256);
+    small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol);
+    return check_cuda(cudaGetLastError(), "small_kernel launch");
+}

@@ -1,0 +1,256 @@
+"""Device engine of the VB Gaussian-mixture hot path.
+
+Owns the device buffers (torch tensors: plumbing only) and drives the kernels of libbgmm.so through the C ABI
+(include/bgmm.h).  One engine lives on one GPU; with a torch.distributed process group every rank holds a
+shard of the rows of X and the only exchange per VB iteration is one all-reduce of the packed statistics
+buffer [K*PITCH raw moments | sum r ln r | rows]  (SURVEY.md §8e).
+
+Reference call sites replaced (bayesml/gaussianmixture/_gaussianmixture.py): the VB loop :862-872 runs on the
+device; the host only syncs once per chunk of iterations to read the ELBO history and the done flag.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DTYPES = {"float64": (_lib.F64, torch.float64), "float32": (_lib.F32, torch.float32)}
+
+
+class VBEngine:
+    def __init__(self, K, D, device=None, precision="float64", group=None, variant=_lib.PASS_AUTO):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("bayesml_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.K, self.D = int(K), int(D)
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if precision not in _DTYPES:
+            raise ValueError(f"precision must be 'float64' or 'float32', got {precision!r}")
+        self.precision = precision
+        self.x_code, self.x_torch_dtype = _DTYPES[precision]
+        self.group = group
+        env = os.environ.get("BAYESML_B200_PASS_VARIANT", "").lower()     # debugging / tests: force a kernel variant
+        if env:
+            variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA}[env]
+        self.variant = variant
+        self.hist_len = 0
+        self.state = None
+        self.x = None
+        self.n_local = 0
+        self.n_global = 0
+        self.center = np.zeros(self.D)
+        self.passes = 0                       # pass launches (for gpu_launches accounting)
+        self.small_launches = 0
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(int(self.lib.bgmm_workspace_doubles(self.K, self.D)), dtype=torch.float64,
+                                         device=self.device)
+        self._alloc_state(2)
+        self.r_dev = self.lnrho_dev = self.argmax_dev = None
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc_state(self, hist_len):
+        if self.state is not None and hist_len <= self.hist_len:
+            return
+        old = None
+        if self.state is not None:
+            old = (self.state, self.off)
+        self.hist_len = int(hist_len)
+        self.off, self.poff = _lib.layout(self.K, self.D, self.hist_len)
+        self.state = torch.zeros(self.off["total"], dtype=torch.float64, device=self.device)
+        if old is not None:  # keep centre + prior + parameter sets (everything before the statistics)
+            n_keep = old[1]["stats"]
+            self.state[:n_keep].copy_(old[0][:n_keep])
+        self._host_ctrl = torch.empty(_lib.N_CTRL, dtype=torch.int32).pin_memory()
+        self._host_hist = torch.empty(self.hist_len, dtype=torch.float64).pin_memory()
+
+    def _view(self, name, length):
+        o = self.off[name]
+        return self.state[o:o + length]
+
+    def _pview(self, which, name, length):
+        o = self.off[f"params{which}"] + self.poff[name]
+        return self.state[o:o + length]
+
+    @property
+    def ctrl(self):
+        o = self.off["ctrl"]
+        return self.state[o:o + _lib.N_CTRL // 2].view(torch.int32)
+
+    @property
+    def stats(self):
+        o = self.off["stats"]
+        return self.state[o:o + self.off["stats_len"]]
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _put(self, view, arr):
+        view.copy_(torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)), non_blocking=False)
+
+    # ------------------------------------------------------------------ data
+    def load_data(self, x):
+        """Upload the local rows of X ((n, D) numpy array or torch tensor), centre them about the global column mean."""
+        K, D = self.K, self.D
+        with torch.cuda.device(self.device):
+            if isinstance(x, torch.Tensor):
+                xt = x.reshape(-1, D)
+                if xt.device != self.device:
+                    xt = xt.to(self.device, non_blocking=True)
+                raw = xt if xt.dtype in (torch.float64, torch.float32) else xt.to(torch.float64)
+                raw = raw.contiguous()
+            else:
+                xa = np.ascontiguousarray(x).reshape(-1, D)
+                if xa.dtype not in (np.float64, np.float32):
+                    xa = xa.astype(np.float64)
+                raw = torch.from_numpy(xa).to(self.device)
+            raw_code = _lib.F64 if raw.dtype == torch.float64 else _lib.F32
+            n = raw.shape[0]
+            self.n_local = int(n)
+            colsum = torch.zeros(D + 1, dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.bgmm_colsum(raw.data_ptr(), n, D, raw_code, colsum.data_ptr(),
+                                            self.workspace.data_ptr(), self._stream()), "bgmm_colsum")
+            colsum[D] = float(n)
+            if self.group is not None:
+                torch.distributed.all_reduce(colsum, group=self.group)
+            tot = colsum.cpu().numpy()
+            self.n_global = int(round(tot[D]))
+            self.center = tot[:D] / max(self.n_global, 1)
+            cview = self._view("center", D)
+            self._put(cview, self.center)
+            if raw.dtype == self.x_torch_dtype and not isinstance(x, torch.Tensor):
+                out = raw          # our own upload buffer: centre in place
+            else:
+                out = torch.empty((n, D), dtype=self.x_torch_dtype, device=self.device)
+            _lib.check(self.lib.bgmm_center(raw.data_ptr(), raw_code, out.data_ptr(), self.x_code, n, D,
+                                            cview.data_ptr(), self._stream()), "bgmm_center")
+            self.x = out
+            self.r_dev = self.lnrho_dev = self.argmax_dev = None
+        return self
+
+    # ------------------------------------------------------------------ prior / parameters
+    def set_prior(self, alpha0, m0, kappa0, nu0, w0inv, ln_b_h0, ln_c_h0_alpha):
+        K, D = self.K, self.D
+        self._put(self._view("alpha0", K), alpha0)
+        self._put(self._view("kappa0", K), kappa0)
+        self._put(self._view("nu0", K), nu0)
+        self._put(self._view("m0", K * D), np.asarray(m0) - self.center)
+        self._put(self._view("w0inv", K * D * D), w0inv)
+        self._put(self._view("lnb0", K), ln_b_h0)
+        self._put(self._view("lnc0", 1), [ln_c_h0_alpha])
+
+    def set_params(self, alpha, m, kappa, nu, winv):
+        """Load (alpha, m, kappa, nu, W^-1) as parameter set 0, reset the control words, compute W/features/coef."""
+        K, D = self.K, self.D
+        self._put(self._pview(0, "alpha", K), alpha)
+        self._put(self._pview(0, "kappa", K), kappa)
+        self._put(self._pview(0, "nu", K), nu)
+        self._put(self._pview(0, "m", K * D), np.asarray(m) - self.center)
+        self._put(self._pview(0, "winv", K * D * D), winv)
+        self.ctrl.zero_()
+        self._small(_lib.SMALL_FEATURES, 0, 0.0)
+
+    def _small(self, mode, max_itr, tol):
+        _lib.check(self.lib.bgmm_small(self.K, self.D, self.state.data_ptr(), mode, int(max_itr), float(tol),
+                                       self.hist_len, self._stream()), "bgmm_small")
+        self.small_launches += 1
+
+    def _pass(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0):
+        ptr = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731
+        _lib.check(self.lib.bgmm_pass(ptr(self.x), self.n_local, self.K, self.D, self.x_code, self.state.data_ptr(),
+                                      self.workspace.data_ptr(), ptr(r_out), ptr(lnrho_out), ptr(argmax_out),
+                                      ptr(r_in), self.variant if r_in is None else _lib.PASS_SIMPLE, force, 0,
+                                      self._stream()), "bgmm_pass")
+        self.passes += 1
+        if self.group is not None:
+            torch.distributed.all_reduce(self.stats, group=self.group)
+
+    # ------------------------------------------------------------------ the VB loop (:860-872)
+    def run(self, max_itr, tol, r_init=None, chunk=None):
+        """Post-init ELBO + up to max_itr VB iterations on the device.
+
+        Returns (vl_history [1 + n_iter], converged).  `r_init`: (n_local, K) responsibilities for the
+        'random_responsibility' initialisation (:734-736); otherwise the first pass is an E-step with the
+        parameters loaded by set_params (:852)."""
+        max_itr = int(max_itr)
+        with torch.cuda.device(self.device):
+            self._alloc_state(max_itr + 1)
+            ctrl = self.ctrl
+            if r_init is not None:
+                r_dev = torch.as_tensor(np.ascontiguousarray(r_init, dtype=np.float64)).to(self.device)
+                self._pass(r_in=r_dev, force=1)
+            else:
+                self._pass()
+            self._small(_lib.SMALL_ITERATE, max_itr, tol)        # iter 0: post-init VL (:860) + first M-step
+            launched = 0
+            step = 4 if chunk is None else int(chunk)
+            done = max_itr == 0
+            n_eval = 1
+            while not done:
+                t0 = time.perf_counter()
+                todo = min(step, max_itr - launched)
+                for _ in range(todo):
+                    self._pass()
+                    self._small(_lib.SMALL_ITERATE, max_itr, tol)
+                launched += todo
+                self._host_ctrl.copy_(ctrl, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                hc = self._host_ctrl
+                done = bool(hc[_lib.CTRL_DONE]) or launched >= max_itr
+                n_eval = int(hc[_lib.CTRL_ITER])
+                if chunk is None:
+                    dt = time.perf_counter() - t0
+                    # aim for ~30 ms between host syncs, at most 64 queued iterations
+                    per = dt / max(todo, 1)
+                    step = int(min(64, max(1, 0.03 / max(per, 1e-6))))
+            self._host_ctrl.copy_(ctrl, non_blocking=True)
+            o = self.off["vlhist"]
+            self._host_hist.copy_(self.state[o:o + self.hist_len], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            hc = self._host_ctrl
+            if int(hc[_lib.CTRL_ERROR]):
+                raise RuntimeError("bgmm_small: a W^-1 matrix was not positive definite (Cholesky failed)")
+            n_eval = int(hc[_lib.CTRL_ITER])
+            hist = self._host_hist[:n_eval].numpy().copy()
+            return hist, bool(hc[_lib.CTRL_CONVERGED])
+
+    # ------------------------------------------------------------------ results
+    def fetch_params(self):
+        """Current parameter set as numpy arrays (m back in the original frame)."""
+        K, D = self.K, self.D
+        host = self.state.cpu().numpy()
+        cur = int(host[self.off["ctrl"]:self.off["ctrl"] + _lib.N_CTRL // 2].view(np.int32)[_lib.CTRL_CUR])
+        base = self.off[f"params{cur}"]
+        g = lambda name, n: host[base + self.poff[name]: base + self.poff[name] + n].copy()  # noqa: E731
+        out = {
+            "alpha": g("alpha", K), "kappa": g("kappa", K), "nu": g("nu", K),
+            "m": g("m", K * D).reshape(K, D) + self.center,
+            "winv": g("winv", K * D * D).reshape(K, D, D), "w": g("w", K * D * D).reshape(K, D, D),
+            "e_ln_pi": g("elnpi", K), "e_ln_lambda_dets": g("elndet", K), "ln_b": g("lnb", K),
+            "coef": g("coef", K * self.off["pitch"]).reshape(K, self.off["pitch"]),
+            "vl_terms": host[self.off["vlterms"]:self.off["vlterms"] + 8].copy(),
+        }
+        out.update(self._stats_from_host(host))
+        return out
+
+    def _stats_from_host(self, host):
+        K, D = self.K, self.D
+        ns = host[self.off["ns"]:self.off["ns"] + K].copy()
+        xbar = host[self.off["xbar"]:self.off["xbar"] + K * D].reshape(K, D) + self.center
+        smats = host[self.off["smats"]:self.off["smats"] + K * D * D].reshape(K, D, D).copy()
+        return {"ns": ns, "x_bar": xbar, "s_mats": smats}
+
+    def final_pass(self, want_r=True, want_lnrho=True, want_argmax=True):
+        """E-step with the current parameters that materialises r / ln rho / argmax (:895, :1186)."""
+        K, n = self.K, self.n_local
+        with torch.cuda.device(self.device):
+            self.r_dev = torch.empty((n, K), dtype=torch.float64, device=self.device) if want_r else None
+            self.lnrho_dev = torch.empty((n, K), dtype=torch.float64, device=self.device) if want_lnrho else None
+            self.argmax_dev = torch.empty(n, dtype=torch.int32, device=self.device) if want_argmax else None
+            self._pass(r_out=self.r_dev, lnrho_out=self.lnrho_dev, argmax_out=self.argmax_dev, force=1)
+            self._small(_lib.SMALL_STATS, 0, 0.0)
+            host = self.state.cpu().numpy()
+        return self._stats_from_host(host)

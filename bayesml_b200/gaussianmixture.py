@@ -1,0 +1,485 @@
+"""Drop-in replacement for `bayesml.gaussianmixture.LearnModel` whose variational-Bayes fit runs on a B200.
+
+Same constructor, methods, attribute names, error types and printed progress text as the reference class
+(/root/reference/bayesml/gaussianmixture/_gaussianmixture.py:369-1245, cited per method).  The E-step, the
+sufficient statistics, the Gauss-Wishart/Dirichlet M-step, the ELBO and the convergence test run in
+hand-written sm_100a kernels (libbgmm.so, include/bgmm.h) through `bayesml_b200.engine.VBEngine`; there is no
+CPU fallback for that path.  What stays on the host is K-sized numpy work outside the iteration loop:
+argument checks, hyperparameter plumbing, the RNG-consuming initialisations (so the random stream is the
+reference's), restart bookkeeping and the predictive parameters.
+
+Additive, defaulted options (do not exist in the reference): `device`, `precision` ('float64' | 'float32'),
+`process_group` (torch.distributed group: rows of x are this rank's shard; statistics are all-reduced).
+"""
+import warnings
+
+import numpy as np
+from scipy.special import digamma, gammaln
+from scipy.stats import dirichlet as ss_dirichlet
+from scipy.stats import multivariate_t as ss_multivariate_t
+from scipy.stats import wishart as ss_wishart
+
+from . import _check, base
+from ._exceptions import CriteriaError, DataFormatError, ParameterFormatError, ResultWarning
+
+__all__ = ["LearnModel"]
+
+_HN_NAMES = ("hn_alpha_vec", "hn_m_vecs", "hn_kappas", "hn_nus", "hn_w_mats", "hn_w_mats_inv")
+_VL_NAMES = ("_vl_p_x", "_vl_p_z", "_vl_p_pi", "_vl_p_mu_lambda", "_vl_q_z", "_vl_q_pi", "_vl_q_mu_lambda", "vl")
+
+
+class _LazyDeviceArray:
+    """(N, K) result that stays on the GPU until the attribute is read (r_vecs / _ln_rho can be GBs)."""
+
+    def __init__(self):
+        self.host = None
+        self.dev = None
+
+    def set_device(self, tensor):
+        self.dev, self.host = tensor, None
+
+    def set_host(self, value):
+        self.dev, self.host = None, value
+
+    def get(self):
+        if self.host is None and self.dev is not None:
+            self.host = self.dev.cpu().numpy()
+            self.dev = None
+        return self.host
+
+
+class LearnModel(base.Posterior, base.PredictiveMixin):
+    """Posterior and predictive distribution of the Bayesian Gaussian mixture (reference :369-420).
+
+    Parameters
+    ----------
+    c_num_classes, c_degree : int
+        number of mixture components K and data dimension D (positive)
+    h0_alpha_vec, h0_m_vecs, h0_kappas, h0_nus, h0_w_mats : optional
+        Dirichlet / Gauss-Wishart prior hyperparameters; defaults 1/2, 0, 1, D, I
+    seed : {None, int}
+        seed of `numpy.random.default_rng` used by the initialisations
+    device, precision, process_group : optional (extensions, see module docstring)
+    """
+
+    def __init__(self, c_num_classes, c_degree, h0_alpha_vec=None, h0_m_vecs=None, h0_kappas=None, h0_nus=None,
+                 h0_w_mats=None, seed=None, *, device=None, precision="float64", process_group=None):
+        self.c_degree = _check.pos_int(c_degree, 'c_degree', ParameterFormatError)
+        self.c_num_classes = _check.pos_int(c_num_classes, 'c_num_classes', ParameterFormatError)
+        self.rng = np.random.default_rng(seed)
+        K, D = self.c_num_classes, self.c_degree
+        self._device, self._precision, self._group = device, precision, process_group
+        self._engine_obj = None
+
+        # prior hyperparameters and their constants (:438-446)
+        self.h0_alpha_vec = np.full(K, 0.5)
+        self.h0_m_vecs = np.zeros((K, D))
+        self.h0_kappas = np.ones(K)
+        self.h0_nus = np.full(K, float(D))
+        self.h0_w_mats = np.tile(np.eye(D), (K, 1, 1))
+        self.h0_w_mats_inv = np.linalg.inv(self.h0_w_mats)
+        self._ln_c_h0_alpha = 0.0
+        self._ln_b_h0_w_nus = np.empty(K)
+
+        # posterior hyperparameters and expectations under q (:449-461)
+        self.hn_alpha_vec = np.empty(K)
+        self.hn_m_vecs = np.empty((K, D))
+        self.hn_kappas = np.empty(K)
+        self.hn_nus = np.empty(K)
+        self.hn_w_mats = np.empty((K, D, D))
+        self.hn_w_mats_inv = np.empty((K, D, D))
+        self._lazy_ln_rho = _LazyDeviceArray()
+        self._lazy_r = _LazyDeviceArray()
+        self._e_lambda_mats = np.empty((K, D, D))
+        self._e_ln_lambda_dets = np.empty(K)
+        self._ln_b_hn_w_nus = np.empty(K)
+        self._e_ln_pi_vec = np.empty(K)
+
+        # sufficient statistics (:464-466) and ELBO terms (:469-476)
+        self.x_bar_vecs = np.empty((K, D))
+        self.ns = np.empty(K)
+        self.s_mats = np.empty((K, D, D))
+        for name in _VL_NAMES:
+            setattr(self, name, 0.0)
+
+        # predictive parameters (:479-482)
+        self.p_pi_vec = np.empty(K)
+        self.p_mu_vecs = np.empty((K, D))
+        self.p_nus = np.empty(K)
+        self.p_lambda_mats = np.empty((K, D, D))
+
+        self.set_h0_params(h0_alpha_vec, h0_m_vecs, h0_kappas, h0_nus, h0_w_mats)
+
+    # ------------------------------------------------------------------ big (N, K) attributes, fetched lazily
+    @property
+    def r_vecs(self):
+        return self._lazy_r.get()
+
+    @r_vecs.setter
+    def r_vecs(self, value):
+        self._lazy_r.set_host(value)
+
+    @property
+    def _ln_rho(self):
+        return self._lazy_ln_rho.get()
+
+    @_ln_rho.setter
+    def _ln_rho(self, value):
+        self._lazy_ln_rho.set_host(value)
+
+    # ------------------------------------------------------------------ constants / hyperparameter plumbing
+    def get_constants(self):
+        """{"c_num_classes", "c_degree"} (:492-501)."""
+        return {"c_num_classes": self.c_num_classes, "c_degree": self.c_degree}
+
+    def _store_hyper(self, prefix, alpha_vec, m_vecs, kappas, nus, w_mats):
+        """Validate and copy one family (h0 / hn) of hyperparameters in place (:526-557, :604-635)."""
+        D = self.c_degree
+        if alpha_vec is not None:
+            _check.pos_floats(alpha_vec, prefix + '_alpha_vec', ParameterFormatError)
+            getattr(self, prefix + '_alpha_vec')[:] = alpha_vec
+        if m_vecs is not None:
+            _check.float_vecs(m_vecs, prefix + '_m_vecs', ParameterFormatError)
+            if m_vecs.shape[-1] != D:
+                raise ParameterFormatError(
+                    f"{prefix}_m_vecs.shape[-1] must coincide with self.c_degree: "
+                    f"{prefix}_m_vecs.shape[-1] = {m_vecs.shape[-1]}, self.c_degree = {D}")
+            getattr(self, prefix + '_m_vecs')[:] = m_vecs
+        if kappas is not None:
+            _check.pos_floats(kappas, prefix + '_kappas', ParameterFormatError)
+            getattr(self, prefix + '_kappas')[:] = kappas
+        if nus is not None:
+            _check.pos_floats(nus, prefix + '_nus', ParameterFormatError)
+            if np.any(nus <= D - 1):
+                raise ParameterFormatError(
+                    f"All the values of {prefix}_nus must be greater than self.c_degree - 1: "
+                    f"self.c_degree = {D}, {prefix}_nus = {nus}")
+            getattr(self, prefix + '_nus')[:] = nus
+        if w_mats is not None:
+            _check.pos_def_sym_mats(w_mats, prefix + '_w_mats', ParameterFormatError)
+            if w_mats.shape[-1] != D:
+                raise ParameterFormatError(
+                    f"{prefix}_w_mats.shape[-1] and {prefix}_w_mats.shape[-2] must coincide with self.c_degree: "
+                    f"{prefix}_w_mats.shape[-1] and {prefix}_w_mats.shape[-2] = {w_mats.shape[-1]}, self.c_degree = {D}")
+            w = getattr(self, prefix + '_w_mats')
+            w[:] = w_mats
+            getattr(self, prefix + '_w_mats_inv')[:] = np.linalg.inv(w)
+
+    def set_h0_params(self, h0_alpha_vec=None, h0_m_vecs=None, h0_kappas=None, h0_nus=None, h0_w_mats=None):
+        """Set the prior hyperparameters, then reset hn_* to them (:503-561)."""
+        self._store_hyper('h0', h0_alpha_vec, h0_m_vecs, h0_kappas, h0_nus, h0_w_mats)
+        self._calc_prior_features()
+        self.reset_hn_params()
+        return self
+
+    def get_h0_params(self):
+        """Live references to h0_* (:563-579)."""
+        return {"h0_alpha_vec": self.h0_alpha_vec, "h0_m_vecs": self.h0_m_vecs, "h0_kappas": self.h0_kappas,
+                "h0_nus": self.h0_nus, "h0_w_mats": self.h0_w_mats}
+
+    def set_hn_params(self, hn_alpha_vec=None, hn_m_vecs=None, hn_kappas=None, hn_nus=None, hn_w_mats=None):
+        """Set the posterior hyperparameters, refresh E_q features and the predictive parameters (:581-641)."""
+        self._store_hyper('hn', hn_alpha_vec, hn_m_vecs, hn_kappas, hn_nus, hn_w_mats)
+        self._calc_q_pi_features()
+        self._calc_q_lambda_features()
+        self.calc_pred_dist()
+        return self
+
+    def get_hn_params(self):
+        """Live references to hn_* (:643-659)."""
+        return {"hn_alpha_vec": self.hn_alpha_vec, "hn_m_vecs": self.hn_m_vecs, "hn_kappas": self.hn_kappas,
+                "hn_nus": self.hn_nus, "hn_w_mats": self.hn_w_mats}
+
+    # ------------------------------------------------------------------ K-sized host features (outside the loop)
+    def _ln_b(self, nus, logdet_w_inv):
+        """ln B(W, nu) of the Wishart normaliser given ln|W^-1| (:663-669, :750-756)."""
+        D = self.c_degree
+        return (nus * logdet_w_inv - nus * D * np.log(2.0) - D * (D - 1) / 2.0 * np.log(np.pi)
+                - 2.0 * gammaln((nus[:, None] - np.arange(D)) / 2.0).sum(axis=1)) / 2.0
+
+    def _calc_prior_features(self):
+        """(:661-669)"""
+        self._ln_c_h0_alpha = gammaln(self.h0_alpha_vec.sum()) - gammaln(self.h0_alpha_vec).sum()
+        self._ln_b_h0_w_nus = self._ln_b(self.h0_nus, -np.linalg.slogdet(self.h0_w_mats)[1])
+
+    def _calc_q_pi_features(self):
+        """(:738-739)"""
+        self._e_ln_pi_vec[:] = digamma(self.hn_alpha_vec) - digamma(self.hn_alpha_vec.sum())
+
+    def _calc_q_lambda_features(self):
+        """(:745-756)"""
+        D = self.c_degree
+        logdet = np.linalg.slogdet(self.hn_w_mats_inv)[1]
+        self._e_lambda_mats[:] = self.hn_nus[:, None, None] * self.hn_w_mats
+        self._e_ln_lambda_dets[:] = (digamma((self.hn_nus[:, None] - np.arange(D)) / 2.0).sum(axis=1)
+                                     + D * np.log(2.0) - logdet)
+        self._ln_b_hn_w_nus[:] = self._ln_b(self.hn_nus, logdet)
+
+    # ------------------------------------------------------------------ device plumbing
+    def _engine(self):
+        if self._engine_obj is None:
+            from .engine import VBEngine
+            self._engine_obj = VBEngine(self.c_num_classes, self.c_degree, device=self._device,
+                                        precision=self._precision, group=self._group)
+        return self._engine_obj
+
+    def _check_x(self, x):
+        _check.float_vecs(x, 'x', DataFormatError)
+        if x.shape[-1] != self.c_degree:
+            raise DataFormatError(
+                "x.shape[-1] must be self.c_degree: "
+                f"x.shape[-1]={x.shape[-1]}, self.c_degree={self.c_degree}")
+        return x.reshape(-1, self.c_degree)
+
+    def _push_prior(self, eng):
+        eng.set_prior(self.h0_alpha_vec, self.h0_m_vecs, self.h0_kappas, self.h0_nus, self.h0_w_mats_inv,
+                      self._ln_b_h0_w_nus, self._ln_c_h0_alpha)
+
+    def _push_hn(self, eng):
+        eng.set_params(self.hn_alpha_vec, self.hn_m_vecs, self.hn_kappas, self.hn_nus, self.hn_w_mats_inv)
+
+    def _pull_state(self, eng):
+        """Device parameter set / statistics / ELBO terms -> the numpy attributes, in place."""
+        p = eng.fetch_params()
+        self.hn_alpha_vec[:] = p["alpha"]
+        self.hn_m_vecs[:] = p["m"]
+        self.hn_kappas[:] = p["kappa"]
+        self.hn_nus[:] = p["nu"]
+        self.hn_w_mats[:] = p["w"]
+        self.hn_w_mats_inv[:] = p["winv"]
+        self._e_ln_pi_vec[:] = p["e_ln_pi"]
+        self._e_ln_lambda_dets[:] = p["e_ln_lambda_dets"]
+        self._ln_b_hn_w_nus[:] = p["ln_b"]
+        self._e_lambda_mats[:] = self.hn_nus[:, None, None] * self.hn_w_mats
+        self._pull_stats(p)
+        for name, val in zip(_VL_NAMES, p["vl_terms"]):
+            setattr(self, name, np.float64(val))
+
+    def _pull_stats(self, s):
+        self.ns[:] = s["ns"]
+        self.x_bar_vecs[:] = s["x_bar"]
+        self.s_mats[:] = s["s_mats"]
+
+    # ------------------------------------------------------------------ initialisations (host: they consume self.rng)
+    def _init_subsampling(self, x):
+        """Class-wise sqrt(N)-row subsamples give the initial m_k and W_k (:786-796).  Host numpy so that the random
+        stream is the reference's (`Generator.choice` over the rows, Floyd sampling, no shuffle)."""
+        n_sub = int(np.sqrt(x.shape[0]))
+        eye_eps = np.eye(self.c_degree) * 1.0E-5
+        for k in range(self.c_num_classes):
+            rows = self.rng.choice(x.shape[0], size=n_sub, replace=False, shuffle=False)
+            sub = x[rows]
+            self.hn_m_vecs[k] = sub.sum(axis=0) / n_sub
+            centred = sub - self.hn_m_vecs[k]
+            self.hn_w_mats_inv[k] = centred.T @ centred / n_sub * self.hn_nus[k] + eye_eps
+            self.hn_w_mats[k] = np.linalg.inv(self.hn_w_mats_inv[k])
+        self._calc_q_lambda_features()
+
+    def _init_random_responsibility(self, n):
+        """Dirichlet(1) responsibilities per row (:734-735); the statistics are computed on the device."""
+        return self.rng.dirichlet(np.ones(self.c_num_classes), n)
+
+    # ------------------------------------------------------------------ the fit (:802-896)
+    def update_posterior(self, x, max_itr=100, num_init=10, tolerance=1.0E-8, init_type='subsampling'):
+        """Update the posterior hyperparameters by variational Bayes with `num_init` restarts (:802-896).
+
+        Parameters
+        ----------
+        x : numpy.ndarray, shape (..., c_degree)
+        max_itr : int, maximum number of VB iterations per restart (default 100)
+        num_init : int, number of restarts (default 10)
+        tolerance : float, relative ELBO change that stops a restart (default 1e-8)
+        init_type : 'subsampling' | 'random_responsibility'
+        """
+        x = self._check_x(x)
+        eng = self._engine()
+        eng.load_data(x)
+        self._push_prior(eng)
+        self._lazy_r.set_host(None)
+        self._lazy_ln_rho.set_host(None)
+
+        best_vl = 0.0
+        best = {name: np.array(getattr(self, name)) for name in _HN_NAMES}      # :838-844
+        never_converged = True
+        for i in range(num_init):
+            self.reset_hn_params()
+            r_init = None
+            if init_type == 'subsampling':
+                self._init_subsampling(x)
+            elif init_type == 'random_responsibility':
+                r_init = self._init_random_responsibility(x.shape[0])
+            else:
+                raise ValueError(
+                    f'init_type={init_type} is unsupported. '
+                    + 'This function supports only '
+                    + '"subsampling" and "random_responsibility"')
+            self._push_hn(eng)
+            hist, converged = eng.run(max_itr, tolerance, r_init=r_init)
+            # same progress text as :861, :868, :871
+            print(f'\r{i}. VL: {hist[0]}', end='')
+            for t in range(len(hist) - 1):
+                print(f'\r{i}. VL: {hist[t + 1]} t={t} ', end='')
+            if converged:
+                never_converged = False
+                print('(converged)', end='')
+            self._pull_state(eng)
+            if i == 0 or self.vl > best_vl:                                      # :873 (strict: ties keep the earlier)
+                print('*')
+                best_vl = self.vl
+                for name in _HN_NAMES:
+                    best[name][:] = getattr(self, name)
+            else:
+                print('')
+        if never_converged:
+            warnings.warn("Algorithm has not converged even once.", ResultWarning)
+
+        for name in _HN_NAMES:                                                    # :887-892
+            getattr(self, name)[:] = best[name]
+        self._calc_q_pi_features()
+        self._calc_q_lambda_features()
+        self._final_e_step(eng)                                                   # :895
+        return self
+
+    def _final_e_step(self, eng):
+        """E-step with the current hn_* that materialises r_vecs / _ln_rho and refreshes ns, x_bar_vecs, s_mats."""
+        self._push_hn(eng)
+        self._pull_stats(eng.final_pass(want_r=True, want_lnrho=True, want_argmax=True))
+        self._lazy_r.set_device(eng.r_dev)
+        self._lazy_ln_rho.set_device(eng.lnrho_dev)
+
+    # ------------------------------------------------------------------ estimates (:898-961)
+    def estimate_params(self, loss="squared"):
+        """Point estimates (or the posterior itself for loss="KL") of pi, mu, Lambda (:898-961)."""
+        K, D = self.c_num_classes, self.c_degree
+        if loss == "squared":
+            return self.hn_alpha_vec / self.hn_alpha_vec.sum(), self.hn_m_vecs, self._e_lambda_mats
+        if loss == "0-1":
+            pi_hat = np.empty(K)
+            if np.all(self.hn_alpha_vec > 1):
+                pi_hat[:] = (self.hn_alpha_vec - 1) / (np.sum(self.hn_alpha_vec) - D)
+            else:
+                warnings.warn("MAP estimate of pi_vec doesn't exist for the current hn_alpha_vec.", ResultWarning)
+                pi_hat[:] = np.nan
+            lambda_hat = np.empty((K, D, D))
+            for k in range(K):
+                if self.hn_nus[k] >= D + 1:
+                    lambda_hat[k] = (self.hn_nus[k] - D - 1) * self.hn_w_mats[k]
+                else:
+                    warnings.warn(f"MAP estimate of lambda_mat doesn't exist for the current hn_nus[{k}].", ResultWarning)
+                    lambda_hat[k] = np.nan
+            return pi_hat, self.hn_m_vecs, lambda_hat
+        if loss == "KL":
+            dof = self.hn_nus - D + 1
+            mu_pdfs = [ss_multivariate_t(loc=self.hn_m_vecs[k],
+                                         shape=self.hn_w_mats_inv[k] / self.hn_kappas[k] / dof[k], df=dof[k])
+                       for k in range(K)]
+            lambda_pdfs = [ss_wishart(df=self.hn_nus[k], scale=self.hn_w_mats[k]) for k in range(K)]
+            return ss_dirichlet(self.hn_alpha_vec), mu_pdfs, lambda_pdfs
+        raise CriteriaError(f"loss={loss} is unsupported. "
+                            + "This function supports \"squared\", \"0-1\", and \"KL\".")
+
+    def visualize_posterior(self):
+        """Print the posterior hyperparameters and plot q(mu), q(Lambda) for D <= 2 (:963-1050); needs matplotlib."""
+        for title, val in (("hn_alpha_vec:", self.hn_alpha_vec),
+                           ("E[pi_vec]:", self.hn_alpha_vec / self.hn_alpha_vec.sum()),
+                           ("hn_m_vecs:", self.hn_m_vecs), ("hn_kappas:", self.hn_kappas), ("hn_nus:", self.hn_nus),
+                           ("hn_w_mats:", self.hn_w_mats), ("E[lambda_mats]=", self._e_lambda_mats)):
+            print(title)
+            print(f"{val}")
+        if self.c_degree > 2:
+            raise ParameterFormatError("if c_degree > 2, it is impossible to visualize the model by this function.")
+        import matplotlib.pyplot as plt
+        _, mu_pdfs, lambda_pdfs = self.estimate_params(loss="KL")
+        K = self.c_num_classes
+        sd = np.sqrt(np.stack([np.diag(self.hn_w_mats_inv[k] / self.hn_kappas[k] / self.hn_nus[k]) for k in range(K)]))
+        if self.c_degree == 1:
+            fig, axes = plt.subplots(1, 2)
+            axes[0].set_xlabel("mu_vecs"); axes[0].set_ylabel("Density")
+            axes[1].set_xlabel("lambda_mats"); axes[1].set_ylabel("Log density")
+            for k in range(K):
+                grid = np.linspace(self.hn_m_vecs[k, 0] - 4.0 * sd[k, 0], self.hn_m_vecs[k, 0] + 4.0 * sd[k, 0], 100)
+                axes[0].plot(grid, mu_pdfs[k].pdf(grid))
+                mean_l = self.hn_nus[k] * self.hn_w_mats[k]
+                half = 4.0 * np.sqrt(self.hn_nus[k] / 2.0) * (2.0 * self.hn_w_mats[k])
+                grid = np.linspace(max(1.0e-8, mean_l - half), mean_l + half, 500)
+                axes[1].plot(grid[:, 0, 0], lambda_pdfs[k].logpdf(grid[:, 0, 0]))
+            fig.tight_layout()
+        else:
+            fig, axes = plt.subplots()
+            weights = self.hn_alpha_vec / self.hn_alpha_vec.sum()
+            for k in range(K):
+                gx = np.linspace(self.hn_m_vecs[k, 0] - 3.0 * sd[k, 0], self.hn_m_vecs[k, 0] + 3.0 * sd[k, 0], 100)
+                gy = np.linspace(self.hn_m_vecs[k, 1] - 3.0 * sd[k, 1], self.hn_m_vecs[k, 1] + 3.0 * sd[k, 1], 100)
+                xx, yy = np.meshgrid(gx, gy)
+                axes.contour(xx, yy, mu_pdfs[k].pdf(np.stack([xx, yy], axis=-1)), cmap='Blues', alpha=weights[k])
+                axes.plot(self.hn_m_vecs[k, 0], self.hn_m_vecs[k, 1], marker="x", color='red')
+            axes.set_xlabel("mu_vec[0]"); axes.set_ylabel("mu_vec[1]")
+        plt.show()
+
+    # ------------------------------------------------------------------ predictive (:1052-1155)
+    def get_p_params(self):
+        """Live references to p_mu_vecs, p_nus, p_lambda_mats (:1052-1062)."""
+        return {"p_mu_vecs": self.p_mu_vecs, "p_nus": self.p_nus, "p_lambda_mats": self.p_lambda_mats}
+
+    def calc_pred_dist(self):
+        """Mixture-of-Student-t predictive parameters from hn_* (:1064-1070)."""
+        self.p_pi_vec[:] = self.hn_alpha_vec / self.hn_alpha_vec.sum()
+        self.p_mu_vecs[:] = self.hn_m_vecs
+        self.p_nus[:] = self.hn_nus - self.c_degree + 1
+        scale = self.hn_kappas * self.p_nus / (self.hn_kappas + 1)
+        self.p_lambda_mats[:] = scale[:, None, None] * self.hn_w_mats
+        return self
+
+    def make_prediction(self, loss="squared"):
+        """Predict a new data point: mixture mean ("squared") or the highest weighted mode ("0-1") (:1072-1102)."""
+        if loss == "squared":
+            return np.sum(self.p_pi_vec[:, None] * self.p_mu_vecs, axis=0)
+        if loss == "0-1":
+            best_val, best_mu = -1.0, np.empty(self.c_degree)
+            for k in range(self.c_num_classes):
+                dens = ss_multivariate_t.pdf(x=self.p_mu_vecs[k], loc=self.p_mu_vecs[k],
+                                             shape=np.linalg.inv(self.p_lambda_mats[k]), df=self.p_nus[k])
+                if dens * self.p_pi_vec[k] > best_val:
+                    best_mu[:] = self.p_mu_vecs[k]
+                    best_val = dens * self.p_pi_vec[k]
+            return best_mu
+        raise CriteriaError(f"loss={loss} is unsupported. "
+                            + "This function supports \"squared\" and \"0-1\".")
+
+    def pred_and_update(self, x, loss="squared", max_itr=100, num_init=10, tolerance=1.0E-8,
+                        init_type='random_responsibility'):
+        """Predict one data point, then make the current posterior the prior and learn from x (:1104-1155)."""
+        _check.float_vec(x, 'x', DataFormatError)
+        if x.shape != (self.c_degree,):
+            raise DataFormatError(f"x must be a 1-dimensional float array whose size is c_degree: {self.c_degree}.")
+        self.calc_pred_dist()
+        prediction = self.make_prediction(loss=loss)
+        self.overwrite_h0_params()
+        self.update_posterior(x[np.newaxis, :], max_itr=max_itr, num_init=num_init, tolerance=tolerance,
+                              init_type=init_type)
+        return prediction
+
+    # ------------------------------------------------------------------ latent variables (:1157-1245)
+    def estimate_latent_vars(self, x, loss="0-1"):
+        """Responsibilities ("squared"/"KL") or one-hot MAP assignments ("0-1") of each row of x (:1157-1196).
+
+        As in the reference, this also overwrites ns / x_bar_vecs / s_mats with the statistics of x."""
+        x = self._check_x(x)
+        eng = self._engine()
+        eng.load_data(x)
+        self._push_prior(eng)
+        self._final_e_step(eng)
+        if loss in ("squared", "KL"):
+            return self.r_vecs
+        if loss == "0-1":
+            return np.eye(self.c_num_classes, dtype=int)[eng.argmax_dev.cpu().numpy()]
+        raise CriteriaError(f"loss={loss} is unsupported. "
+                            + "This function supports \"squared\", \"0-1\", and \"KL\".")
+
+    def estimate_latent_vars_and_update(self, x, loss="0-1", max_itr=100, num_init=10, tolerance=1.0E-8,
+                                        init_type='subsampling'):
+        """estimate_latent_vars, then make the current posterior the prior and learn from x (:1198-1245)."""
+        z_hat = self.estimate_latent_vars(x, loss=loss)
+        self.overwrite_h0_params()
+        self.update_posterior(x, max_itr=max_itr, num_init=num_init, tolerance=tolerance, init_type=init_type)
+        return z_hat

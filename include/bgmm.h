@@ -1,0 +1,158 @@
+/*
+ * bgmm.h — C ABI of the B200-native variational-Bayes Gaussian-mixture hot path.
+ *
+ * The reference (bayesml/BayesML, pure Python/numpy) has NO FFI / plugin interface: the boundary it exposes
+ * is the Python class `bayesml.gaussianmixture.LearnModel`.  This header declares the device entry points
+ * that the drop-in Python class (`bayesml_b200.gaussianmixture.LearnModel`) binds with ctypes; each entry
+ * point cites the reference method it replaces (all paths: bayesml/gaussianmixture/_gaussianmixture.py).
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.  All pointers are DEVICE pointers unless
+ *     the name ends in `_host`.  The library allocates nothing and frees nothing: the caller owns every
+ *     buffer (sizes from bgmm_layout / bgmm_workspace_doubles) and passes the cudaStream_t to launch on.
+ *   - every call is asynchronous on `stream` and returns 0 on success, a negative BGMM_E* code otherwise;
+ *     bgmm_last_error() returns a thread-local message.
+ *   - numbers: the model state is float64.  X is float64 (dtype BGMM_F64) or float32 (BGMM_F32, "fp32 mode").
+ *   - coordinates: X is CENTRED once on upload (x' = x - c, c = global column mean) and every m-vector in the
+ *     device state is expressed in the centred frame; the model is shift-covariant, the host adds c back.
+ *
+ * Feature-map formulation.  With P = 1 + D + D(D+1)/2 and
+ *     phi(x') = [ 1, x'_0..x'_{D-1}, x'_i x'_j (i >= j, packed lower-triangular: idx = i(i+1)/2 + j) ]
+ *   E-step   ln rho_nk = coef_k . phi(x'_n)                      (replaces _update_q_z :772-783)
+ *   M-stats  raw_k     = sum_n r_nk phi(x'_n)                    (replaces _calc_n_x_bar_s :725-732)
+ * so both are GEMMs against the same phi tile.  Rows of coef / raw have pitch PITCH = round_up(P, 8).
+ */
+#ifndef BGMM_H_
+#define BGMM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BGMM_ABI_VERSION 1
+
+/* dtype of X */
+#define BGMM_F64 0
+#define BGMM_F32 1
+
+/* error codes */
+#define BGMM_OK 0
+#define BGMM_EINVAL (-1)   /* bad argument (shape, NULL pointer, unsupported size) */
+#define BGMM_ECUDA (-2)    /* CUDA runtime error; see bgmm_last_error() */
+#define BGMM_ENOSUP (-3)   /* shape not supported by the requested kernel variant */
+
+/* pass variants (bgmm_pass `variant`) */
+#define BGMM_PASS_AUTO 0   /* pick the fastest kernel that supports (K, D, dtype) */
+#define BGMM_PASS_SIMPLE 1 /* generic scalar-FMA kernel: any K, D */
+#define BGMM_PASS_DMMA 2   /* fp64 tensor-pipe kernel (mma.sync.m8n8k4.f64): K*PITCH accumulators on chip */
+
+/* bgmm_small `mode` */
+#define BGMM_SMALL_FEATURES 0 /* features + coef of params[cur] from (alpha, m, kappa, nu, W^-1); no statistics used */
+#define BGMM_SMALL_ITERATE 1  /* ELBO of (params[cur], stats); convergence test; M-step into params[1-cur]; flip */
+#define BGMM_SMALL_STATS 2    /* only ns / x_bar / s_mats from STATS (after the final pass, :895)                 */
+
+/* indices into the offsets table written by bgmm_layout (units: doubles from the start of the state block,
+ * except BGMM_OFF_CTRL which is also in doubles but addresses an int32[16] region) */
+enum {
+    BGMM_OFF_CENTER = 0,     /* c[D]                    global centre subtracted from X                      */
+    BGMM_OFF_ALPHA0,         /* h0_alpha_vec[K]                                                              */
+    BGMM_OFF_KAPPA0,         /* h0_kappas[K]                                                                 */
+    BGMM_OFF_NU0,            /* h0_nus[K]                                                                    */
+    BGMM_OFF_M0,             /* h0_m_vecs[K][D]  (centred)                                                   */
+    BGMM_OFF_W0INV,          /* h0_w_mats_inv[K][D][D]                                                       */
+    BGMM_OFF_LNB0,           /* _ln_b_h0_w_nus[K]                                                            */
+    BGMM_OFF_LNC0,           /* _ln_c_h0_alpha[1] (+pad)                                                     */
+    BGMM_OFF_PARAMS0,        /* parameter set 0 (see BGMM_P_* below)                                         */
+    BGMM_OFF_PARAMS1,        /* parameter set 1 (ping-pong)                                                  */
+    BGMM_OFF_STATS,          /* raw[K][PITCH] then tail[8]: tail[0] = sum_n sum_k r ln r, tail[1] = rows     */
+    BGMM_OFF_NS,             /* ns[K]                                                                        */
+    BGMM_OFF_XBAR,           /* x_bar_vecs[K][D] (centred)                                                   */
+    BGMM_OFF_SMATS,          /* s_mats[K][D][D]                                                              */
+    BGMM_OFF_VLK,            /* per-component ELBO partials [K][8]                                           */
+    BGMM_OFF_VLTERMS,        /* [8]: p_x, p_z, p_pi, p_mu_lambda, q_z, q_pi, q_mu_lambda, vl                 */
+    BGMM_OFF_VLHIST,         /* vl history [hist_len]                                                        */
+    BGMM_OFF_CTRL,           /* int32[16]: see BGMM_CTRL_*                                                   */
+    BGMM_OFF_TOTAL,          /* total size of the state block in doubles                                     */
+    BGMM_OFF_STATS_LEN,      /* K*PITCH + 8: length (doubles) of the all-reduced statistics buffer           */
+    BGMM_OFF_PARAMS_LEN,     /* length of one parameter set                                                  */
+    BGMM_OFF_PITCH,          /* PITCH                                                                        */
+    BGMM_N_OFFSETS
+};
+
+/* sub-offsets inside one parameter set (written by bgmm_layout into `param_offsets`) */
+enum {
+    BGMM_P_ALPHA = 0,  /* hn_alpha_vec[K]        */
+    BGMM_P_KAPPA,      /* hn_kappas[K]           */
+    BGMM_P_NU,         /* hn_nus[K]              */
+    BGMM_P_M,          /* hn_m_vecs[K][D] (centred) */
+    BGMM_P_WINV,       /* hn_w_mats_inv[K][D][D] */
+    BGMM_P_W,          /* hn_w_mats[K][D][D]     */
+    BGMM_P_ELNPI,      /* _e_ln_pi_vec[K]        */
+    BGMM_P_ELNDET,     /* _e_ln_lambda_dets[K]   */
+    BGMM_P_LNB,        /* _ln_b_hn_w_nus[K]      */
+    BGMM_P_COEF,       /* coef[K][PITCH]  E-step coefficient rows */
+    BGMM_N_PARAM_OFFSETS
+};
+
+/* control words (int32) */
+enum {
+    BGMM_CTRL_CUR = 0,    /* which parameter set is current (0/1)                                   */
+    BGMM_CTRL_ITER,       /* number of ELBO evaluations so far (0 = none; 1 = post-init value done) */
+    BGMM_CTRL_DONE,       /* 1 -> bgmm_pass / bgmm_small(ITERATE) return immediately (no-ops)       */
+    BGMM_CTRL_CONVERGED,  /* 1 -> the tolerance test fired (:869)                                   */
+    BGMM_CTRL_TICKET,     /* internal: last-CTA election for bgmm_small                             */
+    BGMM_CTRL_PASS_TICKET,/* internal: last-CTA election for bgmm_pass                              */
+    BGMM_CTRL_ERROR,      /* 1 -> a W^-1 was not positive definite (Cholesky failed)                */
+    BGMM_N_CTRL = 16
+};
+
+int bgmm_abi_version(void);
+const char* bgmm_last_error(void);
+
+/* Sizes.  offsets[BGMM_N_OFFSETS], param_offsets[BGMM_N_PARAM_OFFSETS] are HOST arrays. */
+int bgmm_layout(int K, int D, int hist_len, int64_t* offsets_host, int64_t* param_offsets_host);
+/* doubles of scratch needed by bgmm_pass for per-CTA partial statistics */
+int64_t bgmm_workspace_doubles(int K, int D);
+
+/* ---- data preparation (no reference counterpart: the reference keeps x on the host) ----
+ * column sums of the local rows (fp64 accumulation, deterministic), to build the global centre c */
+int bgmm_colsum(const void* x_raw, int64_t n, int D, int dtype_in, double* colsum_out /*[D]*/,
+                double* workspace, void* stream);
+/* x'[n][d] = x_raw[n][d] - c[d], written as dtype_out (may alias x_raw when dtypes match) */
+int bgmm_center(const void* x_raw, int dtype_in, void* x_out, int dtype_out, int64_t n, int D,
+                const double* center /*[D]*/, void* stream);
+
+/* ---- the hot path ----
+ * bgmm_pass: one E-step + sufficient-statistics sweep over the local rows of centred X.
+ *   replaces `_update_q_z` (:772-784) incl. `_calc_n_x_bar_s` (:725-732) and the O(N K) term of `_calc_vl` (:704).
+ *   Reads coef from params[ctrl.cur]; writes state.STATS (raw moments about the centre, sum r ln r, rows).
+ *   r_out / lnrho_out ([n][K] float64) and argmax_out ([n] int32, first index on ties — np.argmax, :1191) are
+ *   optional (NULL inside the VB loop: r never touches HBM).
+ *   r_in (optional, [n][K] float64): statistics of GIVEN responsibilities instead of the E-step
+ *   (`_init_random_responsibility` :734-736).  No-op when ctrl.done != 0 unless `force`.
+ *   accumulate != 0: add to state.STATS instead of overwriting (row-chunked uploads). */
+int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, double* state, double* workspace,
+              double* r_out, double* lnrho_out, int32_t* argmax_out, const double* r_in,
+              int variant, int force, int accumulate, void* stream);
+
+/* 1 when `variant` (BGMM_PASS_SIMPLE / BGMM_PASS_DMMA) can run this shape, else 0 */
+int bgmm_pass_supported(int K, int D, int dtype, int variant);
+
+/* bgmm_small: everything that is O(K D^3): replaces `_update_q_mu_lambda` (:758-770), `_update_q_pi` (:741-743),
+ *   `_calc_q_pi_features` (:738-739), `_calc_q_lambda_features` (:745-756), the K-sized terms of `_calc_vl`
+ *   (:671-723) and the convergence test (:869).  One CTA per component; Cholesky-based inverse / log-det.
+ *   mode FEATURES: params[cur] holds (alpha, m, kappa, nu, W^-1) from the host; fills W, features, coef.
+ *   mode ITERATE : vl of (params[cur], STATS) -> vlhist[iter]; if iter >= 1 and |(vl - vl_prev)/vl_prev| < tol
+ *                  -> converged, done; else if iter == max_itr -> done; else M-step into params[1-cur], flip cur.
+ *                  Also refreshes ns / x_bar / s_mats (s_mats[k] untouched when N_k == 0, as at :729).
+ *   mode STATS   : ns / x_bar / s_mats only; parameters and control words untouched. */
+int bgmm_small(int K, int D, double* state, int mode, int max_itr, double tol, int hist_len, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGMM_H_ */
