@@ -60,17 +60,20 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-struct DmmaCfg {
-    int SP;       // shared-memory feature pitch (multiple of 16)
-    int RP;       // shared-memory pitch of the r tile (multiple of 16, >= 8*KB)
-    int nbt;      // SP / 8  n-blocks of the M-GEMM
-};
+constexpr int DM_MAXTQ = 5;         // quadratic features per lane per row: D(D+1)/2 <= 160
 
-template <int KB, int MAXNB>
+__device__ __forceinline__ int fsw(int row) { return ((row & 1) << 3) | ((row & 2) << 1); }
+__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+template <int KB, int SP>
 __global__ void __launch_bounds__(DM_THREADS, 1)
-pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
+pass_dmma_kernel(const PassArgs a, const Layout L) {
+    constexpr int RP = (8 * KB < 16) ? 16 : 8 * KB;          // pitch of the r tile (multiple of 16)
+    constexpr int NBT = SP / 8;                               // n-blocks of the M-GEMM
+    constexpr int MAXNB = ((NBT + 3) / 4 + 1) / 2;            // n-blocks owned by one warp
+    constexpr int EW = SP / 32;                               // E-GEMM: 16-column groups per k half
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int K = L.K, D = L.D, P = L.P, SP = cfg.SP, RP = cfg.RP;
+    const int K = L.K, D = L.D, P = L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
     if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
@@ -85,8 +88,6 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
     double* exch = xS + 2 * DM_TILE * D;                                 // [8 warps][32 lanes][2*KB]
     double* red = exch + DM_WARPS * 32 * 2 * KB;                         // [40]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 40);              // [2]
-    unsigned short* ij = reinterpret_cast<unsigned short*>(bars + 2);    // [SP] packed (i<<8)|j ; 0xFFFF = zero pad,
-                                                                         //   0xFFFE = constant 1, 0xFF00|i = linear x_i
 
     const int64_t ntiles = (a.n + DM_TILE - 1) / DM_TILE;
     const uint32_t tile_bytes = (uint32_t)(DM_TILE * D * sizeof(double));
@@ -108,21 +109,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
         if ((int64_t)blockIdx.x + gridDim.x < ntiles) issue_tile((int64_t)blockIdx.x + gridDim.x, 1);
     }
 
-    // ---- one-time: feature index table and swizzled coefficient matrix ----
-    for (int p = tid; p < SP; p += DM_THREADS) {
-        unsigned short v;
-        if (p >= P) v = 0xFFFF;
-        else if (p == 0) v = 0xFFFE;
-        else if (p <= D) v = (unsigned short)(0xFF00 | (p - 1));
-        else {
-            const int qq = p - 1 - D;
-            int i = (int)((sqrtf(8.0f * qq + 1.0f) - 1.0f) * 0.5f);
-            while (i * (i + 1) / 2 > qq) --i;
-            while ((i + 1) * (i + 2) / 2 <= qq) ++i;
-            v = (unsigned short)((i << 8) | (qq - i * (i + 1) / 2));
-        }
-        ij[p] = v;
-    }
+    // ---- one-time: swizzled coefficient matrix; the tile-invariant columns of Phi (constant 1 and zero padding) ----
     for (int e = tid; e < 8 * KB * SP; e += DM_THREADS) {
         const int k = e / SP, p = e - k * SP;
         double v = 0.0;
@@ -130,6 +117,26 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
         else if (p == 0) v = -1.0e300;                                    // padded components: r == 0 exactly
         coefS[swz(k, phys_col(p), SP)] = v;
     }
+    for (int e = tid; e < DM_TILE * (SP - P + 1); e += DM_THREADS) {
+        const int r = e / (SP - P + 1), c = e - r * (SP - P + 1);
+        if (c == 0) phiS[swz(r, phys_col(0), SP)] = 1.0;
+        else phiS[swz(r, phys_col(P + c - 1), SP)] = 0.0;
+    }
+    // per-lane feature table of the Phi expansion (this lane produces the same features for every row)
+    const int NQ = D * (D + 1) / 2;
+    int qi[DM_MAXTQ], qj[DM_MAXTQ], qc[DM_MAXTQ];
+#pragma unroll
+    for (int t = 0; t < DM_MAXTQ; ++t) {
+        const int qq = lane + 32 * t;
+        qi[t] = 0; qj[t] = 0; qc[t] = -1;
+        if (qq < NQ) {
+            int i = (int)((sqrtf(8.0f * qq + 1.0f) - 1.0f) * 0.5f);
+            while (i * (i + 1) / 2 > qq) --i;
+            while ((i + 1) * (i + 2) / 2 <= qq) ++i;
+            qi[t] = i; qj[t] = qq - i * (i + 1) / 2; qc[t] = phys_col(1 + D + qq);
+        }
+    }
+    const int lc = (lane < D) ? phys_col(1 + lane) : -1;                  // linear feature of this lane
 
     // ---- persistent accumulators of the M-GEMM: this warp owns n-blocks b = (warp%4) + 4*(2*l + warp/4) ----
     double macc[MAXNB][KB][2];
@@ -139,8 +146,23 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
         for (int kb = 0; kb < KB; ++kb) { macc[l][kb][0] = 0.0; macc[l][kb][1] = 0.0; }
     double ent = 0.0;
 
-    const int mp = warp & 3, kh = warp >> 2;            // E-GEMM: m-block pair, k half
-    const int pairs_half = SP / 16;                     // k-step pairs per half (SP/4 k-steps total)
+    // ---- loop-invariant fragment pointers (all swizzles resolved here; the loops below use immediates only) ----
+    const int mp = warp & 3, kh = warp >> 2;                // E-GEMM: m-block pair, k half
+    const int fg = fsw(g), fq = fsw(q);
+    const double* eA = phiS + (16 * mp + g) * SP + kh * (16 * EW);   // rows 16mp+g (+8): same swizzle as row g
+    const double* eB = coefS + g * SP + kh * (16 * EW);
+    const int eo0 = (2 * q) ^ fg, eo1 = (8 + 2 * q) ^ fg;
+    const int lrow = (2 * mp + kh) * 8 + g;                 // the row this thread finalises in the softmax
+    double* rst = rS + lrow * RP + ((4 * q) ^ fg);
+    const double* mR = rS + q * RP + ((2 * g) ^ fq);
+    const double* mP[MAXNB];
+    bool mOn[MAXNB];
+#pragma unroll
+    for (int l = 0; l < MAXNB; ++l) {
+        const int b = (warp & 3) + 4 * (2 * l + (warp >> 2));
+        mOn[l] = b < NBT;
+        mP[l] = phiS + q * SP + ((8 * (mOn[l] ? b : 0) + g) ^ fq);
+    }
     uint32_t phase[2] = {0u, 0u};
     __syncthreads();
 
@@ -158,39 +180,54 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
             __syncthreads();
         }
 
-        // ---- 2. feature tile ----
-        for (int e = tid; e < DM_TILE * SP; e += DM_THREADS) {
-            const int r = e / SP, p = e - r * SP;
-            const unsigned short c = ij[p];
-            const int i = c >> 8, j = c & 0xFF;
-            double v;
-            if (i == 0xFF) v = (j == 0xFF) ? 0.0 : (j == 0xFE ? 1.0 : xt[r * D + j]);
-            else v = xt[r * D + i] * xt[r * D + j];
-            phiS[swz(r, phys_col(p), SP)] = v;
+        // ---- 2. feature tile: warp w expands rows 8w..8w+7; a lane owns the same features in every row ----
+        {
+            const double* xr = xt + (8 * warp) * D;
+            double* pr = phiS + (8 * warp) * SP;
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+                const int f = fsw(rr);                       // 8*warp does not change the low row bits
+                if (lc >= 0) pr[lc ^ f] = xr[lane];
+#pragma unroll
+                for (int tq = 0; tq < DM_MAXTQ; ++tq)
+                    if (qc[tq] >= 0) pr[qc[tq] ^ f] = xr[qi[tq]] * xr[qj[tq]];
+                xr += D;
+                pr += SP;
+            }
         }
         __syncthreads();
         // x tile consumed: refill this stage two tiles ahead
         if (tid == 0 && t + 2 * (int64_t)gridDim.x < ntiles) issue_tile(t + 2 * (int64_t)gridDim.x, stage);
 
-        // ---- 3. E-GEMM: this warp -> m-blocks {2mp, 2mp+1}, k-step pairs [kh*pairs_half, (kh+1)*pairs_half) ----
+        // ---- 3. E-GEMM: this warp -> m-blocks {2mp, 2mp+1}, the k half kh (EW groups of 16 physical columns) ----
         double acc[2][KB][2];
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) { acc[m][kb][0] = 0.0; acc[m][kb][1] = 0.0; }
-        {
-            const int rA0 = (2 * mp) * 8 + g, rA1 = rA0 + 8;
-            for (int u = kh * pairs_half; u < (kh + 1) * pairs_half; ++u) {
-                const int c = 8 * u + 2 * q;
-                const double2 a0 = *reinterpret_cast<const double2*>(&phiS[swz(rA0, c, SP)]);
-                const double2 a1 = *reinterpret_cast<const double2*>(&phiS[swz(rA1, c, SP)]);
+#pragma unroll
+        for (int w = 0; w < EW; ++w) {
+            double2 af[2][2], bf[KB][2];
+            af[0][0] = lds2(eA + 16 * w + eo0);
+            af[0][1] = lds2(eA + 16 * w + eo1);
+            af[1][0] = lds2(eA + 8 * SP + 16 * w + eo0);
+            af[1][1] = lds2(eA + 8 * SP + 16 * w + eo1);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                bf[kb][0] = lds2(eB + kb * 8 * SP + 16 * w + eo0);
+                bf[kb][1] = lds2(eB + kb * 8 * SP + 16 * w + eo1);
+            }
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
-                    const double2 b = *reinterpret_cast<const double2*>(&coefS[swz(8 * kb + g, c, SP)]);
-                    dmma(acc[0][kb][0], acc[0][kb][1], a0.x, b.x);
-                    dmma(acc[1][kb][0], acc[1][kb][1], a1.x, b.x);
-                    dmma(acc[0][kb][0], acc[0][kb][1], a0.y, b.y);
-                    dmma(acc[1][kb][0], acc[1][kb][1], a1.y, b.y);
+                    dmma(acc[0][kb][0], acc[0][kb][1], af[0][par].x, bf[kb][par].x);
+                    dmma(acc[1][kb][0], acc[1][kb][1], af[1][par].x, bf[kb][par].x);
+                }
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    dmma(acc[0][kb][0], acc[0][kb][1], af[0][par].y, bf[kb][par].y);
+                    dmma(acc[1][kb][0], acc[1][kb][1], af[1][par].y, bf[kb][par].y);
                 }
             }
         }
@@ -198,10 +235,9 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
         {
             double* mine = exch + (warp * 32 + lane) * 2 * KB;
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {            // kh is warp-uniform: selects, not dynamic register indexing
-                mine[2 * kb] = kh ? acc[0][kb][0] : acc[1][kb][0];
-                mine[2 * kb + 1] = kh ? acc[0][kb][1] : acc[1][kb][1];
-            }
+            for (int kb = 0; kb < KB; ++kb)                   // kh is warp-uniform: selects, not dynamic register indexing
+                *reinterpret_cast<double2*>(mine + 2 * kb) =
+                    kh ? make_double2(acc[0][kb][0], acc[0][kb][1]) : make_double2(acc[1][kb][0], acc[1][kb][1]);
         }
         __syncthreads();
         double lr[KB][2];
@@ -209,13 +245,13 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
             const double* theirs = exch + (((warp ^ 4) * 32) + lane) * 2 * KB;
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
-                lr[kb][0] = (kh ? acc[1][kb][0] : acc[0][kb][0]) + theirs[2 * kb];
-                lr[kb][1] = (kh ? acc[1][kb][1] : acc[0][kb][1]) + theirs[2 * kb + 1];
+                const double2 o = lds2(theirs + 2 * kb);
+                lr[kb][0] = (kh ? acc[1][kb][0] : acc[0][kb][0]) + o.x;
+                lr[kb][1] = (kh ? acc[1][kb][1] : acc[0][kb][1]) + o.y;
             }
         }
 
-        // ---- 4. softmax over k for row (2mp+kh)*8 + g; this thread holds components 8kb + 2q + {0,1} ----
-        const int lrow = (2 * mp + kh) * 8 + g;
+        // ---- 4. softmax over k for row lrow; this thread holds components 8kb + 2q + {0,1} ----
         const int64_t grow = row0 + lrow;
         const bool valid = lrow < rows;
         double mx = -INFINITY;
@@ -248,19 +284,20 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
         dot += __shfl_xor_sync(0xffffffffu, dot, 1);
         dot += __shfl_xor_sync(0xffffffffu, dot, 2);
         const double inv = valid ? 1.0 / sum : 0.0;     // rows past the end contribute r = 0
-        if (valid && q == 0) ent += dot / sum - log(sum);
-        int best = 0x7fffffff;
-        double bestv = -1.0;
+        if (valid && q == 0) ent += dot * inv - log(sum);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
+        for (int kb = 0; kb < KB; ++kb) { lr[kb][0] *= inv; lr[kb][1] *= inv; }
+        // r tile: physical column 16(kb>>1) + 4q + 2e + (kb&1), swizzle folded into `rst`
+        if constexpr (KB >= 2) {
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double r = lr[kb][e] * inv;
-                lr[kb][e] = r;
-                const int k = 8 * kb + 2 * q + e;
-                if (r > bestv) { bestv = r; best = k; }   // ascending k within the thread: first index wins ties
-                rS[swz(lrow, 16 * (kb >> 1) + 2 * (2 * q + e) + (kb & 1), RP)] = r;
-            }
+            for (int v = 0; v < KB / 2; ++v)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    *reinterpret_cast<double2*>(rst + 16 * v + 2 * e) = make_double2(lr[2 * v][e], lr[2 * v + 1][e]);
+        } else {
+            rst[0] = lr[0][0];
+            rst[2] = lr[0][1];
+        }
         if (a.r_out != nullptr && valid) {
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
@@ -271,6 +308,13 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
                 }
         }
         if (a.argmax_out != nullptr) {
+            int best = 0x7fffffff;
+            double bestv = -1.0;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (lr[kb][e] > bestv) { bestv = lr[kb][e]; best = 8 * kb + 2 * q + e; }   // ascending k: first wins
 #pragma unroll
             for (int o = 1; o <= 2; o <<= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, bestv, o);
@@ -282,27 +326,25 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
         __syncthreads();
 
         // ---- 5. M-GEMM: raw[k][p] += sum_n r[n][k] phi[n][p]; A = R^T (8 comps x 4 samples), B = Phi (4 x 8) ----
-#pragma unroll 2
+#pragma unroll
         for (int ks = 0; ks < DM_TILE / 4; ++ks) {
-            const int rown = 4 * ks + q;
             double ra[KB];
             if constexpr (KB >= 2) {
 #pragma unroll
                 for (int v = 0; v < KB / 2; ++v) {
-                    const double2 r2 = *reinterpret_cast<const double2*>(&rS[swz(rown, 16 * v + 2 * g, RP)]);
+                    const double2 r2 = lds2(mR + ks * 4 * RP + 16 * v);
                     ra[2 * v] = r2.x;
                     ra[2 * v + 1] = r2.y;
                 }
             } else {
-                ra[0] = rS[swz(rown, 2 * g, RP)];
+                ra[0] = mR[ks * 4 * RP];
             }
 #pragma unroll
             for (int l = 0; l < MAXNB; ++l) {
-                const int b = (warp & 3) + 4 * (2 * l + (warp >> 2));
-                if (b < cfg.nbt) {
-                    const double bf = phiS[swz(rown, 8 * b + g, SP)];
+                if (mOn[l]) {
+                    const double bfr = mP[l][ks * 4 * SP];
 #pragma unroll
-                    for (int kb = 0; kb < KB; ++kb) dmma(macc[l][kb][0], macc[l][kb][1], ra[kb], bf);
+                    for (int kb = 0; kb < KB; ++kb) dmma(macc[l][kb][0], macc[l][kb][1], ra[kb], bfr);
                 }
             }
         }
@@ -315,7 +357,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
 #pragma unroll
     for (int l = 0; l < MAXNB; ++l) {
         const int b = (warp & 3) + 4 * (2 * l + (warp >> 2));
-        if (b < cfg.nbt) {
+        if (b < NBT) {
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
@@ -365,24 +407,21 @@ pass_dmma_kernel(const PassArgs a, const Layout L, const DmmaCfg cfg) {
 // ---- host side ----
 struct DmmaPlan {
     bool ok;
-    int KB, MAXNB, SP, RP, nbt;
+    int KB, SP, RP;
     size_t smem;
 };
 
 static DmmaPlan plan_dmma(int K, int D) {
     DmmaPlan p{};
     const int P = feat_count(D);
-    p.SP = (P + 15) & ~15;
+    p.SP = (P + 31) & ~31;
     p.KB = K <= 8 ? 1 : (((K + 15) & ~15) / 8);
-    p.RP = ((8 * p.KB) + 15) & ~15;
-    p.nbt = p.SP / 8;
-    const int slots = (p.nbt + 3) / 4;
-    p.MAXNB = (slots + 1) / 2;
+    p.RP = 8 * p.KB < 16 ? 16 : 8 * p.KB;
     p.smem = sizeof(double) * ((size_t)DM_TILE * p.SP + (size_t)8 * p.KB * p.SP + (size_t)DM_TILE * p.RP +
                                (size_t)2 * DM_TILE * D + (size_t)DM_WARPS * 32 * 2 * p.KB + 40) +
-             2 * sizeof(uint64_t) + sizeof(unsigned short) * p.SP + 128;
-    p.ok = (D <= 254) && (p.KB == 1 || p.KB == 2 || p.KB == 4) && p.MAXNB <= 3 && p.smem <= 227 * 1024 &&
-           (D * sizeof(double) * DM_TILE) % 16 == 0;
+             2 * sizeof(uint64_t) + 128;
+    p.ok = D * (D + 1) / 2 <= 32 * DM_MAXTQ && D <= 32 && (p.KB == 1 || p.KB == 2 || p.KB == 4) && p.SP <= 192 &&
+           p.smem <= 227 * 1024 - 512 && (D * sizeof(double) * DM_TILE) % 16 == 0;
     return p;
 }
 
@@ -390,8 +429,12 @@ bool dmma_supported(int K, int D, int dtype) { return dtype == BGMM_F64 && plan_
 
 static int dmma_grid(int64_t n) {
     const int64_t ntiles = (n + DM_TILE - 1) / DM_TILE;
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
     return (int)(ntiles < 1 ? 1 : (ntiles < sms ? ntiles : sms));
 }
 
@@ -400,13 +443,16 @@ int64_t dmma_workspace_doubles(int K, int D) {
     return (int64_t)160 * ((int64_t)K * feat_pitch(D) + 8);   // >= SM count of any sm_100 part
 }
 
-template <int KB, int MAXNB>
+template <int KB, int SP>
 static int launch_cfg(const PassArgs& a, const Layout& L, const DmmaPlan& p, cudaStream_t stream) {
-    auto kern = pass_dmma_kernel<KB, MAXNB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_dmma)");
-    const DmmaCfg cfg{p.SP, p.RP, p.nbt};
-    kern<<<dmma_grid(a.n), DM_THREADS, p.smem, stream>>>(a, L, cfg);
+    auto kern = pass_dmma_kernel<KB, SP>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_dmma)");
+        configured = true;
+    }
+    kern<<<dmma_grid(a.n), DM_THREADS, p.smem, stream>>>(a, L);
     return check_cuda(cudaGetLastError(), "pass_dmma_kernel launch");
 }
 
@@ -421,12 +467,13 @@ int launch_pass_dmma(const PassArgs& a, int K, int D, int dtype, cudaStream_t st
         return BGMM_EINVAL;
     }
     const Layout L = make_layout(K, D, 1);
-#define BGMM_DM_CASE(kb, nb) if (p.KB == kb && p.MAXNB == nb) return launch_cfg<kb, nb>(a, L, p, stream);
-    BGMM_DM_CASE(1, 1) BGMM_DM_CASE(1, 2) BGMM_DM_CASE(1, 3)
-    BGMM_DM_CASE(2, 1) BGMM_DM_CASE(2, 2) BGMM_DM_CASE(2, 3)
-    BGMM_DM_CASE(4, 1) BGMM_DM_CASE(4, 2) BGMM_DM_CASE(4, 3)
+#define BGMM_DM_CASE(kb, sp) if (p.KB == kb && p.SP == sp) return launch_cfg<kb, sp>(a, L, p, stream);
+#define BGMM_DM_ROW(kb) BGMM_DM_CASE(kb, 32) BGMM_DM_CASE(kb, 64) BGMM_DM_CASE(kb, 96) BGMM_DM_CASE(kb, 128) \
+                        BGMM_DM_CASE(kb, 160) BGMM_DM_CASE(kb, 192)
+    BGMM_DM_ROW(1) BGMM_DM_ROW(2) BGMM_DM_ROW(4)
+#undef BGMM_DM_ROW
 #undef BGMM_DM_CASE
-    set_error("bgmm_pass(dmma): no instantiation for KB=%d MAXNB=%d", p.KB, p.MAXNB);
+    set_error("bgmm_pass(dmma): no instantiation for KB=%d SP=%d", p.KB, p.SP);
     return BGMM_ENOSUP;
 }
 

@@ -260,24 +260,63 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         self.x_bar_vecs[:] = s["x_bar"]
         self.s_mats[:] = s["s_mats"]
 
+    # ------------------------------------------------------------------ row sharding over a process group
+    def _dist_sum(self, arr):
+        """Sum a small numpy array over the process group (device tensor for NCCL, host tensor for gloo)."""
+        import torch
+        import torch.distributed as dist
+        t = torch.as_tensor(np.ascontiguousarray(arr))
+        if dist.get_backend(self._group) == "nccl":
+            dev = self._engine().device
+            t = t.to(dev)
+            dist.all_reduce(t, group=self._group)
+            return t.cpu().numpy()
+        dist.all_reduce(t, group=self._group)
+        return t.numpy()
+
+    def _shard_layout(self, n_local):
+        """(row offset of this rank's shard, global row count): shards are concatenated in rank order."""
+        if self._group is None:
+            return 0, n_local
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(self._group), dist.get_rank(self._group)
+        counts = np.zeros(world, dtype=np.int64)
+        counts[rank] = n_local
+        counts = self._dist_sum(counts)
+        return int(counts[:rank].sum()), int(counts.sum())
+
+    def _take_global_rows(self, x, rows, offset):
+        """Rows `rows` (global indices) of the row-sharded data set; every rank returns the same array."""
+        if self._group is None:
+            return x[rows]
+        mine = (rows >= offset) & (rows < offset + x.shape[0])
+        sub = np.zeros((rows.shape[0], self.c_degree), dtype=np.result_type(x.dtype, np.float32))
+        sub[mine] = x[rows[mine] - offset]
+        return self._dist_sum(sub)       # each row is owned by exactly one rank: the others add exact zeros
+
     # ------------------------------------------------------------------ initialisations (host: they consume self.rng)
-    def _init_subsampling(self, x):
+    def _init_subsampling(self, x, offset=0, n_total=None):
         """Class-wise sqrt(N)-row subsamples give the initial m_k and W_k (:786-796).  Host numpy so that the random
-        stream is the reference's (`Generator.choice` over the rows, Floyd sampling, no shuffle)."""
-        n_sub = int(np.sqrt(x.shape[0]))
+        stream is the reference's (`Generator.choice` over the rows, Floyd sampling, no shuffle).  With a process
+        group the indices are drawn over the GLOBAL rows (same seed on every rank => identical initial state, equal
+        to the single-process run on the concatenated shards)."""
+        n_total = x.shape[0] if n_total is None else n_total
+        n_sub = int(np.sqrt(n_total))
         eye_eps = np.eye(self.c_degree) * 1.0E-5
         for k in range(self.c_num_classes):
-            rows = self.rng.choice(x.shape[0], size=n_sub, replace=False, shuffle=False)
-            sub = x[rows]
+            rows = self.rng.choice(n_total, size=n_sub, replace=False, shuffle=False)
+            sub = self._take_global_rows(x, rows, offset)
             self.hn_m_vecs[k] = sub.sum(axis=0) / n_sub
             centred = sub - self.hn_m_vecs[k]
             self.hn_w_mats_inv[k] = centred.T @ centred / n_sub * self.hn_nus[k] + eye_eps
             self.hn_w_mats[k] = np.linalg.inv(self.hn_w_mats_inv[k])
         self._calc_q_lambda_features()
 
-    def _init_random_responsibility(self, n):
-        """Dirichlet(1) responsibilities per row (:734-735); the statistics are computed on the device."""
-        return self.rng.dirichlet(np.ones(self.c_num_classes), n)
+    def _init_random_responsibility(self, n, offset=0, n_total=None):
+        """Dirichlet(1) responsibilities per row (:734-735); the statistics are computed on the device.  With a
+        process group every rank draws the global stream and keeps the rows of its shard."""
+        n_total = n if n_total is None else n_total
+        return self.rng.dirichlet(np.ones(self.c_num_classes), n_total)[offset:offset + n]
 
     # ------------------------------------------------------------------ the fit (:802-896)
     def update_posterior(self, x, max_itr=100, num_init=10, tolerance=1.0E-8, init_type='subsampling'):
@@ -294,6 +333,7 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         x = self._check_x(x)
         eng = self._engine()
         eng.load_data(x)
+        offset, n_total = self._shard_layout(x.shape[0])
         self._push_prior(eng)
         self._lazy_r.set_host(None)
         self._lazy_ln_rho.set_host(None)
@@ -305,9 +345,9 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
             self.reset_hn_params()
             r_init = None
             if init_type == 'subsampling':
-                self._init_subsampling(x)
+                self._init_subsampling(x, offset, n_total)
             elif init_type == 'random_responsibility':
-                r_init = self._init_random_responsibility(x.shape[0])
+                r_init = self._init_random_responsibility(x.shape[0], offset, n_total)
             else:
                 raise ValueError(
                     f'init_type={init_type} is unsupported. '

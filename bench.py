@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — VB Gaussian-mixture hot path on B200: VB iterations/s as N*K point*components per second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--scaling strong|weak] [--impl reference]
+
+One "step" = one VB iteration of `gaussianmixture.LearnModel.update_posterior` (reference
+_gaussianmixture.py:863-869): M-step + q(pi) update + E-step/statistics pass over all rows + ELBO + convergence
+test.  On the device that is: bgmm_pass (the fused E/statistics sweep) -> [all-reduce of the statistics when
+N > 1] -> bgmm_small (ELBO, convergence flag, M-step).  Workload: BASELINE.json configs[1]
+(N=10M, D=16, K=32, fp64) on synthetic mixture data; X (1.28 GB) is larger than L2 so every
+timed iteration streams it from HBM.
+
+Printed JSON keys follow the driver contract; `value` is whole-job throughput with X resident in HBM, `e2e` is
+the same metric through the public API (`LearnModel.update_posterior`) with a HOST array, uploads/downloads
+inside the timed region.  `--impl reference` times the reference's algorithm (the numpy oracle port — the
+reference is pure Python and cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "VB iters/sec (N*K points*comps/s) GMM"
+UNIT = "point*comps/s"
+
+# name -> (N_total, D, K, precision, config index for the data seed)
+CONFIGS = {
+    "c1": (1000, 2, 3, "float64", 0),
+    "c2": (10_000_000, 16, 32, "float64", 1),
+    "c3": (200_000_000, 2, 8, "float32", 2),
+    "c4": (2_000_000, 128, 64, "float64", 3),
+    "c5": (4_000_000, 32, 16, "float64", 4),
+}
+FP64_PEAK_TFLOPS = 37.0   # measured on this pool's B200 (profiles/r01_peaks_b200.json: DMMA 37.0, DFMA 36.7, cuBLAS DGEMM 35.4)
+
+
+def alg_flops_per_iter(n, d, k):
+    """dense forms the reference executes, E: 2D^2+2D, M: 2D^2+2D+1 per (sample, component)."""
+    return n * k * (4 * d * d + 4 * d + 1)
+
+
+def mixture_params(d, k, seed):
+    rng = np.random.default_rng(seed)
+    mu = rng.normal(0.0, 4.0, size=(k, d))
+    a = rng.normal(size=(k, d, d))
+    chol = np.linalg.cholesky(a @ a.transpose(0, 2, 1) / d + 0.5 * np.eye(d))
+    return mu, chol
+
+
+def synth_host(n, d, k, seed, sample_seed=0):
+    """Seeded mixture sample on the host (numpy) — used by the CPU arms."""
+    mu, chol = mixture_params(d, k, seed)
+    rng = np.random.default_rng([seed, sample_seed])
+    z = rng.integers(0, k, size=n)
+    x = np.empty((n, d))
+    step = 1 << 18
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        x[s:e] = mu[z[s:e]] + np.einsum("nij,nj->ni", chol[z[s:e]], rng.normal(size=(e - s, d)))
+    return x
+
+
+def synth_device(n, d, k, seed, sample_seed, device, dtype):
+    """Same mixture, sampled on the device with torch (plumbing: data generation is not part of the path)."""
+    import torch
+    mu, chol = mixture_params(d, k, seed)
+    mu_t = torch.as_tensor(mu, device=device)
+    chol_t = torch.as_tensor(chol, device=device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed * 1000 + sample_seed)
+    x = torch.empty((n, d), device=device, dtype=dtype)
+    step = 1 << 20
+    for s in range(0, n, step):
+        e = min(n, s + step)
+        z = torch.randint(0, k, (e - s,), generator=g, device=device)
+        eps = torch.randn(e - s, d, generator=g, device=device, dtype=torch.float64)
+        x[s:e] = (mu_t[z] + torch.einsum("nij,nj->ni", chol_t[z], eps)).to(dtype)
+    return x
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [v.strip() for v in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def oracle_iteration_time(x, k, d, t_lo=1, t_hi=3):
+    """Per-iteration wall time of the numpy oracle port: (T(max_itr=t_hi) - T(max_itr=t_lo)) / (t_hi - t_lo)."""
+    from oracle.gmm_vb_oracle import OracleGMM, fit
+    times = {}
+    for t in (t_lo, t_hi):
+        m = OracleGMM(k, d, seed=0)
+        t0 = time.perf_counter()
+        fit(m, x, max_itr=t, num_init=1, tolerance=0.0)
+        times[t] = time.perf_counter() - t0
+    return (times[t_hi] - times[t_lo]) / (t_hi - t_lo)
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(cfg, budget_rows=200_000):
+    n_total, d, k, _, idx = CONFIGS[cfg]
+    n = min(n_total, budget_rows)
+    x = synth_host(n, d, k, 1234 + idx)
+    per_iter = oracle_iteration_time(x, k, d)
+    return {"value": n * k / per_iter, "unit": UNIT, "cores": blas_threads(), "host_cpus": os.cpu_count(),
+            "kind": "port", "s_per_iter_at_sample": per_iter,
+            "sample": f"numpy oracle port (oracle/gmm_vb_oracle.py), N={n} rows of the {cfg} workload (D={d}, K={k}), "
+                      f"(T(max_itr=3)-T(max_itr=1))/2, tolerance=0.0, num_init=1; linear in N"}
+
+
+def run_reference_arm(args):
+    """The reference's algorithm on the host cores (oracle port; the reference itself is Python and is not on the box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.gmm_vb_oracle import OracleGMM, fit  # noqa: F401
+    n_total, d, k, _, idx = CONFIGS[args.config]
+    total_iters = args.steps + args.warmup
+    n = int(min(n_total, max(20_000, 200_000 * min(1.0, 30.0 / max(total_iters, 1)))))
+    x = synth_host(n, d, k, 1234 + idx)
+    from oracle.gmm_vb_oracle import OracleGMM as O
+    m = O(k, d, seed=0)
+    m.alloc(n)
+    m.reset_hn(); m.init_rho_r(); m.init_subsampling(x); m.e_step(x); m.calc_vl()
+    for _ in range(args.warmup):
+        m.iterate(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.iterate(x)
+    dt = time.perf_counter() - t0
+    value = n * k * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.config}: GMM VB N={n_total} D={d} K={k} (timed on a bounded sample of N={n} rows)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "host_cpus": os.cpu_count(),
+                         "kind": "port",
+                         "sample": f"numpy oracle port, N={n} rows, {args.steps} VB iterations after {args.warmup} warm-up"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--variant", default="auto", choices=["auto", "simple", "dmma"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bayesml_b200 import _lib, gaussianmixture
+    from bayesml_b200.engine import VBEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device(f"cuda:{local_rank}")
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+        group = dist.group.WORLD
+    warmup = max(args.warmup, 3)
+
+    n_total, d, k, precision, idx = CONFIGS[args.config]
+    if args.scaling == "weak":
+        n_total = n_total * world
+    n_local = n_total // world + (1 if rank < n_total % world else 0)
+    xdtype = torch.float64 if precision == "float64" else torch.float32
+    x_dev = synth_device(n_local, d, k, 1234 + idx, rank, device, xdtype)
+
+    variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA}[args.variant]
+    eng = VBEngine(k, d, device=device, precision=precision, group=group, variant=variant)
+    eng.load_data(x_dev)                       # centres into the engine's own buffer
+    del x_dev
+
+    # initial parameters in the spirit of `_init_subsampling` (:786-796): rank 0 draws sqrt(N) of its rows per class
+    model = gaussianmixture.LearnModel(k, d, seed=0)
+    init = torch.empty(k * d + k * d * d, dtype=torch.float64, device=device)
+    if rank == 0:
+        n_sub = int(np.sqrt(n_total))
+        rng = np.random.default_rng(0)
+        m0 = np.empty((k, d)); winv0 = np.empty((k, d, d))
+        for c in range(k):
+            rows = torch.as_tensor(rng.choice(n_local, size=n_sub, replace=False, shuffle=False), device=device)
+            sub = eng.x[rows].double().cpu().numpy() + eng.center
+            m0[c] = sub.sum(axis=0) / n_sub
+            cen = sub - m0[c]
+            winv0[c] = cen.T @ cen / n_sub * model.hn_nus[c] + np.eye(d) * 1e-5
+        init.copy_(torch.as_tensor(np.concatenate([m0.ravel(), winv0.ravel()])))
+    if world > 1:
+        dist.broadcast(init, src=0)
+    init_h = init.cpu().numpy()
+    eng.set_prior(model.h0_alpha_vec, model.h0_m_vecs, model.h0_kappas, model.h0_nus, model.h0_w_mats_inv,
+                  model._ln_b_h0_w_nus, model._ln_c_h0_alpha)
+    eng._alloc_state(args.steps + warmup + 8)
+    eng.set_params(model.hn_alpha_vec, init_h[:k * d].reshape(k, d), model.hn_kappas, model.hn_nus,
+                   init_h[k * d:].reshape(k, d, d))
+    big = 1 << 30
+
+    def vb_iteration():
+        eng._pass()
+        eng._small(_lib.SMALL_ITERATE, big, 0.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(warmup):
+        vb_iteration()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    pass_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.passes + eng.small_launches
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        pass_ev[i][0].record()
+        _lib.check(eng.lib.bgmm_pass(eng.x.data_ptr(), eng.n_local, k, d, eng.x_code, eng.state.data_ptr(),
+                                     eng.workspace.data_ptr(), 0, 0, 0, 0, eng.variant, 0, 0, eng._stream()), "bgmm_pass")
+        pass_ev[i][1].record()
+        eng.passes += 1
+        if group is not None:
+            dist.all_reduce(eng.stats, group=group)
+        eng._small(_lib.SMALL_ITERATE, big, 0.0)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    pass_ms = torch.tensor([np.mean([a.elapsed_time(b) for a, b in pass_ev])], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pass_ms, op=dist.ReduceOp.MAX)
+    ms_total, pass_ms = float(ms_total.item()), float(pass_ms.item())
+    launches = eng.passes + eng.small_launches - launches0
+    ms_per_step = ms_total / args.steps
+    value = n_total * k / (ms_per_step * 1e-3)
+    # sanity: the loop really ran (ELBO history is finite and non-decreasing after the first step)
+    hist = eng.state[eng.off["vlhist"]: eng.off["vlhist"] + warmup + args.steps].cpu().numpy()
+    ok = bool(np.all(np.isfinite(hist)) and np.all(np.diff(hist[1:]) >= -1e-9 * np.abs(hist[1:-1])))
+
+    # roofline of the dominant kernel (the pass): algorithmic flops of this rank's rows / its average duration
+    flops = alg_flops_per_iter(n_local, d, k)
+    ach_tflops = flops / (pass_ms * 1e-3) / 1e12
+    x_bytes = n_local * d * (8 if precision == "float64" else 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(f"{args.config}_n{world}")
+    except Exception:
+        pass
+    roofline = {
+        "bound": "tensor", "achieved": ach_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+        "frac": ach_tflops / FP64_PEAK_TFLOPS, "traffic": traffic,
+        "kernel": "bgmm::pass_dmma_kernel" if eng.lib.bgmm_pass_supported(k, d, eng.x_code, _lib.PASS_DMMA)
+                  and args.variant != "simple" else "bgmm::pass_simple_kernel",
+        "kernel_ms": pass_ms, "kernel_share_of_step": pass_ms / ms_per_step,
+        "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": x_bytes,
+        "peak_source": "FP64 tensor pipe (DMMA.8x8x4) measured by tools/peaks on this pool's B200 "
+                       "(MEASURED_PEAKS.json has no FP64 entry); 'of measured'",
+        "hbm": {"achieved_gbs": x_bytes / (pass_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "frac": x_bytes / (pass_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
+    }
+
+    # ---- e2e: the public API with a HOST array (pinned), upload + init + steps iterations + final E-step + readback ----
+    e2e = None
+    if not args.no_e2e:
+        del eng
+        torch.cuda.empty_cache()
+        x_host_t = torch.empty((n_local, d), dtype=xdtype).pin_memory()
+        x_host_t.copy_(synth_device(n_local, d, k, 1234 + idx, rank, device, xdtype))
+        x_host = x_host_t.numpy()
+        lm = gaussianmixture.LearnModel(k, d, seed=0, device=device, precision=precision, process_group=group)
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            lm.update_posterior(x_host[: min(n_local, 100_000)], max_itr=2, num_init=1, tolerance=0.0)   # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            lm.update_posterior(x_host, max_itr=args.steps, num_init=1, tolerance=0.0)
+            _ = float(lm.vl); _ = lm.hn_alpha_vec.sum()
+            torch.cuda.synchronize(device)
+            dt = time.perf_counter() - t0
+        dt_t = torch.tensor([dt], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+        dt = float(dt_t.item())
+        state_bytes = int(lm._engine().state.numel() * 8)
+        e2e = {"value": n_total * k * args.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(x_host.nbytes / args.steps), "d2h_bytes_per_step": int(2 * state_bytes / args.steps),
+               "seconds": dt, "api": "bayesml_b200.gaussianmixture.LearnModel.update_posterior(x_host, max_itr=steps, "
+                                     "num_init=1, tolerance=0.0): upload + centring + host init + steps iterations + final E-step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f64" if precision == "float64" else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: GMM VB N={n_total} D={d} K={k} {precision}, rows sharded over {world} GPU(s), "
+                                   f"one all-reduce of K*(1+D+D(D+1)/2)+1 doubles per iteration" if world > 1 else
+                                   f"{args.config}: GMM VB N={n_total} D={d} K={k} {precision}, 1 GPU",
+                       "l2": f"X resident in HBM, {x_bytes / 1e6:.0f} MB per GPU per iteration (> 126 MB L2), no flush needed"
+                             if x_bytes > 130e6 else "X fits in L2: cold-L2 not enforced",
+                       "init": "subsampling-style (sqrt(N) rows per class), default priors, tolerance=0.0"},
+            "iters_per_s": 1e3 / ms_per_step, "elbo_finite_and_monotone": ok,
+            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.config)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
