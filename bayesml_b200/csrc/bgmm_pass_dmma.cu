@@ -78,6 +78,32 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
+// exp(z) for finite z <= 0, branch-free: z = n ln2 + f, |f| <= ln2/2, degree-12 Taylor (truncation 1.7e-16 relative),
+// scaled by adding n to the exponent field.  Below z = -700 the result is flushed to 0 (true value < 1e-304).
+__device__ __forceinline__ double exp_nonpos(double z) {
+    const double magic = 6755399441055744.0;                    // 1.5 * 2^52: rint() by addition
+    const double t = fma(z, 1.4426950408889634074, magic);
+    const int n = __double2loint(t);
+    const double nd = t - magic;
+    double f = fma(nd, -6.93147180369123816490e-01, z);         // ln2 split (Cody-Waite)
+    f = fma(nd, -1.90821492927058770002e-10, f);
+    double p = 1.0 / 479001600.0;
+    p = fma(p, f, 1.0 / 39916800.0);
+    p = fma(p, f, 1.0 / 3628800.0);
+    p = fma(p, f, 1.0 / 362880.0);
+    p = fma(p, f, 1.0 / 40320.0);
+    p = fma(p, f, 1.0 / 5040.0);
+    p = fma(p, f, 1.0 / 720.0);
+    p = fma(p, f, 1.0 / 120.0);
+    p = fma(p, f, 1.0 / 24.0);
+    p = fma(p, f, 1.0 / 6.0);
+    p = fma(p, f, 0.5);
+    p = fma(p, f, 1.0);
+    p = fma(p, f, 1.0);
+    const double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return z < -700.0 ? 0.0 : r;
+}
+
 template <int KB, int SP, int NPS>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 pass_dmma_kernel(const PassArgs a, const Layout L) {
@@ -233,6 +259,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
         for (int l = 0; l < MAXNB; ++l) mPo[l] = q * SP + ((8 * (wq + 4 * l) + g) ^ fq);   // n-block b = wq + 4l
 
         int jj = 0;
+        double sprod = 1.0;
         for (int j = wg; j < nloc; j += 2, ++jj) {
             const int ps = j % NPS;
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)j * gridDim.x) * DM_TILE;
@@ -296,7 +323,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const double z = lr[kb][e] - mx;
-                    const double ex = exp(z);
+                    const double ex = exp_nonpos(z);
                     lr[kb][e] = ex;
                     sum += ex;
                     dot = fma(ex, z, dot);              // z is finite (padding uses -1e300), so 0 * z == 0
@@ -306,7 +333,9 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
             dot += __shfl_xor_sync(0xffffffffu, dot, 1);
             dot += __shfl_xor_sync(0xffffffffu, dot, 2);
             const double inv = valid ? 1.0 / sum : 0.0;     // rows past the end contribute r = 0
-            if (valid && q == 0) ent += dot * inv - log(sum);
+            // sum_k r ln r = dot/sum - ln(sum); 1 <= sum <= K, so the logs of up to 8 rows are taken as one log of a product
+            if (valid && q == 0) { ent = fma(dot, inv, ent); sprod *= sum; }
+            if ((jj & 7) == 7) { ent -= log(sprod); sprod = 1.0; }
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) { lr[kb][0] *= inv; lr[kb][1] *= inv; }
             // r tile: physical column 16(kb>>1) + 4q + 2e + (kb&1), swizzle folded into rsto
@@ -373,6 +402,8 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
             }
             mbar_arrive(&pempty[ps]);                                     // this thread is done with the Phi stage
         }
+
+        ent -= log(sprod);
 
         // ---- this warpgroup's partial statistics (logical layout [K][pitch]) ----
         double* part = a.workspace + ((int64_t)blockIdx.x * 2 + wg) * len;
