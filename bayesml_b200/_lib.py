@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libbgmm.so")
 # constants mirrored from include/bgmm.h (checked against bgmm_abi_version at load time)
 ABI_VERSION = 1
 F64, F32 = 0, 1
-PASS_AUTO, PASS_SIMPLE, PASS_DMMA = 0, 1, 2
+PASS_AUTO, PASS_SIMPLE, PASS_DMMA, PASS_F32 = 0, 1, 2, 3
 SMALL_FEATURES, SMALL_ITERATE, SMALL_STATS = 0, 1, 2
 
 OFF_NAMES = ("center", "alpha0", "kappa0", "nu0", "m0", "w0inv", "lnb0", "lnc0", "params0", "params1", "stats",

@@ -25,6 +25,9 @@ int simple_grid_cap(int K, int D);
 bool dmma_supported(int K, int D, int dtype);
 int launch_pass_dmma(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream);
 int64_t dmma_workspace_doubles(int K, int D);
+bool f32_supported(int K, int D, int dtype);
+int launch_pass_f32(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream);
+int64_t f32_workspace_doubles(int K, int D);
 
 // ---- data preparation ----
 constexpr int PREP_THREADS = 256;
@@ -95,6 +98,8 @@ extern "C" int64_t bgmm_workspace_doubles(int K, int D) {
     int64_t w = (int64_t)simple_grid_cap(K, D) * len;
     const int64_t wd = dmma_workspace_doubles(K, D);
     if (wd > w) w = wd;
+    const int64_t wf = f32_workspace_doubles(K, D);
+    if (wf > w) w = wf;
     const int64_t wc = colsum_stride(D);
     if (wc > w) w = wc;
     return w;
@@ -141,6 +146,7 @@ extern "C" int bgmm_center(const void* x, int dtype_in, void* y, int dtype_out, 
 extern "C" int bgmm_pass_supported(int K, int D, int dtype, int variant) {
     if (K <= 0 || D <= 0 || (dtype != BGMM_F64 && dtype != BGMM_F32)) return 0;
     if (variant == BGMM_PASS_DMMA) return dmma_supported(K, D, dtype) ? 1 : 0;
+    if (variant == BGMM_PASS_F32) return f32_supported(K, D, dtype) ? 1 : 0;
     return variant == BGMM_PASS_SIMPLE || variant == BGMM_PASS_AUTO;
 }
 
@@ -154,8 +160,18 @@ extern "C" int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, doub
     }
     PassArgs a{x, n, state, workspace, r_out, lnrho_out, argmax_out, r_in, force, accumulate};
     cudaStream_t s = (cudaStream_t)stream;
-    if (variant == BGMM_PASS_AUTO)
-        variant = (r_in == nullptr && dmma_supported(K, D, dtype)) ? BGMM_PASS_DMMA : BGMM_PASS_SIMPLE;
+    if (variant == BGMM_PASS_AUTO) {
+        if (r_in == nullptr && dmma_supported(K, D, dtype)) variant = BGMM_PASS_DMMA;
+        else if (r_in == nullptr && f32_supported(K, D, dtype)) variant = BGMM_PASS_F32;
+        else variant = BGMM_PASS_SIMPLE;
+    }
+    if (variant == BGMM_PASS_F32) {
+        if (r_in != nullptr || !f32_supported(K, D, dtype)) {
+            set_error("bgmm_pass: F32 variant does not support K=%d D=%d dtype=%d r_in=%p", K, D, dtype, (const void*)r_in);
+            return BGMM_ENOSUP;
+        }
+        return launch_pass_f32(a, K, D, dtype, s);
+    }
     if (variant == BGMM_PASS_DMMA) {
         if (r_in != nullptr || !dmma_supported(K, D, dtype)) {
             set_error("bgmm_pass: DMMA variant does not support K=%d D=%d dtype=%d r_in=%p", K, D, dtype, (const void*)r_in);

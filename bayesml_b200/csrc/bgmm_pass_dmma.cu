@@ -405,58 +405,66 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
 
         ent -= log(sprod);
 
-        // ---- this warpgroup's partial statistics (logical layout [K][pitch]) ----
-        double* part = a.workspace + ((int64_t)blockIdx.x * 2 + wg) * len;
+        // ---- merge the two warpgroups' accumulators through shared memory (the Phi ring is free now) and write ONE
+        //      partial per CTA (logical layout [K][pitch]); the cross-CTA sum is done by reduce_partials_kernel ----
+        wg_sync(2 + wg);
+        asm volatile("bar.sync 4, 256;" ::: "memory");        // both consumer warpgroups are done with every Phi stage
+        double* mrg = phiS;                                    // [8*KB][SP] in (component, physical column) order
+        if (wg == 1) {
 #pragma unroll
-        for (int l = 0; l < MAXNB; ++l) {
-            const int b = wq + 4 * l;
+            for (int l = 0; l < MAXNB; ++l)
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
+                for (int kb = 0; kb < KB; ++kb)
+                    *reinterpret_cast<double2*>(&mrg[(8 * kb + g) * SP + 8 * (wq + 4 * l) + 2 * q]) =
+                        make_double2(macc[l][kb][0], macc[l][kb][1]);
+        }
+        asm volatile("bar.sync 4, 256;" ::: "memory");
+        if (wg == 0) {
+            double* part = a.workspace + (int64_t)blockIdx.x * len;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+            for (int l = 0; l < MAXNB; ++l) {
+                const int b = wq + 4 * l;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    const double2 o = lds2(&mrg[(8 * kb + g) * SP + 8 * b + 2 * q]);
                     const int k = 8 * kb + g;              // C fragment: row g = component, cols 2q+e = physical 8b+2q+e
-                    const int p = 8 * b + 4 * e + q;       // physical 8b + 2q + e  <->  logical 8b + 4e + q
-                    if (k < K && p < L.pitch) part[(int64_t)k * L.pitch + p] = macc[l][kb][e];
+                    const int p0 = 8 * b + q;              // physical 8b + 2q + e  <->  logical 8b + 4e + q
+                    if (k < K && p0 < L.pitch) part[(int64_t)k * L.pitch + p0] = macc[l][kb][0] + o.x;
+                    if (k < K && p0 + 4 < L.pitch) part[(int64_t)k * L.pitch + p0 + 4] = macc[l][kb][1] + o.y;
                 }
+            }
         }
     }
     ent = block_sum(ent, red);
     if (tid == 0) {
-        double* part = a.workspace + (int64_t)blockIdx.x * 2 * len;
+        double* part = a.workspace + (int64_t)blockIdx.x * len;
         part[(int64_t)K * L.pitch] = ent;
         for (int o = 1; o < 8; ++o) part[(int64_t)K * L.pitch + o] = 0.0;
-        for (int o = 0; o < 8; ++o) part[len + (int64_t)K * L.pitch + o] = 0.0;
     }
+}
 
-    // ---- last CTA reduces the 2*grid partials in a fixed order ----
-    __shared__ int is_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int tk = atomicAdd(const_cast<int*>(&ctrl[BGMM_CTRL_PASS_TICKET]), 1);
-        is_last = (tk == (int)gridDim.x - 1);
+// Cross-CTA reduction of the per-CTA partial statistics, fully parallel and in a fixed order (deterministic):
+// out[o] = sum_b ws[b][o].  tail[1] of the statistics buffer is set to the local row count.
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const double* __restrict__ ws, const int nparts,
+                                                              const int64_t len, double* __restrict__ out,
+                                                              const int64_t rows_slot, const double rows,
+                                                              const int accumulate, const int* __restrict__ ctrl,
+                                                              const int force) {
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    const int64_t o = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (o >= len) return;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = 0;
+    for (; b + 3 < nparts; b += 4) {
+        s0 += ws[(int64_t)(b + 0) * len + o];
+        s1 += ws[(int64_t)(b + 1) * len + o];
+        s2 += ws[(int64_t)(b + 2) * len + o];
+        s3 += ws[(int64_t)(b + 3) * len + o];
     }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    double* out = a.state + L.stats;
-    const double* ws = a.workspace;
-    const int nparts = 2 * (int)gridDim.x;
-    for (int64_t o = tid; o < len; o += DM_THREADS) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int bidx = 0;
-        for (; bidx + 3 < nparts; bidx += 4) {
-            s0 += __ldcg(&ws[(int64_t)(bidx + 0) * len + o]);
-            s1 += __ldcg(&ws[(int64_t)(bidx + 1) * len + o]);
-            s2 += __ldcg(&ws[(int64_t)(bidx + 2) * len + o]);
-            s3 += __ldcg(&ws[(int64_t)(bidx + 3) * len + o]);
-        }
-        for (; bidx < nparts; ++bidx) s0 += __ldcg(&ws[(int64_t)bidx * len + o]);
-        double acc = (s0 + s1) + (s2 + s3);
-        if (o == (int64_t)K * L.pitch + 1) acc = (double)a.n;
-        out[o] = a.accumulate ? out[o] + acc : acc;
-    }
-    if (tid == 0) ctrl[BGMM_CTRL_PASS_TICKET] = 0;
+    for (; b < nparts; ++b) s0 += ws[(int64_t)b * len + o];
+    double acc = (s0 + s1) + (s2 + s3);
+    if (o == rows_slot) acc = rows;
+    out[o] = accumulate ? out[o] + acc : acc;
 }
 
 // ---- host side ----
@@ -492,30 +500,28 @@ bool dmma_supported(int K, int D, int dtype) { return dtype == BGMM_F64 && plan_
 
 static int dmma_grid(int64_t n) {
     const int64_t ntiles = (n + 2 * DM_TILE - 1) / (2 * DM_TILE);   // at least two sub-tiles per CTA when possible
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        sms = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return (int)(ntiles < 1 ? 1 : (ntiles < sms ? ntiles : sms));
 }
 
 int64_t dmma_workspace_doubles(int K, int D) {
     if (!plan_dmma(K, D).ok) return 0;
-    return (int64_t)2 * 160 * ((int64_t)K * feat_pitch(D) + 8);   // 2 partials per CTA, >= SM count of any sm_100 part
+    return (int64_t)160 * ((int64_t)K * feat_pitch(D) + 8);   // one partial per CTA, >= SM count of any sm_100 part
 }
 
 template <int KB, int SP, int NPS>
 static int launch_cfg(const PassArgs& a, const Layout& L, const DmmaPlan& p, cudaStream_t stream) {
     auto kern = pass_dmma_kernel<KB, SP, NPS>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_dmma)");
-        configured = true;
-    }
-    kern<<<dmma_grid(a.n), DM_THREADS, p.smem, stream>>>(a, L);
+    // per launch: the attribute is per device and a process may drive several devices
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_dmma)");
+    const int grid = dmma_grid(a.n);
+    kern<<<grid, DM_THREADS, p.smem, stream>>>(a, L);
+    const int64_t len = L.stats_len;
+    reduce_partials_kernel<<<(int)((len + 127) / 128), 128, 0, stream>>>(
+        a.workspace, grid, len, a.state + L.stats, (int64_t)L.K * L.pitch + 1, (double)a.n, a.accumulate,
+        reinterpret_cast<const int*>(a.state + L.ctrl), a.force);
     return check_cuda(cudaGetLastError(), "pass_dmma_kernel launch");
 }
 

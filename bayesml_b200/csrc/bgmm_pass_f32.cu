@@ -1,0 +1,249 @@
+// bgmm_pass, fp32 streaming variant (BGMM_PASS_F32) for small D (<= 3) and K (<= 8): BASELINE config C3
+// (N = 200M, D = 2, K = 8, "fp32 mode").
+//
+// One thread owns one sample at a time; everything per sample lives in registers:
+//   E-step   ln rho_nk in base 2, whitened form  a2_k - |L'_k^T (x' - m'_k)|^2   (L' = chol(nu W) * sqrt(log2(e)/2)),
+//            softmax with MUFU.EX2 / MUFU.RCP, entropy term with MUFU.LG2;
+//   M-stats  raw_k += r_nk * phi(x'_n) in per-thread fp32 accumulators, flushed every F32_FLUSH samples through a
+//            warp shuffle reduction into per-warp fp64 accumulators in shared memory (fp32 error stays ~1e-7 relative).
+// X is streamed once with coalesced vector loads (D*4 bytes per sample); r never touches HBM.  The whitened form keeps
+// (x' - m'_k) explicit, so fp32 cancellation does not grow with the distance of a component from the centre.
+// The kernel is FP32-issue bound, not HBM bound (8 components per 8-byte sample).
+// Replaces `_update_q_z` :772-784, `_calc_n_x_bar_s` :725-732, `xlogy` :704 (reference GMM file) in fp32 mode; parity
+// bar 1e-4 relative against the fp64 oracle fed the same fp32-rounded X.
+#include "bgmm_common.cuh"
+#include <math.h>
+
+namespace bgmm {
+
+constexpr int F32_THREADS = 256;
+constexpr int F32_KMAX = 8;
+constexpr int F32_FLUSH = 128;       // samples per thread between flushes of the fp32 accumulators
+
+template <int D>
+struct F32Params {                   // per component, fp32, in shared memory
+    float m[D];
+    float lt[D * (D + 1) / 2];       // packed lower triangle of L' (row-major: (i, j<=i) at i(i+1)/2 + j)
+    float a2;                        // ln rho constant in base 2
+};
+
+template <int D>
+__global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a, const Layout L) {
+    constexpr int P = 1 + D + D * (D + 1) / 2;
+    constexpr int NW = F32_THREADS / 32;
+    __shared__ F32Params<D> prm[F32_KMAX];
+    __shared__ double wsum[NW][F32_KMAX * P + 1];
+    __shared__ double red[40];
+    __shared__ int is_last;
+    const int K = L.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
+    if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
+    const double* Pc = a.state + L.params[ctrl[BGMM_CTRL_CUR]];
+    const float* __restrict__ x = static_cast<const float*>(a.x);
+
+    // ---- prologue: whitening factors of Lambda_k = nu_k W_k (fp64 Cholesky of a D x D matrix per component) ----
+    if (tid < F32_KMAX) {
+        const int k = tid;
+        F32Params<D>& q = prm[k];
+        if (k < K) {
+            const double nu = Pc[L.p_nu + k], kappa = Pc[L.p_kappa + k];
+            const double* W = Pc + L.p_w + (int64_t)k * D * D;
+            double lo[D][D];
+            bool ok = true;
+            for (int i = 0; i < D; ++i)
+                for (int j = 0; j <= i; ++j) {
+                    double s = nu * W[i * D + j];
+                    for (int l = 0; l < j; ++l) s -= lo[i][l] * lo[j][l];
+                    if (i == j) { ok = ok && (s > 0.0); lo[i][i] = sqrt(s); }
+                    else lo[i][j] = s / lo[j][j];
+                }
+            const double sc = sqrt(0.5 * 1.4426950408889634074);
+            for (int i = 0; i < D; ++i) {
+                q.m[i] = (float)Pc[L.p_m + (int64_t)k * D + i];
+                for (int j = 0; j <= i; ++j) q.lt[i * (i + 1) / 2 + j] = (float)(lo[i][j] * sc);
+            }
+            const double ak = Pc[L.p_elnpi + k] + 0.5 * (Pc[L.p_elndet + k] - D * 1.837877066409345483560659472811 - D / kappa);
+            q.a2 = (float)(ak * 1.4426950408889634074);
+            if (!ok) ctrl[BGMM_CTRL_ERROR] = 1;
+        } else {
+            for (int i = 0; i < D; ++i) q.m[i] = 0.f;
+            for (int i = 0; i < D * (D + 1) / 2; ++i) q.lt[i] = 0.f;
+            q.a2 = -1.0e30f;                                  // padded components: r == 0 exactly
+        }
+    }
+    for (int i = lane; i < F32_KMAX * P + 1; i += 32) wsum[warp][i] = 0.0;
+    __syncthreads();
+
+    float acc[F32_KMAX][P];
+#pragma unroll
+    for (int k = 0; k < F32_KMAX; ++k)
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[k][p] = 0.f;
+    float ent = 0.f;
+    int pending = 0;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < F32_KMAX; ++k)
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                float v = acc[k][p];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) wsum[warp][k * P + p] += (double)v;
+                acc[k][p] = 0.f;
+            }
+        float v = ent;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) wsum[warp][F32_KMAX * P] += (double)v;
+        ent = 0.f;
+        pending = 0;
+    };
+
+    // warp-uniform loop (every lane runs the same number of iterations; rows past the end are masked) so that the
+    // full-warp shuffles of flush() are always executed by all 32 lanes
+    const int64_t stride = (int64_t)gridDim.x * F32_THREADS;
+    for (int64_t base = (int64_t)blockIdx.x * F32_THREADS + warp * 32; base < a.n; base += stride) {
+        const int64_t n = base + lane;
+        const bool valid = n < a.n;
+        float xv[D];
+        if (valid) {
+            if constexpr (D == 2) {
+                const float2 v = reinterpret_cast<const float2*>(x)[n];
+                xv[0] = v.x; xv[1] = v.y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < D; ++i) xv[i] = x[n * D + i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) xv[i] = 0.f;
+        }
+        // E-step
+        float l2[F32_KMAX];
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int k = 0; k < F32_KMAX; ++k) {
+            float d[D];
+#pragma unroll
+            for (int i = 0; i < D; ++i) d[i] = xv[i] - prm[k].m[i];
+            float qf = 0.f;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                float y = 0.f;
+#pragma unroll
+                for (int i = j; i < D; ++i) y = fmaf(prm[k].lt[i * (i + 1) / 2 + j], d[i], y);
+                qf = fmaf(y, y, qf);
+            }
+            l2[k] = prm[k].a2 - qf;
+            mx = fmaxf(mx, l2[k]);
+        }
+        if (a.lnrho_out != nullptr && valid)
+            for (int k = 0; k < K; ++k) a.lnrho_out[n * K + k] = (double)l2[k] * 0.693147180559945309417232121458;
+        float s = 0.f, dot = 0.f, e[F32_KMAX];
+#pragma unroll
+        for (int k = 0; k < F32_KMAX; ++k) {
+            const float z = fmaxf(l2[k] - mx, -1.0e30f);
+            e[k] = exp2f(z);
+            s += e[k];
+            dot = fmaf(e[k], z, dot);
+        }
+        const float inv = valid ? __frcp_rn(s) : 0.f;
+        if (valid) ent += 0.693147180559945309f * (dot * inv - __log2f(s));
+        // statistics about the global centre: phi = [1, x, x_i x_j (i >= j)]
+        float phi[P];
+        phi[0] = 1.f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) phi[1 + i] = xv[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) phi[1 + D + i * (i + 1) / 2 + j] = xv[i] * xv[j];
+        int best = 0;
+        float bestv = -1.f;
+#pragma unroll
+        for (int k = 0; k < F32_KMAX; ++k) {
+            const float r = e[k] * inv;
+            e[k] = r;
+            if (r > bestv) { bestv = r; best = k; }
+            acc[k][0] += r;
+#pragma unroll
+            for (int p = 1; p < P; ++p) acc[k][p] = fmaf(r, phi[p], acc[k][p]);
+        }
+        if (a.r_out != nullptr && valid)
+            for (int k = 0; k < K; ++k) a.r_out[n * K + k] = (double)e[k];
+        if (a.argmax_out != nullptr && valid) a.argmax_out[n] = best;
+        if (++pending == F32_FLUSH) flush();
+    }
+    flush();
+    __syncthreads();
+
+    // ---- per-CTA partial (fp64, logical layout [K][pitch]) ----
+    const int64_t len = L.stats_len;
+    double* part = a.workspace + (int64_t)blockIdx.x * len;
+    for (int64_t o = tid; o < len; o += F32_THREADS) part[o] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < K * P; i += F32_THREADS) {
+        const int k = i / P, p = i - k * P;
+        double v = 0.0;
+        for (int w = 0; w < NW; ++w) v += wsum[w][k * P + p];
+        part[(int64_t)k * L.pitch + p] = v;
+    }
+    if (tid == 0) {
+        double v = 0.0;
+        for (int w = 0; w < NW; ++w) v += wsum[w][F32_KMAX * P];
+        part[(int64_t)K * L.pitch] = v;
+    }
+
+    // ---- last CTA reduces the partials in CTA order ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int tk = atomicAdd(const_cast<int*>(&ctrl[BGMM_CTRL_PASS_TICKET]), 1);
+        is_last = (tk == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double* out = a.state + L.stats;
+    const double* ws = a.workspace;
+    for (int64_t o = tid; o < len; o += F32_THREADS) {
+        double s0 = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) s0 += __ldcg(&ws[(int64_t)b * len + o]);
+        if (o == (int64_t)K * L.pitch + 1) s0 = (double)a.n;
+        out[o] = a.accumulate ? out[o] + s0 : s0;
+    }
+    if (tid == 0) ctrl[BGMM_CTRL_PASS_TICKET] = 0;
+    (void)red;
+}
+
+bool f32_supported(int K, int D, int dtype) { return dtype == BGMM_F32 && D >= 1 && D <= 3 && K <= F32_KMAX; }
+
+static int f32_grid(int64_t n) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (n + F32_THREADS - 1) / F32_THREADS;
+    const int64_t cap = (int64_t)sms * 2;                      // 2 resident CTAs per SM (register bound)
+    return (int)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
+int64_t f32_workspace_doubles(int K, int D) {
+    if (!(D >= 1 && D <= 3 && K <= F32_KMAX)) return 0;
+    return (int64_t)2 * 160 * ((int64_t)K * feat_pitch(D) + 8);
+}
+
+int launch_pass_f32(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream) {
+    if (!f32_supported(K, D, dtype)) {
+        set_error("bgmm_pass(f32): unsupported shape K=%d D=%d dtype=%d", K, D, dtype);
+        return BGMM_ENOSUP;
+    }
+    const Layout L = make_layout(K, D, 1);
+    const int grid = f32_grid(a.n);
+    if (D == 1) pass_f32_kernel<1><<<grid, F32_THREADS, 0, stream>>>(a, L);
+    else if (D == 2) pass_f32_kernel<2><<<grid, F32_THREADS, 0, stream>>>(a, L);
+    else pass_f32_kernel<3><<<grid, F32_THREADS, 0, stream>>>(a, L);
+    return check_cuda(cudaGetLastError(), "pass_f32_kernel launch");
+}
+
+}  // namespace bgmm

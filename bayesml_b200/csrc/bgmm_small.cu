@@ -287,12 +287,10 @@ extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, do
         set_error("bgmm_small: D=%d needs %zu B of shared memory (> 227 KiB)", D, smem);
         return BGMM_ENOSUP;
     }
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024) {   // per launch: the attribute is per device
         int rc = check_cuda(cudaFuncSetAttribute(small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                             "cudaFuncSetAttribute(small_kernel)");
         if (rc) return rc;
-        configured = smem;
     }
     const int nt = D <= 8 ? 64 : (D <= 32 ? 128 : 256);
     small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol);

@@ -21,6 +21,23 @@ from . import _lib
 _DTYPES = {"float64": (_lib.F64, torch.float64), "float32": (_lib.F32, torch.float32)}
 
 
+class _Phase:
+    """Wall-clock phase timer (device-synchronised), active only with BAYESML_B200_TIMING=1."""
+
+    def __init__(self, eng, name):
+        self.eng, self.name = eng, name
+
+    def __enter__(self):
+        if self.eng.timing is not None:
+            torch.cuda.synchronize(self.eng.device)
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        if self.eng.timing is not None:
+            torch.cuda.synchronize(self.eng.device)
+            self.eng.timing[self.name] = self.eng.timing.get(self.name, 0.0) + time.perf_counter() - self.t0
+
+
 class VBEngine:
     def __init__(self, K, D, device=None, precision="float64", group=None, variant=_lib.PASS_AUTO):
         self.lib = _lib.load()
@@ -35,7 +52,7 @@ class VBEngine:
         self.group = group
         env = os.environ.get("BAYESML_B200_PASS_VARIANT", "").lower()     # debugging / tests: force a kernel variant
         if env:
-            variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA}[env]
+            variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "f32": _lib.PASS_F32}[env]
         self.variant = variant
         self.hist_len = 0
         self.state = None
@@ -43,6 +60,7 @@ class VBEngine:
         self.n_local = 0
         self.n_global = 0
         self.center = np.zeros(self.D)
+        self.timing = {} if os.environ.get("BAYESML_B200_TIMING") else None
         self.passes = 0                       # pass launches (for gpu_launches accounting)
         self.small_launches = 0
         with torch.cuda.device(self.device):
@@ -50,6 +68,9 @@ class VBEngine:
                                          device=self.device)
         self._alloc_state(2)
         self.r_dev = self.lnrho_dev = self.argmax_dev = None
+
+    def phase(self, name):
+        return _Phase(self, name)
 
     # ------------------------------------------------------------------ buffers
     def _alloc_state(self, hist_len):

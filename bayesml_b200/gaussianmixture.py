@@ -332,7 +332,8 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         """
         x = self._check_x(x)
         eng = self._engine()
-        eng.load_data(x)
+        with eng.phase("upload+centre"):
+            eng.load_data(x)
         offset, n_total = self._shard_layout(x.shape[0])
         self._push_prior(eng)
         self._lazy_r.set_host(None)
@@ -342,19 +343,21 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         best = {name: np.array(getattr(self, name)) for name in _HN_NAMES}      # :838-844
         never_converged = True
         for i in range(num_init):
-            self.reset_hn_params()
-            r_init = None
-            if init_type == 'subsampling':
-                self._init_subsampling(x, offset, n_total)
-            elif init_type == 'random_responsibility':
-                r_init = self._init_random_responsibility(x.shape[0], offset, n_total)
-            else:
-                raise ValueError(
-                    f'init_type={init_type} is unsupported. '
-                    + 'This function supports only '
-                    + '"subsampling" and "random_responsibility"')
-            self._push_hn(eng)
-            hist, converged = eng.run(max_itr, tolerance, r_init=r_init)
+            with eng.phase("host_init"):
+                self.reset_hn_params()
+                r_init = None
+                if init_type == 'subsampling':
+                    self._init_subsampling(x, offset, n_total)
+                elif init_type == 'random_responsibility':
+                    r_init = self._init_random_responsibility(x.shape[0], offset, n_total)
+                else:
+                    raise ValueError(
+                        f'init_type={init_type} is unsupported. '
+                        + 'This function supports only '
+                        + '"subsampling" and "random_responsibility"')
+                self._push_hn(eng)
+            with eng.phase("vb_loop"):
+                hist, converged = eng.run(max_itr, tolerance, r_init=r_init)
             # same progress text as :861, :868, :871
             print(f'\r{i}. VL: {hist[0]}', end='')
             for t in range(len(hist) - 1):
@@ -362,7 +365,8 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
             if converged:
                 never_converged = False
                 print('(converged)', end='')
-            self._pull_state(eng)
+            with eng.phase("pull_state"):
+                self._pull_state(eng)
             if i == 0 or self.vl > best_vl:                                      # :873 (strict: ties keep the earlier)
                 print('*')
                 best_vl = self.vl
@@ -377,7 +381,8 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
             getattr(self, name)[:] = best[name]
         self._calc_q_pi_features()
         self._calc_q_lambda_features()
-        self._final_e_step(eng)                                                   # :895
+        with eng.phase("final_e_step"):
+            self._final_e_step(eng)                                               # :895
         return self
 
     def _final_e_step(self, eng):

@@ -49,6 +49,7 @@ extern "C" {
 #define BGMM_PASS_AUTO 0   /* pick the fastest kernel that supports (K, D, dtype) */
 #define BGMM_PASS_SIMPLE 1 /* generic scalar-FMA kernel: any K, D */
 #define BGMM_PASS_DMMA 2   /* fp64 tensor-pipe kernel (mma.sync.m8n8k4.f64): K*PITCH accumulators on chip */
+#define BGMM_PASS_F32 3    /* fp32-mode streaming kernel: X float32, D <= 3, K <= 8 (fp64 accumulation of partials) */
 
 /* bgmm_small `mode` */
 #define BGMM_SMALL_FEATURES 0 /* features + coef of params[cur] from (alpha, m, kappa, nu, W^-1); no statistics used */

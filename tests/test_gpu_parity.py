@@ -219,3 +219,36 @@ def test_larger_shapes_against_oracle_and_elbo_monotone(shape, variant, monkeypa
     assert np.array_equal(np.argmax(m.r_vecs, axis=1), np.argmax(o.r_vecs, axis=1))
     assert np.allclose(m.r_vecs.sum(axis=1), 1.0, rtol=0, atol=1e-12)
     assert np.isclose(m.ns.sum(), n, rtol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(60000, 2, 8), (30000, 3, 5), (20000, 1, 3), (4097, 2, 2)])
+def test_fp32_mode_against_fp64_oracle(shape):
+    """precision='float32' (BASELINE config C3's mode): X is rounded to fp32 once and the SAME rounded X is fed to the
+    fp64 oracle (the reference promotes float32 input to float64, :780); bar 1e-4 relative, assignments exact."""
+    from bayesml_b200 import _lib, gaussianmixture
+    from oracle.gmm_vb_oracle import OracleGMM, fit
+    n, d, k = shape
+    assert _lib.load().bgmm_pass_supported(k, d, _lib.F32, _lib.PASS_F32)
+    rng = np.random.default_rng(n + d + k)
+    mu = rng.normal(0, 5.0, size=(k, d))
+    z = rng.integers(0, k, size=n)
+    x32 = (mu[z] + rng.normal(size=(n, d)) * rng.uniform(0.5, 1.5, size=(k, 1))[z]).astype(np.float32)
+    m = gaussianmixture.LearnModel(k, d, seed=2, precision="float32")
+    o = OracleGMM(k, d, seed=2)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m.update_posterior(x32, max_itr=10, num_init=1, tolerance=0.0)
+    tr = fit(o, x32, max_itr=10, num_init=1, tolerance=0.0)
+    tol = 1e-4
+    vals = _parse_progress(buf.getvalue())[0][0]
+    _close(vals, tr.vl_history[0], rtol=tol, what="fp32-mode VL history")
+    for f in ("hn_alpha_vec", "hn_m_vecs", "hn_kappas", "hn_nus", "hn_w_mats_inv", "ns", "x_bar_vecs", "s_mats"):
+        _close(getattr(m, f), getattr(o, f), rtol=tol, what="fp32-mode " + f)
+    big = o.r_vecs > 1e-3                                  # responsibilities that carry weight: relative bar
+    assert np.allclose(m.r_vecs[big], o.r_vecs[big], rtol=tol)
+    assert np.allclose(m.r_vecs, o.r_vecs, rtol=0, atol=1e-5)
+    margin = np.sort(o.r_vecs, axis=1)
+    clear = (margin[:, -1] - margin[:, -2]) > 1e-4         # exclude numerical near-ties (SURVEY §7)
+    assert np.array_equal(np.argmax(m.r_vecs, axis=1)[clear], np.argmax(o.r_vecs, axis=1)[clear])
+    assert clear.mean() > 0.99
