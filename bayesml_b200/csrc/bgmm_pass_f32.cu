@@ -16,9 +16,25 @@
 
 namespace bgmm {
 
-constexpr int F32_THREADS = 256;
+constexpr int F32_THREADS = 128;
 constexpr int F32_KMAX = 8;
 constexpr int F32_FLUSH = 128;       // samples per thread between flushes of the fp32 accumulators
+
+__device__ __forceinline__ float ex2_approx(float x) {       // MUFU.EX2, flush-to-zero: 2^x for x <= 0 (2 ulp)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 template <int D>
 struct F32Params {                   // per component, fp32, in shared memory
@@ -74,6 +90,21 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
     for (int i = lane; i < F32_KMAX * P + 1; i += 32) wsum[warp][i] = 0.0;
     __syncthreads();
 
+    // D <= 2: the component parameters live in registers (48 floats at D=2, K=8); per-(n,k) shared-memory broadcasts
+    // would make the kernel LSU bound.  D = 3 keeps them in shared memory (register budget).
+    constexpr bool kRegParams = (D <= 2);
+    constexpr int NLT = D * (D + 1) / 2;
+    float pm[kRegParams ? F32_KMAX : 1][D], plt[kRegParams ? F32_KMAX : 1][NLT], pa2[kRegParams ? F32_KMAX : 1];
+    if constexpr (kRegParams) {
+#pragma unroll
+        for (int k = 0; k < F32_KMAX; ++k) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) pm[k][i] = prm[k].m[i];
+#pragma unroll
+            for (int i = 0; i < NLT; ++i) plt[k][i] = prm[k].lt[i];
+            pa2[k] = prm[k].a2;
+        }
+    }
     float acc[F32_KMAX][P];
 #pragma unroll
     for (int k = 0; k < F32_KMAX; ++k)
@@ -104,22 +135,34 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
     // warp-uniform loop (every lane runs the same number of iterations; rows past the end are masked) so that the
     // full-warp shuffles of flush() are always executed by all 32 lanes
     const int64_t stride = (int64_t)gridDim.x * F32_THREADS;
+    auto load_row = [&](int64_t row, float (&dst)[D]) {
+        if (row < a.n) {
+            if constexpr (D == 2) {
+                const float2 v = __ldg(reinterpret_cast<const float2*>(x) + row);
+                dst[0] = v.x; dst[1] = v.y;
+            } else {
+#pragma unroll
+                for (int i = 0; i < D; ++i) dst[i] = __ldg(x + row * D + i);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) dst[i] = 0.f;
+        }
+    };
+    // software pipeline: the loads of the next two grid-stride rows are in flight while this row is processed
+    float xn1[D], xn2[D];
+    {
+        const int64_t b0 = (int64_t)blockIdx.x * F32_THREADS + warp * 32 + lane;
+        load_row(b0, xn1);
+        load_row(b0 + stride, xn2);
+    }
     for (int64_t base = (int64_t)blockIdx.x * F32_THREADS + warp * 32; base < a.n; base += stride) {
         const int64_t n = base + lane;
         const bool valid = n < a.n;
         float xv[D];
-        if (valid) {
-            if constexpr (D == 2) {
-                const float2 v = reinterpret_cast<const float2*>(x)[n];
-                xv[0] = v.x; xv[1] = v.y;
-            } else {
 #pragma unroll
-                for (int i = 0; i < D; ++i) xv[i] = x[n * D + i];
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < D; ++i) xv[i] = 0.f;
-        }
+        for (int i = 0; i < D; ++i) { xv[i] = xn1[i]; xn1[i] = xn2[i]; }
+        load_row(n + 2 * stride, xn2);
         // E-step
         float l2[F32_KMAX];
         float mx = -3.0e38f;
@@ -127,30 +170,34 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
         for (int k = 0; k < F32_KMAX; ++k) {
             float d[D];
 #pragma unroll
-            for (int i = 0; i < D; ++i) d[i] = xv[i] - prm[k].m[i];
+            for (int i = 0; i < D; ++i) d[i] = xv[i] - (kRegParams ? pm[kRegParams ? k : 0][i] : prm[k].m[i]);
             float qf = 0.f;
 #pragma unroll
             for (int j = 0; j < D; ++j) {
                 float y = 0.f;
 #pragma unroll
-                for (int i = j; i < D; ++i) y = fmaf(prm[k].lt[i * (i + 1) / 2 + j], d[i], y);
+                for (int i = j; i < D; ++i)
+                    y = fmaf(kRegParams ? plt[kRegParams ? k : 0][i * (i + 1) / 2 + j] : prm[k].lt[i * (i + 1) / 2 + j], d[i], y);
                 qf = fmaf(y, y, qf);
             }
-            l2[k] = prm[k].a2 - qf;
+            l2[k] = (kRegParams ? pa2[kRegParams ? k : 0] : prm[k].a2) - qf;
             mx = fmaxf(mx, l2[k]);
         }
-        if (a.lnrho_out != nullptr && valid)
-            for (int k = 0; k < K; ++k) a.lnrho_out[n * K + k] = (double)l2[k] * 0.693147180559945309417232121458;
+        if (a.lnrho_out != nullptr && valid) {
+#pragma unroll
+            for (int k = 0; k < F32_KMAX; ++k)          // unrolled + guarded: keeps l2[] in registers
+                if (k < K) a.lnrho_out[n * K + k] = (double)l2[k] * 0.693147180559945309417232121458;
+        }
         float s = 0.f, dot = 0.f, e[F32_KMAX];
 #pragma unroll
         for (int k = 0; k < F32_KMAX; ++k) {
-            const float z = fmaxf(l2[k] - mx, -1.0e30f);
-            e[k] = exp2f(z);
+            const float z = l2[k] - mx;                 // finite: padded components sit at -1e30
+            e[k] = ex2_approx(z);
             s += e[k];
             dot = fmaf(e[k], z, dot);
         }
-        const float inv = valid ? __frcp_rn(s) : 0.f;
-        if (valid) ent += 0.693147180559945309f * (dot * inv - __log2f(s));
+        const float inv = valid ? rcp_approx(s) : 0.f;  // 1 <= s <= K
+        if (valid) ent += 0.693147180559945309f * (dot * inv - lg2_approx(s));
         // statistics about the global centre: phi = [1, x, x_i x_j (i >= j)]
         float phi[P];
         phi[0] = 1.f;
@@ -171,8 +218,11 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
 #pragma unroll
             for (int p = 1; p < P; ++p) acc[k][p] = fmaf(r, phi[p], acc[k][p]);
         }
-        if (a.r_out != nullptr && valid)
-            for (int k = 0; k < K; ++k) a.r_out[n * K + k] = (double)e[k];
+        if (a.r_out != nullptr && valid) {
+#pragma unroll
+            for (int k = 0; k < F32_KMAX; ++k)
+                if (k < K) a.r_out[n * K + k] = (double)e[k];
+        }
         if (a.argmax_out != nullptr && valid) a.argmax_out[n] = best;
         if (++pending == F32_FLUSH) flush();
     }
@@ -220,17 +270,21 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
 
 bool f32_supported(int K, int D, int dtype) { return dtype == BGMM_F32 && D >= 1 && D <= 3 && K <= F32_KMAX; }
 
+template <int D>
 static int f32_grid(int64_t n) {
-    int dev = 0, sms = 148;
+    int dev = 0, sms = 148, occ = 1;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_f32_kernel<D>, F32_THREADS, 0);
+    if (occ < 1) occ = 1;
     const int64_t want = (n + F32_THREADS - 1) / F32_THREADS;
-    const int64_t cap = (int64_t)sms * 2;                      // 2 resident CTAs per SM (register bound)
+    int64_t cap = (int64_t)sms * occ;                          // one resident wave: persistent grid-stride CTAs
+    if (cap > 1024) cap = 1024;
     return (int)(want < 1 ? 1 : (want < cap ? want : cap));
 }
 
 int64_t f32_workspace_doubles(int K, int D) {
     if (!(D >= 1 && D <= 3 && K <= F32_KMAX)) return 0;
-    return (int64_t)2 * 160 * ((int64_t)K * feat_pitch(D) + 8);
+    return (int64_t)1024 * ((int64_t)K * feat_pitch(D) + 8);
 }
 
 int launch_pass_f32(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream) {
@@ -239,10 +293,9 @@ int launch_pass_f32(const PassArgs& a, int K, int D, int dtype, cudaStream_t str
         return BGMM_ENOSUP;
     }
     const Layout L = make_layout(K, D, 1);
-    const int grid = f32_grid(a.n);
-    if (D == 1) pass_f32_kernel<1><<<grid, F32_THREADS, 0, stream>>>(a, L);
-    else if (D == 2) pass_f32_kernel<2><<<grid, F32_THREADS, 0, stream>>>(a, L);
-    else pass_f32_kernel<3><<<grid, F32_THREADS, 0, stream>>>(a, L);
+    if (D == 1) pass_f32_kernel<1><<<f32_grid<1>(a.n), F32_THREADS, 0, stream>>>(a, L);
+    else if (D == 2) pass_f32_kernel<2><<<f32_grid<2>(a.n), F32_THREADS, 0, stream>>>(a, L);
+    else pass_f32_kernel<3><<<f32_grid<3>(a.n), F32_THREADS, 0, stream>>>(a, L);
     return check_cuda(cudaGetLastError(), "pass_f32_kernel launch");
 }
 

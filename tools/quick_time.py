@@ -22,14 +22,15 @@ def synth(n, d, k, seed=0, dtype=torch.float64):
 def main():
     n, d, k = (int(v) for v in sys.argv[1:4]) if len(sys.argv) > 3 else (10_000_000, 16, 32)
     variants = sys.argv[4].split(",") if len(sys.argv) > 4 else ["dmma", "simple"]
-    x = synth(n, d, k)
-    xh_sub = x[:200000].cpu().numpy()
+    prec = sys.argv[5] if len(sys.argv) > 5 else "float64"
+    x = synth(n, d, k, dtype=torch.float64 if prec == "float64" else torch.float32)
+    xh_sub = x[:200000].double().cpu().numpy()
     for vname in variants:
-        code = {"simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "auto": 0}[vname]
-        if not _lib.load().bgmm_pass_supported(k, d, _lib.F64, code):
+        code = {"simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "auto": 0, "f32": _lib.PASS_F32}[vname]
+        if not _lib.load().bgmm_pass_supported(k, d, _lib.F64 if prec == "float64" else _lib.F32, code):
             print(vname, "unsupported"); continue
-        eng = VBEngine(k, d, variant=code)
-        eng.load_data(x.clone())
+        eng = VBEngine(k, d, variant=code, precision=prec)
+        eng.load_data(x)
         D = d
         eng.set_prior(np.full(k, .5), np.zeros((k, d)), np.ones(k), np.full(k, float(d)), np.tile(np.eye(d), (k, 1, 1)),
                       np.zeros(k), 0.0)
@@ -49,7 +50,7 @@ def main():
         ms = e0.elapsed_time(e1) / iters
         flops = n * k * (4 * d * d + 4 * d + 1)
         print(f"{vname}: N={n} D={d} K={k}: {ms:.3f} ms/iter  {n*k/ms/1e6:.1f} G pt*comp/s  alg {flops/ms/1e9:.2f} TFLOP/s "
-              f"({flops/ms/1e9/37.0:.3f} of 37 TF)  X {n*d*8/ms/1e6:.1f} GB/s", flush=True)
+              f"({flops/ms/1e9/37.0:.3f} of 37 TF)  X {n*d*(8 if prec == "float64" else 4)/ms/1e6:.1f} GB/s", flush=True)
         h = eng.state.cpu().numpy()
         print("   vlhist", h[eng.off['vlhist']:eng.off['vlhist']+4], "ns", h[eng.off['ns']:eng.off['ns']+4])
 
