@@ -292,7 +292,8 @@ extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, do
                             "cudaFuncSetAttribute(small_kernel)");
         if (rc) return rc;
     }
-    const int nt = D <= 8 ? 64 : (D <= 32 ? 128 : 256);
+    // latency-bound kernel full of block barriers: one warp per component while the D x D work is tiny
+    const int nt = D <= 16 ? 32 : (D <= 32 ? 64 : (D <= 64 ? 128 : 256));
     small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol);
     return check_cuda(cudaGetLastError(), "small_kernel launch");
 }

@@ -190,53 +190,73 @@ class VBEngine:
             torch.distributed.all_reduce(self.stats, group=self.group)
 
     # ------------------------------------------------------------------ the VB loop (:860-872)
+    # begin / enqueue / poll / finish let a caller interleave several engines (concurrent restarts on CUDA streams);
+    # run() is the single-engine driver.
+    def begin(self, max_itr, tol, r_init=None):
+        """Post-init pass + ELBO (:852/:854, :860) and the first M-step; nothing is synchronised."""
+        self._max_itr, self._tol, self._launched = int(max_itr), float(tol), 0
+        with torch.cuda.device(self.device):
+            self._alloc_state(self._max_itr + 1)
+            if r_init is not None:
+                r_dev = torch.as_tensor(np.ascontiguousarray(r_init, dtype=np.float64)).to(self.device)
+                self._pass(r_in=r_dev, force=1)
+            else:
+                self._pass()
+            self._small(_lib.SMALL_ITERATE, self._max_itr, self._tol)
+
+    def enqueue(self, n_iters):
+        """Queue up to n_iters VB iterations (no-ops on the device once ctrl.done is set), then an async read of ctrl."""
+        todo = max(0, min(int(n_iters), self._max_itr - self._launched))
+        with torch.cuda.device(self.device):
+            for _ in range(todo):
+                self._pass()
+                self._small(_lib.SMALL_ITERATE, self._max_itr, self._tol)
+            self._launched += todo
+            self._host_ctrl.copy_(self.ctrl, non_blocking=True)
+        return todo
+
+    def finished(self):
+        """After the stream has been synchronised: did the device stop (converged / max_itr) or is the budget queued?"""
+        return bool(self._host_ctrl[_lib.CTRL_DONE]) or self._launched >= self._max_itr
+
+    def finish(self):
+        """-> (vl_history [1 + n_iter], converged)."""
+        with torch.cuda.device(self.device):
+            self._host_ctrl.copy_(self.ctrl, non_blocking=True)
+            o = self.off["vlhist"]
+            self._host_hist.copy_(self.state[o:o + self.hist_len], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        hc = self._host_ctrl
+        if int(hc[_lib.CTRL_ERROR]):
+            raise RuntimeError("bgmm_small: a W^-1 matrix was not positive definite (Cholesky failed)")
+        n_eval = int(hc[_lib.CTRL_ITER])
+        return self._host_hist[:n_eval].numpy().copy(), bool(hc[_lib.CTRL_CONVERGED])
+
     def run(self, max_itr, tol, r_init=None, chunk=None):
         """Post-init ELBO + up to max_itr VB iterations on the device.
 
         Returns (vl_history [1 + n_iter], converged).  `r_init`: (n_local, K) responsibilities for the
         'random_responsibility' initialisation (:734-736); otherwise the first pass is an E-step with the
         parameters loaded by set_params (:852)."""
-        max_itr = int(max_itr)
-        with torch.cuda.device(self.device):
-            self._alloc_state(max_itr + 1)
-            ctrl = self.ctrl
-            if r_init is not None:
-                r_dev = torch.as_tensor(np.ascontiguousarray(r_init, dtype=np.float64)).to(self.device)
-                self._pass(r_in=r_dev, force=1)
-            else:
-                self._pass()
-            self._small(_lib.SMALL_ITERATE, max_itr, tol)        # iter 0: post-init VL (:860) + first M-step
-            launched = 0
-            step = 4 if chunk is None else int(chunk)
-            done = max_itr == 0
-            n_eval = 1
-            while not done:
-                t0 = time.perf_counter()
-                todo = min(step, max_itr - launched)
-                for _ in range(todo):
-                    self._pass()
-                    self._small(_lib.SMALL_ITERATE, max_itr, tol)
-                launched += todo
-                self._host_ctrl.copy_(ctrl, non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
-                hc = self._host_ctrl
-                done = bool(hc[_lib.CTRL_DONE]) or launched >= max_itr
-                n_eval = int(hc[_lib.CTRL_ITER])
-                if chunk is None:
-                    dt = time.perf_counter() - t0
-                    # aim for ~30 ms between host syncs, at most 64 queued iterations
-                    per = dt / max(todo, 1)
-                    step = int(min(64, max(1, 0.03 / max(per, 1e-6))))
-            self._host_ctrl.copy_(ctrl, non_blocking=True)
-            o = self.off["vlhist"]
-            self._host_hist.copy_(self.state[o:o + self.hist_len], non_blocking=True)
+        self.begin(max_itr, tol, r_init)
+        step = 4 if chunk is None else int(chunk)
+        done = self._max_itr == 0
+        while not done:
+            t0 = time.perf_counter()
+            todo = self.enqueue(step)
             torch.cuda.current_stream(self.device).synchronize()
-            hc = self._host_ctrl
-            if int(hc[_lib.CTRL_ERROR]):
-                raise RuntimeError("bgmm_small: a W^-1 matrix was not positive definite (Cholesky failed)")
-            n_eval = int(hc[_lib.CTRL_ITER])
-            hist = self._host_hist[:n_eval].numpy().copy()
-            return hist, bool(hc[_lib.CTRL_CONVERGED])
+            done = self.finished()
+            if chunk is None:      # aim for ~30 ms between host syncs, at most 64 queued iterations
+                per = (time.perf_counter() - t0) / max(todo, 1)
+                step = int(min(64, max(1, 0.03 / max(per, 1e-6))))
+        return self.finish()
+
+    def share_data_from(self, other):
+        """Use another engine's resident X (read-only) — concurrent restarts on one GPU."""
+        self.x, self.n_local, self.n_global, self.center = other.x, other.n_local, other.n_global, other.center
+        self._put(self._view("center", self.D), self.center)
+        self.r_dev = self.lnrho_dev = self.argmax_dev = None
+        return self
 
     # ------------------------------------------------------------------ results
     def fetch_params(self):

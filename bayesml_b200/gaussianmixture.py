@@ -9,7 +9,8 @@ argument checks, hyperparameter plumbing, the RNG-consuming initialisations (so 
 reference's), restart bookkeeping and the predictive parameters.
 
 Additive, defaulted options (do not exist in the reference): `device`, `precision` ('float64' | 'float32'),
-`process_group` (torch.distributed group: rows of x are this rank's shard; statistics are all-reduced).
+`process_group` (torch.distributed group: rows of x are this rank's shard; statistics are all-reduced),
+`restart_group` (torch.distributed group: x is replicated and the `num_init` restarts are spread over the ranks).
 """
 import warnings
 
@@ -63,13 +64,15 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
     """
 
     def __init__(self, c_num_classes, c_degree, h0_alpha_vec=None, h0_m_vecs=None, h0_kappas=None, h0_nus=None,
-                 h0_w_mats=None, seed=None, *, device=None, precision="float64", process_group=None):
+                 h0_w_mats=None, seed=None, *, device=None, precision="float64", process_group=None, restart_group=None):
         self.c_degree = _check.pos_int(c_degree, 'c_degree', ParameterFormatError)
         self.c_num_classes = _check.pos_int(c_num_classes, 'c_num_classes', ParameterFormatError)
         self.rng = np.random.default_rng(seed)
         K, D = self.c_num_classes, self.c_degree
         self._device, self._precision, self._group = device, precision, process_group
+        self._restart_group = restart_group
         self._engine_obj = None
+        self._extra_engines = []
 
         # prior hyperparameters and their constants (:438-446)
         self.h0_alpha_vec = np.full(K, 0.5)
@@ -238,9 +241,8 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
     def _push_hn(self, eng):
         eng.set_params(self.hn_alpha_vec, self.hn_m_vecs, self.hn_kappas, self.hn_nus, self.hn_w_mats_inv)
 
-    def _pull_state(self, eng):
-        """Device parameter set / statistics / ELBO terms -> the numpy attributes, in place."""
-        p = eng.fetch_params()
+    def _apply_state(self, p):
+        """One restart's device result (parameter set / statistics / ELBO terms) -> the numpy attributes, in place."""
         self.hn_alpha_vec[:] = p["alpha"]
         self.hn_m_vecs[:] = p["m"]
         self.hn_kappas[:] = p["kappa"]
@@ -329,6 +331,12 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         num_init : int, number of restarts (default 10)
         tolerance : float, relative ELBO change that stops a restart (default 1e-8)
         init_type : 'subsampling' | 'random_responsibility'
+
+        The restarts are independent given their initial states, and nothing else consumes `self.rng` between them
+        (:847-859), so all initial states are drawn first (same random stream as the reference's sequential loop) and
+        the restarts then run concurrently: on several CUDA streams when one restart cannot fill the GPU, and spread
+        round-robin over the ranks of `restart_group` (x replicated).  The reference's selection rule (:873) is then
+        applied in restart order, and the same progress text is printed.
         """
         x = self._check_x(x)
         eng = self._engine()
@@ -341,9 +349,9 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
 
         best_vl = 0.0
         best = {name: np.array(getattr(self, name)) for name in _HN_NAMES}      # :838-844
-        never_converged = True
-        for i in range(num_init):
-            with eng.phase("host_init"):
+        with eng.phase("host_init"):
+            inits = []
+            for i in range(num_init):
                 self.reset_hn_params()
                 r_init = None
                 if init_type == 'subsampling':
@@ -355,18 +363,23 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
                         f'init_type={init_type} is unsupported. '
                         + 'This function supports only '
                         + '"subsampling" and "random_responsibility"')
-                self._push_hn(eng)
-            with eng.phase("vb_loop"):
-                hist, converged = eng.run(max_itr, tolerance, r_init=r_init)
+                inits.append({"alpha": self.hn_alpha_vec.copy(), "m": self.hn_m_vecs.copy(),
+                              "kappa": self.hn_kappas.copy(), "nu": self.hn_nus.copy(),
+                              "winv": self.hn_w_mats_inv.copy(), "r_init": r_init})
+        with eng.phase("vb_loop"):
+            results = self._run_restarts(eng, inits, max_itr, tolerance)
+
+        never_converged = True
+        for i, res in enumerate(results):
+            hist = res["hist"]
             # same progress text as :861, :868, :871
             print(f'\r{i}. VL: {hist[0]}', end='')
             for t in range(len(hist) - 1):
                 print(f'\r{i}. VL: {hist[t + 1]} t={t} ', end='')
-            if converged:
+            if res["converged"]:
                 never_converged = False
                 print('(converged)', end='')
-            with eng.phase("pull_state"):
-                self._pull_state(eng)
+            self._apply_state(res["state"])
             if i == 0 or self.vl > best_vl:                                      # :873 (strict: ties keep the earlier)
                 print('*')
                 best_vl = self.vl
@@ -384,6 +397,118 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         with eng.phase("final_e_step"):
             self._final_e_step(eng)                                               # :895
         return self
+
+    # ---- concurrent restarts ----
+    _STATE_KEYS = ("alpha", "m", "kappa", "nu", "w", "winv", "e_ln_pi", "e_ln_lambda_dets", "ln_b", "vl_terms", "ns",
+                   "x_bar", "s_mats")
+
+    def _restart_streams(self, eng, n_restarts):
+        """How many restarts to keep in flight on this GPU: one restart of >= one wave of tiles already fills it."""
+        tiles = max(1, -(-eng.n_local // 64))
+        return int(max(1, min(n_restarts, 148 // tiles, 16)))
+
+    def _run_restarts(self, eng, inits, max_itr, tolerance):
+        """Run every restart of `inits` (this rank's share when `restart_group` is set); -> per-restart results in order."""
+        import torch
+        rank, world = 0, 1
+        if self._restart_group is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(self._restart_group), dist.get_world_size(self._restart_group)
+        mine = [i for i in range(len(inits)) if i % world == rank]
+        results = {}
+        n_streams = self._restart_streams(eng, len(mine)) if mine else 0
+        if n_streams <= 1:
+            for i in mine:
+                ini = inits[i]
+                eng.set_params(ini["alpha"], ini["m"], ini["kappa"], ini["nu"], ini["winv"])
+                hist, conv = eng.run(max_itr, tolerance, r_init=ini["r_init"])
+                results[i] = {"hist": hist, "converged": conv, "state": self._state_of(eng)}
+        else:
+            from .engine import VBEngine
+            while len(self._extra_engines) < n_streams - 1:
+                self._extra_engines.append(VBEngine(self.c_num_classes, self.c_degree, device=eng.device,
+                                                    precision=self._precision, group=self._group))
+            slots = [(eng, torch.cuda.Stream(device=eng.device))]
+            for extra in self._extra_engines[:n_streams - 1]:
+                extra.share_data_from(eng)
+                self._push_prior(extra)
+                slots.append((extra, torch.cuda.Stream(device=eng.device)))
+            torch.cuda.current_stream(eng.device).synchronize()
+            todo, running = list(mine), {}
+
+            def start(slot):
+                e, st = slots[slot]
+                i = todo.pop(0)
+                ini = inits[i]
+                with torch.cuda.stream(st):
+                    e.set_params(ini["alpha"], ini["m"], ini["kappa"], ini["nu"], ini["winv"])
+                    e.begin(max_itr, tolerance, r_init=ini["r_init"])
+                running[slot] = i
+
+            for slot in range(len(slots)):
+                if todo:
+                    start(slot)
+            while running:
+                for slot in list(running):
+                    e, st = slots[slot]
+                    with torch.cuda.stream(st):
+                        e.enqueue(8)
+                for slot in list(running):
+                    e, st = slots[slot]
+                    st.synchronize()
+                    if e.finished():
+                        with torch.cuda.stream(st):
+                            hist, conv = e.finish()
+                            results[running[slot]] = {"hist": hist, "converged": conv, "state": self._state_of(e)}
+                        del running[slot]
+                        if todo:
+                            start(slot)
+        if world > 1:
+            results = self._gather_restarts(results, len(inits), max_itr, rank, world)
+        return [results[i] for i in range(len(inits))]
+
+    def _state_of(self, eng):
+        p = eng.fetch_params()
+        return {k: np.asarray(p[k], dtype=np.float64) for k in self._STATE_KEYS}
+
+    def _gather_restarts(self, results, n_restarts, max_itr, rank, world):
+        """All-gather the per-restart results over `restart_group` (fixed-size records, padded ELBO history)."""
+        import torch
+        import torch.distributed as dist
+        K, D = self.c_num_classes, self.c_degree
+        sizes = {"alpha": K, "m": K * D, "kappa": K, "nu": K, "w": K * D * D, "winv": K * D * D, "e_ln_pi": K,
+                 "e_ln_lambda_dets": K, "ln_b": K, "vl_terms": 8, "ns": K, "x_bar": K * D, "s_mats": K * D * D}
+        rec_len = 3 + (max_itr + 1) + sum(sizes.values())
+        per_rank = -(-n_restarts // world)
+        buf = np.zeros((per_rank, rec_len))
+        for slot, i in enumerate(i for i in range(n_restarts) if i % world == rank):
+            res = results[i]
+            h = res["hist"]
+            rec = [np.array([1.0, float(res["converged"]), float(len(h))]), np.pad(h, (0, max_itr + 1 - len(h)))]
+            rec += [res["state"][k].ravel() for k in self._STATE_KEYS]
+            buf[slot] = np.concatenate(rec)
+        t = torch.as_tensor(buf)
+        nccl = dist.get_backend(self._restart_group) == "nccl"
+        if nccl:
+            t = t.to(self._engine().device)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t, group=self._restart_group)
+        out = [o.cpu().numpy() for o in out]
+        shapes = {"alpha": (K,), "m": (K, D), "kappa": (K,), "nu": (K,), "w": (K, D, D), "winv": (K, D, D),
+                  "e_ln_pi": (K,), "e_ln_lambda_dets": (K,), "ln_b": (K,), "vl_terms": (8,), "ns": (K,), "x_bar": (K, D),
+                  "s_mats": (K, D, D)}
+        full = {}
+        for i in range(n_restarts):
+            rec = out[i % world][i // world]
+            assert rec[0] == 1.0, "restart record missing"
+            n_h = int(rec[2])
+            pos = 3 + max_itr + 1
+            state = {}
+            for k in self._STATE_KEYS:
+                state[k] = rec[pos:pos + sizes[k]].reshape(shapes[k]).copy()
+                pos += sizes[k]
+            full[i] = {"hist": rec[3:3 + n_h].copy(), "converged": bool(rec[1]), "state": state}
+        return full
 
     def _final_e_step(self, eng):
         """E-step with the current hn_* that materialises r_vecs / _ln_rho and refreshes ns, x_bar_vecs, s_mats."""

@@ -35,6 +35,14 @@ for init in ("subsampling", "random_responsibility"):
     out[init] = {"alpha": m.hn_alpha_vec.tolist(), "m": m.hn_m_vecs.tolist(), "winv": m.hn_w_mats_inv.tolist(),
                  "vl": float(m.vl), "ns": m.ns.tolist(), "r_rows": int(m.r_vecs.shape[0]),
                  "r_head": m.r_vecs[:5].tolist(), "stdout": buf.getvalue()}
+# restarts spread over the ranks (x replicated), BASELINE config C5's mode
+m = gaussianmixture.LearnModel(k, d, seed=6, device=f"cuda:{rank}", restart_group=dist.group.WORLD)
+buf = io.StringIO()
+with contextlib.redirect_stdout(buf), warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    m.update_posterior(x, max_itr=25, num_init=5)
+out["restarts"] = {"alpha": m.hn_alpha_vec.tolist(), "m": m.hn_m_vecs.tolist(), "winv": m.hn_w_mats_inv.tolist(),
+                   "vl": float(m.vl), "ns": m.ns.tolist(), "stdout": buf.getvalue()}
 with open(os.path.join(os.environ["BGMM_OUT"], f"rank{rank}.json"), "w") as f:
     json.dump(out, f)
 dist.barrier()
@@ -79,3 +87,15 @@ def test_two_gpu_sharded_fit_matches_single_gpu_and_oracle(tmp_path):
             assert np.isclose(a["vl"], float(ref.vl), rtol=1e-9)
             assert np.allclose(a["ns"], ref.ns, rtol=1e-9)
         assert np.allclose(a["r_head"], o.r_vecs[:5], rtol=1e-9, atol=1e-300)
+
+    # restarts distributed over the ranks: every rank ends in the state of the single-GPU run, bit for bit
+    a, b = ranks[0]["restarts"], ranks[1]["restarts"]
+    assert a == b
+    single = gaussianmixture.LearnModel(k, d, seed=6)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        single.update_posterior(x, max_itr=25, num_init=5)
+    assert a["stdout"] == buf.getvalue()
+    assert a["alpha"] == single.hn_alpha_vec.tolist() and a["winv"] == single.hn_w_mats_inv.tolist()
+    assert a["vl"] == float(single.vl) and a["ns"] == single.ns.tolist()

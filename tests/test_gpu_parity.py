@@ -252,3 +252,23 @@ def test_fp32_mode_against_fp64_oracle(shape):
     clear = (margin[:, -1] - margin[:, -2]) > 1e-4         # exclude numerical near-ties
     assert np.array_equal(np.argmax(m.r_vecs, axis=1)[clear], np.argmax(o.r_vecs, axis=1)[clear])
     assert clear.mean() > 0.99
+
+
+def test_high_dimension_shape_runs_on_generic_path():
+    """BASELINE config C4's shape class (D=128, K=64) at a size the oracle finishes in seconds: exercises the
+    per-component kernel with a 128x128 Cholesky in shared memory and the generic pass kernel."""
+    from bayesml_b200 import gaussianmixture
+    from oracle.gmm_vb_oracle import OracleGMM, fit
+    n, d, k = 3000, 128, 64
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(n, d)) + 3.0 * rng.normal(size=(k, d))[rng.integers(0, k, size=n)]
+    m = gaussianmixture.LearnModel(k, d, seed=1)
+    o = OracleGMM(k, d, seed=1)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m.update_posterior(x, max_itr=3, num_init=1, tolerance=0.0)
+    fit(o, x, max_itr=3, num_init=1, tolerance=0.0)
+    _close(m.vl, o.vl, what="vl")
+    for f in ("hn_alpha_vec", "hn_m_vecs", "hn_nus", "hn_w_mats_inv", "ns", "x_bar_vecs"):
+        _close(getattr(m, f), getattr(o, f), what=f)
+    assert np.array_equal(np.argmax(m.r_vecs, axis=1), np.argmax(o.r_vecs, axis=1))
