@@ -9,7 +9,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libbgmm.so")
 
 # constants mirrored from include/bgmm.h (checked against bgmm_abi_version at load time)
-ABI_VERSION = 1
+ABI_VERSION = 2
 F64, F32 = 0, 1
 PASS_AUTO, PASS_SIMPLE, PASS_DMMA, PASS_F32 = 0, 1, 2, 3
 SMALL_FEATURES, SMALL_ITERATE, SMALL_STATS = 0, 1, 2
@@ -17,7 +17,8 @@ SMALL_FEATURES, SMALL_ITERATE, SMALL_STATS = 0, 1, 2
 OFF_NAMES = ("center", "alpha0", "kappa0", "nu0", "m0", "w0inv", "lnb0", "lnc0", "params0", "params1", "stats",
              "ns", "xbar", "smats", "vlk", "vlterms", "vlhist", "ctrl", "total", "stats_len", "params_len", "pitch")
 POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb", "coef")
-CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR = range(7)
+CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR, CTRL_SEQ = range(8)
+MAX_RANKS = 16
 N_CTRL = 16
 
 _lib = None
@@ -51,7 +52,19 @@ def load():
     lib.bgmm_pass_supported.restype = i32
     lib.bgmm_pass_supported.argtypes = [i32, i32, i32, i32]
     lib.bgmm_small.restype = i32
-    lib.bgmm_small.argtypes = [i32, i32, vp, i32, i32, f64, i32, vp]
+    lib.bgmm_small.argtypes = [i32, i32, vp, i32, i32, f64, i32, vp, vp]
+    lib.bgmm_comm_block_doubles.restype = i64
+    lib.bgmm_comm_block_doubles.argtypes = [i32, i32]
+    lib.bgmm_comm_alloc.restype = i32
+    lib.bgmm_comm_alloc.argtypes = [i64, ctypes.POINTER(vp), ctypes.c_char_p]
+    lib.bgmm_comm_open.restype = i32
+    lib.bgmm_comm_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.bgmm_comm_close.restype = i32
+    lib.bgmm_comm_close.argtypes = [vp]
+    lib.bgmm_comm_free.restype = i32
+    lib.bgmm_comm_free.argtypes = [vp]
+    lib.bgmm_publish.restype = i32
+    lib.bgmm_publish.argtypes = [i32, i32, vp, vp, i32, vp]
     if lib.bgmm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libbgmm ABI {lib.bgmm_abi_version()} != binding ABI {ABI_VERSION}; rebuild the library")
     _lib = lib

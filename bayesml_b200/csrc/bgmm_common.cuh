@@ -82,6 +82,13 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
     return scratch[32];
 }
 
+// Device-resident descriptor of the peer-memory exchange (bgmm_comm.cu); mirrors the layout documented in bgmm.h.
+struct CommDesc {
+    int world, rank;
+    int64_t reserved;
+    double* xchg[BGMM_MAX_RANKS];      // exchange block of every rank as mapped in THIS process ([rank] = own block)
+};
+
 // Arguments of one pass launch (see bgmm_pass in include/bgmm.h).
 struct PassArgs {
     const void* x;

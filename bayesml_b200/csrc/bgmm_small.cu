@@ -32,8 +32,15 @@ constexpr double LN2 = 0.693147180559945309417232121458;
 constexpr double LNPI = 1.144729885849400174143427351353;
 constexpr double LN2PI = 1.837877066409345483560659472811;
 
+__device__ __forceinline__ double ld_peer(const double* p) {     // peer / exchange memory: never from a stale L1 line
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, const Layout L, const int mode,
-                                                    const int max_itr, const double tol) {
+                                                    const int max_itr, const double tol,
+                                                    const CommDesc* __restrict__ cd) {
     extern __shared__ double sm[];
     const int K = L.K, D = L.D, DD = D * D, k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
@@ -56,6 +63,38 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     const double alpha0 = st[L.alpha0 + k], kappa0 = st[L.kappa0 + k], nu0 = st[L.nu0 + k];
 
     double kn, nun, an, alpha_sum_new;
+
+    // ---- fused all-reduce over peer memory: wait for every rank's stamp, sum the published blocks in rank order ----
+    const bool fused = (cd != nullptr) && (iterate || stats_only);
+    const double* xb[BGMM_MAX_RANKS];
+    int world = 1;
+    if (fused) {
+        world = cd->world;
+        const int seq = ctrl[BGMM_CTRL_SEQ] - 1;                // the exchange published by the preceding bgmm_publish
+        const int64_t len = L.stats_len;
+        if (tid < world) {
+            const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(cd->xchg[cd->rank] + 2 * len) +
+                                             (seq & 1) * BGMM_MAX_RANKS + tid;
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            } while (v < (unsigned long long)(seq + 1));
+        }
+        __syncthreads();
+        for (int r = 0; r < world; ++r) xb[r] = cd->xchg[r] + (int64_t)(seq & 1) * len;
+        double* row = st + L.stats + (int64_t)k * L.pitch;      // this CTA owns row k of the reduced statistics
+        for (int p = tid; p < L.pitch; p += nt) {
+            double acc = 0.0;
+            for (int r = 0; r < world; ++r) acc += ld_peer(xb[r] + (int64_t)k * L.pitch + p);
+            row[p] = acc;
+        }
+        if (k == 0 && tid < 8) {
+            double acc = 0.0;
+            for (int r = 0; r < world; ++r) acc += ld_peer(xb[r] + (int64_t)K * L.pitch + tid);
+            st[L.stats + (int64_t)K * L.pitch + tid] = acc;
+        }
+        __syncthreads();
+    }
 
     if (iterate || stats_only) {
         // ---- statistics of component k from the raw moments (about the centre) ----
@@ -126,7 +165,16 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
             winv_out[e] = v;
         }
         double asum = 0.0;
-        for (int j = tid; j < K; j += nt) asum += st[L.alpha0 + j] + st[L.stats + (int64_t)j * L.pitch];
+        for (int j = tid; j < K; j += nt) {
+            double nj;
+            if (fused) {                                        // other CTAs own the other rows: sum N_j from the peers
+                nj = 0.0;
+                for (int r = 0; r < world; ++r) nj += ld_peer(xb[r] + (int64_t)j * L.pitch);
+            } else {
+                nj = st[L.stats + (int64_t)j * L.pitch];
+            }
+            asum += st[L.alpha0 + j] + nj;
+        }
         alpha_sum_new = block_sum(asum, scratch);
         if (tid == 0) { Pn[L.p_kappa + k] = kn; Pn[L.p_nu + k] = nun; Pn[L.p_alpha + k] = an; }
         for (int i = tid; i < D; i += nt) Pn[L.p_m + (int64_t)k * D + i] = mnew[i];
@@ -271,7 +319,7 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
 }  // namespace bgmm
 
 extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, double tol, int hist_len,
-                          void* stream) {
+                          const void* comm_desc, void* stream) {
     using namespace bgmm;
     if (K <= 0 || D <= 0 || state == nullptr || hist_len < 1) {
         set_error("bgmm_small: bad argument (K=%d D=%d state=%p hist_len=%d)", K, D, (void*)state, hist_len);
@@ -294,6 +342,7 @@ extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, do
     }
     // latency-bound kernel full of block barriers: one warp per component while the D x D work is tiny
     const int nt = D <= 16 ? 32 : (D <= 32 ? 64 : (D <= 64 ? 128 : 256));
-    small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol);
+    small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol,
+                                                        static_cast<const CommDesc*>(comm_desc));
     return check_cuda(cudaGetLastError(), "small_kernel launch");
 }

@@ -10,8 +10,10 @@ device; the host only syncs once per chunk of iterations to read the ELBO histor
 """
 from __future__ import annotations
 
+import ctypes
 import os
 import time
+import warnings
 
 import numpy as np
 import torch
@@ -39,7 +41,7 @@ class _Phase:
 
 
 class VBEngine:
-    def __init__(self, K, D, device=None, precision="float64", group=None, variant=_lib.PASS_AUTO):
+    def __init__(self, K, D, device=None, precision="float64", group=None, variant=_lib.PASS_AUTO, fused_comm=True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("bayesml_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -68,6 +70,61 @@ class VBEngine:
                                          device=self.device)
         self._alloc_state(2)
         self.r_dev = self.lnrho_dev = self.argmax_dev = None
+        # multi-GPU exchange: peer memory (fused into bgmm_small) when the ranks share a box, else ncclAllReduce
+        self.comm_desc = None
+        self._comm_base, self._comm_peers = None, []
+        if group is not None and fused_comm and os.environ.get("BAYESML_B200_COMM", "peer").lower() != "nccl":
+            self._setup_peer_comm()
+
+    def _setup_peer_comm(self):
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if dist.get_backend(self.group) != "nccl" or world > _lib.MAX_RANKS or world < 2:
+            return
+        lib = self.lib
+        ok = 1
+        base, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            try:
+                _lib.check(lib.bgmm_comm_alloc(lib.bgmm_comm_block_doubles(self.K, self.D), ctypes.byref(base), handle),
+                           "bgmm_comm_alloc")
+            except RuntimeError:
+                ok = 0
+            handles = [None] * world
+            dist.all_gather_object(handles, (handle.raw, ok), group=self.group)
+            ptrs = [0] * world
+            if all(h[1] for h in handles):
+                for r in range(world):
+                    if r == rank:
+                        ptrs[r] = base.value
+                        continue
+                    p = ctypes.c_void_p()
+                    if lib.bgmm_comm_open(handles[r][0], ctypes.byref(p)) != 0:
+                        ok = 0
+                        break
+                    ptrs[r] = p.value
+                    self._comm_peers.append(p.value)
+            else:
+                ok = 0
+            flag = torch.tensor([ok], device=self.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 0:
+                warnings.warn("bayesml_b200: peer-memory exchange unavailable (CUDA IPC); using ncclAllReduce")
+                return
+            self._comm_base = base.value
+            desc = np.zeros(2 + _lib.MAX_RANKS, dtype=np.int64)
+            desc[0] = world | (rank << 32)                       # int32 world, int32 rank (little endian)
+            desc[2:2 + world] = ptrs
+            self.comm_desc = torch.as_tensor(desc).to(self.device)
+            dist.barrier(group=self.group)
+
+    def close(self):
+        """Release the peer-memory mappings (optional; process exit does it too)."""
+        for p in self._comm_peers:
+            self.lib.bgmm_comm_close(p)
+        if self._comm_base:
+            self.lib.bgmm_comm_free(self._comm_base)
+        self._comm_peers, self._comm_base, self.comm_desc = [], None, None
 
     def phase(self, name):
         return _Phase(self, name)
@@ -82,9 +139,11 @@ class VBEngine:
         self.hist_len = int(hist_len)
         self.off, self.poff = _lib.layout(self.K, self.D, self.hist_len)
         self.state = torch.zeros(self.off["total"], dtype=torch.float64, device=self.device)
-        if old is not None:  # keep centre + prior + parameter sets (everything before the statistics)
+        if old is not None:  # keep centre + prior + parameter sets (everything before the statistics) + control words
             n_keep = old[1]["stats"]
             self.state[:n_keep].copy_(old[0][:n_keep])
+            oc = old[1]["ctrl"]
+            self.state[self.off["ctrl"]:self.off["ctrl"] + _lib.N_CTRL // 2].copy_(old[0][oc:oc + _lib.N_CTRL // 2])
         self._host_ctrl = torch.empty(_lib.N_CTRL, dtype=torch.int32).pin_memory()
         self._host_hist = torch.empty(self.hist_len, dtype=torch.float64).pin_memory()
 
@@ -171,12 +230,15 @@ class VBEngine:
         self._put(self._pview(0, "nu", K), nu)
         self._put(self._pview(0, "m", K * D), np.asarray(m) - self.center)
         self._put(self._pview(0, "winv", K * D * D), winv)
-        self.ctrl.zero_()
+        c = self.ctrl                                            # reset everything but the exchange sequence number
+        c[:_lib.CTRL_SEQ].zero_()
+        c[_lib.CTRL_SEQ + 1:].zero_()
         self._small(_lib.SMALL_FEATURES, 0, 0.0)
 
     def _small(self, mode, max_itr, tol):
+        comm = self.comm_desc.data_ptr() if (self.comm_desc is not None and mode != _lib.SMALL_FEATURES) else 0
         _lib.check(self.lib.bgmm_small(self.K, self.D, self.state.data_ptr(), mode, int(max_itr), float(tol),
-                                       self.hist_len, self._stream()), "bgmm_small")
+                                       self.hist_len, comm, self._stream()), "bgmm_small")
         self.small_launches += 1
 
     def _pass(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0):
@@ -186,7 +248,15 @@ class VBEngine:
                                       ptr(r_in), self.variant if r_in is None else _lib.PASS_SIMPLE, force, 0,
                                       self._stream()), "bgmm_pass")
         self.passes += 1
-        if self.group is not None:
+        self.exchange(force)
+
+    def exchange(self, force=0):
+        """The per-iteration exchange of the statistics between row shards: publish to peer memory (the reduction is
+        fused into the next bgmm_small) or, without peer access, ncclAllReduce."""
+        if self.comm_desc is not None:
+            _lib.check(self.lib.bgmm_publish(self.K, self.D, self.state.data_ptr(), self.comm_desc.data_ptr(), int(force),
+                                             self._stream()), "bgmm_publish")
+        elif self.group is not None:
             torch.distributed.all_reduce(self.stats, group=self.group)
 
     # ------------------------------------------------------------------ the VB loop (:860-872)

@@ -427,7 +427,7 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
             from .engine import VBEngine
             while len(self._extra_engines) < n_streams - 1:
                 self._extra_engines.append(VBEngine(self.c_num_classes, self.c_degree, device=eng.device,
-                                                    precision=self._precision, group=self._group))
+                                                    precision=self._precision, group=self._group, fused_comm=False))
             slots = [(eng, torch.cuda.Stream(device=eng.device))]
             for extra in self._extra_engines[:n_streams - 1]:
                 extra.share_data_from(eng)

@@ -275,6 +275,7 @@ def main():
     eng.set_params(model.hn_alpha_vec, init_h[:k * d].reshape(k, d), model.hn_kappas, model.hn_nus,
                    init_h[k * d:].reshape(k, d, d))
     big = 1 << 30
+    eng_comm = eng.comm_desc is not None
 
     def vb_iteration():
         eng._pass()
@@ -302,8 +303,7 @@ def main():
                                      eng.workspace.data_ptr(), 0, 0, 0, 0, eng.variant, 0, 0, eng._stream()), "bgmm_pass")
         pass_ev[i][1].record()
         eng.passes += 1
-        if group is not None:
-            dist.all_reduce(eng.stats, group=group)
+        eng.exchange()
         eng._small(_lib.SMALL_ITERATE, big, 0.0)
     e1.record()
     barrier()
@@ -387,7 +387,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64" if precision == "float64" else "f32", "data": "synthetic",
             "config": {"workload": f"{args.config}: GMM VB N={n_total} D={d} K={k} {precision}, rows sharded over {world} GPU(s), "
-                                   f"one all-reduce of K*(1+D+D(D+1)/2)+1 doubles per iteration" if world > 1 else
+                                   f"one exchange of K*PITCH+8 doubles per iteration ({'peer-memory, fused into bgmm_small' if eng_comm else 'ncclAllReduce'})" if world > 1 else
                                    f"{args.config}: GMM VB N={n_total} D={d} K={k} {precision}, 1 GPU",
                        "l2": f"X resident in HBM, {x_bytes / 1e6:.0f} MB per GPU per iteration (> 126 MB L2), no flush needed"
                              if x_bytes > 130e6 else "X fits in L2: cold-L2 not enforced",

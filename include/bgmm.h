@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BGMM_ABI_VERSION 1
+#define BGMM_ABI_VERSION 2
 
 /* dtype of X */
 #define BGMM_F64 0
@@ -108,6 +108,7 @@ enum {
     BGMM_CTRL_TICKET,     /* internal: last-CTA election for bgmm_small                             */
     BGMM_CTRL_PASS_TICKET,/* internal: last-CTA election for bgmm_pass                              */
     BGMM_CTRL_ERROR,      /* 1 -> a W^-1 was not positive definite (Cholesky failed)                */
+    BGMM_CTRL_SEQ,        /* number of peer-memory exchanges published so far (bgmm_publish)        */
     BGMM_N_CTRL = 16
 };
 
@@ -151,7 +152,25 @@ int bgmm_pass_supported(int K, int D, int dtype, int variant);
  *                  -> converged, done; else if iter == max_itr -> done; else M-step into params[1-cur], flip cur.
  *                  Also refreshes ns / x_bar / s_mats (s_mats[k] untouched when N_k == 0, as at :729).
  *   mode STATS   : ns / x_bar / s_mats only; parameters and control words untouched. */
-int bgmm_small(int K, int D, double* state, int mode, int max_itr, double tol, int hist_len, void* stream);
+int bgmm_small(int K, int D, double* state, int mode, int max_itr, double tol, int hist_len, const void* comm_desc,
+               void* stream);
+
+/* ---- multi-GPU exchange over NVLink peer memory (no reference counterpart: the reference is single-process) ----
+ * Row-sharded fit: the per-iteration all-reduce of state.STATS is fused into bgmm_small.  Every rank owns an exchange
+ * block  [2][stats_len] doubles | [2][BGMM_MAX_RANKS] uint64 stamps  allocated by bgmm_comm_alloc (cudaMalloc, zeroed)
+ * and mapped by its peers through CUDA IPC (bgmm_comm_open on the 64-byte handle).  `comm_desc` is a DEVICE struct
+ *   { int32 world; int32 rank; int64 reserved; double* xchg[BGMM_MAX_RANKS]; }   (xchg[rank] = own block)
+ * built by the caller.  bgmm_publish (after bgmm_pass) copies state.STATS into the own block, fences at system scope and
+ * stamps every peer; bgmm_small with comm_desc != NULL (modes ITERATE, STATS) waits for all stamps, sums the peers' blocks
+ * in rank order (bit-identical result on every rank) and stores the sums back into state.STATS.  comm_desc == NULL:
+ * state.STATS is used as is (single GPU, or all-reduced by the caller, e.g. ncclAllReduce). */
+#define BGMM_MAX_RANKS 16
+int64_t bgmm_comm_block_doubles(int K, int D);
+int bgmm_comm_alloc(int64_t doubles, void** base_out, void* ipc_handle_out /* 64 bytes, host */);
+int bgmm_comm_open(const void* ipc_handle /* 64 bytes, host */, void** peer_ptr_out);
+int bgmm_comm_close(void* peer_ptr);
+int bgmm_comm_free(void* base);
+int bgmm_publish(int K, int D, double* state, const void* comm_desc, int force, void* stream);
 
 #ifdef __cplusplus
 }

@@ -28,6 +28,7 @@ bounds = np.linspace(0, n, world + 1).astype(int)
 out = {}
 for init in ("subsampling", "random_responsibility"):
     m = gaussianmixture.LearnModel(k, d, seed=5, device=f"cuda:{rank}", process_group=dist.group.WORLD)
+    out.setdefault("comm", "peer" if m._engine().comm_desc is not None else "nccl")
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf), warnings.catch_warnings():
         warnings.simplefilter("ignore")
