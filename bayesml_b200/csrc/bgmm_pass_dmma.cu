@@ -444,25 +444,36 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
 }
 
 // Cross-CTA reduction of the per-CTA partial statistics, fully parallel and in a fixed order (deterministic):
-// out[o] = sum_b ws[b][o].  tail[1] of the statistics buffer is set to the local row count.
-__global__ void __launch_bounds__(128) reduce_partials_kernel(const double* __restrict__ ws, const int nparts,
+// out[o] = sum_b ws[b][o].  A 256-thread CTA owns 32 outputs; its 8 warps each sum one slice of the partials (short
+// dependency chains, 256-byte coalesced loads) and warp 0 adds the 8 slice sums in slice order.
+// tail[1] of the statistics buffer is set to the local row count.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ ws, const int nparts,
                                                               const int64_t len, double* __restrict__ out,
                                                               const int64_t rows_slot, const double rows,
                                                               const int accumulate, const int* __restrict__ ctrl,
                                                               const int force) {
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
-    const int64_t o = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    if (o >= len) return;
+    __shared__ double slice[8][32];
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int64_t o = (int64_t)blockIdx.x * 32 + lane;
+    const int per = (nparts + 7) / 8, b0 = sl * per, b1 = min(nparts, b0 + per);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int b = 0;
-    for (; b + 3 < nparts; b += 4) {
-        s0 += ws[(int64_t)(b + 0) * len + o];
-        s1 += ws[(int64_t)(b + 1) * len + o];
-        s2 += ws[(int64_t)(b + 2) * len + o];
-        s3 += ws[(int64_t)(b + 3) * len + o];
+    if (o < len) {
+        int b = b0;
+        for (; b + 3 < b1; b += 4) {
+            s0 += ws[(int64_t)(b + 0) * len + o];
+            s1 += ws[(int64_t)(b + 1) * len + o];
+            s2 += ws[(int64_t)(b + 2) * len + o];
+            s3 += ws[(int64_t)(b + 3) * len + o];
+        }
+        for (; b < b1; ++b) s0 += ws[(int64_t)b * len + o];
     }
-    for (; b < nparts; ++b) s0 += ws[(int64_t)b * len + o];
-    double acc = (s0 + s1) + (s2 + s3);
+    slice[sl][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (sl != 0 || o >= len) return;
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += slice[i][lane];
     if (o == rows_slot) acc = rows;
     out[o] = accumulate ? out[o] + acc : acc;
 }
@@ -519,7 +530,7 @@ static int launch_cfg(const PassArgs& a, const Layout& L, const DmmaPlan& p, cud
     const int grid = dmma_grid(a.n);
     kern<<<grid, DM_THREADS, p.smem, stream>>>(a, L);
     const int64_t len = L.stats_len;
-    reduce_partials_kernel<<<(int)((len + 127) / 128), 128, 0, stream>>>(
+    reduce_partials_kernel<<<(int)((len + 31) / 32), 256, 0, stream>>>(
         a.workspace, grid, len, a.state + L.stats, (int64_t)L.K * L.pitch + 1, (double)a.n, a.accumulate,
         reinterpret_cast<const int*>(a.state + L.ctrl), a.force);
     return check_cuda(cudaGetLastError(), "pass_dmma_kernel launch");

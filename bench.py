@@ -337,11 +337,16 @@ def main():
         traffic = tr.get(f"{args.config}_n{world}")
     except Exception:
         pass
+    if eng.lib.bgmm_pass_supported(k, d, eng.x_code, _lib.PASS_DMMA) and args.variant in ("auto", "dmma"):
+        kname = "bgmm::pass_dmma_kernel"
+    elif eng.lib.bgmm_pass_supported(k, d, eng.x_code, _lib.PASS_F32) and args.variant == "auto":
+        kname = "bgmm::pass_f32_kernel"
+    else:
+        kname = "bgmm::pass_simple_kernel"
     roofline = {
         "bound": "tensor", "achieved": ach_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
         "frac": ach_tflops / FP64_PEAK_TFLOPS, "traffic": traffic,
-        "kernel": "bgmm::pass_dmma_kernel" if eng.lib.bgmm_pass_supported(k, d, eng.x_code, _lib.PASS_DMMA)
-                  and args.variant != "simple" else "bgmm::pass_simple_kernel",
+        "kernel": kname,
         "kernel_ms": pass_ms, "kernel_share_of_step": pass_ms / ms_per_step,
         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": x_bytes,
         "peak_source": "FP64 tensor pipe (DMMA.8x8x4) measured by tools/peaks on this pool's B200 "
@@ -350,6 +355,14 @@ def main():
                 "frac": x_bytes / (pass_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
     }
+
+    if precision == "float32":
+        # fp32 mode (C3): BASELINE labels it HBM-streaming; the kernel is in fact FP32-issue bound (SURVEY.md §8d caveat),
+        # so the HBM fraction is the headline roofline and the FP32 FMA-pipe fraction is reported beside it
+        roofline.update({"bound": "hbm", "achieved": roofline["hbm"]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                         "frac": roofline["hbm"]["frac"], "peak_source": roofline["hbm"]["peak_source"],
+                         "fp32": {"achieved_tflops": ach_tflops, "peak_tflops": 73.3, "frac": ach_tflops / 73.3,
+                                  "peak_source": "FFMA2 73.3 / FFMA 70.5 TFLOP/s measured by tools/peaks (profiles/r01_peaks_b200.json)"}})
 
     # ---- e2e: the public API with a HOST array (pinned), upload + init + steps iterations + final E-step + readback ----
     e2e = None
