@@ -185,6 +185,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
 
     if (wg == 2) {
         // =========================== PRODUCER WARPGROUP ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");      // hand registers to the consumer warpgroups
         const int ptid = tid - 256;
         auto issue_tile = [&](int j) {                                    // local sub-tile j -> X stage j % NXS (full tiles only)
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)j * gridDim.x) * DM_TILE;
@@ -240,6 +241,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
         }
     } else {
         // =========================== CONSUMER WARPGROUPS ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");     // 2*128*208 + 128*88 = 64512 <= 65536 registers
         double macc[MAXNB][KB][2];
 #pragma unroll
         for (int l = 0; l < MAXNB; ++l)
@@ -284,14 +286,18 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
                     b0[kb] = lds2(eB + kb * 8 * SP + 16 * w + eo0);
                     b1[kb] = lds2(eB + kb * 8 * SP + 16 * w + eo1);
                 }
+                // the .x and .y k-steps of one LDS.128 accumulate into different sets: whatever order ptxas picks,
+                // two consecutive DMMAs never depend on each other (DMMA latency ~29 cycles, issue interval 16)
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) dmma(acc[w & 1][kb][0], acc[w & 1][kb][1], a0.x, b0[kb].x);
+                for (int kb = 0; kb < KB; ++kb) {
+                    dmma(acc[0][kb][0], acc[0][kb][1], a0.x, b0[kb].x);
+                    dmma(acc[1][kb][0], acc[1][kb][1], a0.y, b0[kb].y);
+                }
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) dmma(acc[w & 1][kb][0], acc[w & 1][kb][1], a0.y, b0[kb].y);
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) dmma(acc[w & 1][kb][0], acc[w & 1][kb][1], a1.x, b1[kb].x);
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) dmma(acc[w & 1][kb][0], acc[w & 1][kb][1], a1.y, b1[kb].y);
+                for (int kb = 0; kb < KB; ++kb) {
+                    dmma(acc[0][kb][0], acc[0][kb][1], a1.x, b1[kb].x);
+                    dmma(acc[1][kb][0], acc[1][kb][1], a1.y, b1[kb].y);
+                }
             }
             double lr[KB][2];
 #pragma unroll
