@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libbgmm.so")
 # constants mirrored from include/bgmm.h (checked against bgmm_abi_version at load time)
 ABI_VERSION = 2
 F64, F32 = 0, 1
-PASS_AUTO, PASS_SIMPLE, PASS_DMMA, PASS_F32 = 0, 1, 2, 3
+PASS_AUTO, PASS_SIMPLE, PASS_DMMA, PASS_F32, PASS_LARGE = 0, 1, 2, 3, 4
 SMALL_FEATURES, SMALL_ITERATE, SMALL_STATS = 0, 1, 2
 
 OFF_NAMES = ("center", "alpha0", "kappa0", "nu0", "m0", "w0inv", "lnb0", "lnc0", "params0", "params1", "stats",
@@ -51,6 +51,8 @@ def load():
     lib.bgmm_pass.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.bgmm_pass_supported.restype = i32
     lib.bgmm_pass_supported.argtypes = [i32, i32, i32, i32]
+    lib.bgmm_pass_resolve.restype = i32
+    lib.bgmm_pass_resolve.argtypes = [i32, i32, i32, i32, i32]
     lib.bgmm_small.restype = i32
     lib.bgmm_small.argtypes = [i32, i32, vp, i32, i32, f64, i32, vp, vp]
     lib.bgmm_comm_block_doubles.restype = i64

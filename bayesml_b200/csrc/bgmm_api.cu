@@ -28,6 +28,9 @@ int64_t dmma_workspace_doubles(int K, int D);
 bool f32_supported(int K, int D, int dtype);
 int launch_pass_f32(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream);
 int64_t f32_workspace_doubles(int K, int D);
+bool large_supported(int K, int D, int dtype);
+int launch_pass_large(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream);
+int64_t large_workspace_doubles(int K, int D);
 
 // ---- data preparation ----
 constexpr int PREP_THREADS = 256;
@@ -100,6 +103,8 @@ extern "C" int64_t bgmm_workspace_doubles(int K, int D) {
     if (wd > w) w = wd;
     const int64_t wf = f32_workspace_doubles(K, D);
     if (wf > w) w = wf;
+    const int64_t wl = large_workspace_doubles(K, D);
+    if (wl > w) w = wl;
     const int64_t wc = colsum_stride(D);
     if (wc > w) w = wc;
     return w;
@@ -147,7 +152,17 @@ extern "C" int bgmm_pass_supported(int K, int D, int dtype, int variant) {
     if (K <= 0 || D <= 0 || (dtype != BGMM_F64 && dtype != BGMM_F32)) return 0;
     if (variant == BGMM_PASS_DMMA) return dmma_supported(K, D, dtype) ? 1 : 0;
     if (variant == BGMM_PASS_F32) return f32_supported(K, D, dtype) ? 1 : 0;
+    if (variant == BGMM_PASS_LARGE) return large_supported(K, D, dtype) ? 1 : 0;
     return variant == BGMM_PASS_SIMPLE || variant == BGMM_PASS_AUTO;
+}
+
+extern "C" int bgmm_pass_resolve(int K, int D, int dtype, int variant, int has_r_in) {
+    if (variant != BGMM_PASS_AUTO) return variant;
+    if (has_r_in) return BGMM_PASS_SIMPLE;
+    if (dmma_supported(K, D, dtype)) return BGMM_PASS_DMMA;
+    if (large_supported(K, D, dtype)) return BGMM_PASS_LARGE;
+    if (f32_supported(K, D, dtype)) return BGMM_PASS_F32;
+    return BGMM_PASS_SIMPLE;
 }
 
 extern "C" int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, double* state, double* workspace,
@@ -160,10 +175,10 @@ extern "C" int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, doub
     }
     PassArgs a{x, n, state, workspace, r_out, lnrho_out, argmax_out, r_in, force, accumulate};
     cudaStream_t s = (cudaStream_t)stream;
-    if (variant == BGMM_PASS_AUTO) {
-        if (r_in == nullptr && dmma_supported(K, D, dtype)) variant = BGMM_PASS_DMMA;
-        else if (r_in == nullptr && f32_supported(K, D, dtype)) variant = BGMM_PASS_F32;
-        else variant = BGMM_PASS_SIMPLE;
+    variant = bgmm_pass_resolve(K, D, dtype, variant, r_in != nullptr);
+    if (variant == BGMM_PASS_LARGE) {
+        if (r_in != nullptr) { set_error("bgmm_pass: LARGE variant does not take r_in"); return BGMM_ENOSUP; }
+        return launch_pass_large(a, K, D, dtype, s);
     }
     if (variant == BGMM_PASS_F32) {
         if (r_in != nullptr || !f32_supported(K, D, dtype)) {

@@ -102,6 +102,9 @@ struct PassArgs {
     int force, accumulate;
 };
 
+// sum of `nparts` per-CTA partial statistics buffers (workspace) into state.STATS, fixed order (bgmm_pass_dmma.cu)
+void launch_reduce_partials(const PassArgs& a, const Layout& L, int nparts, cudaStream_t stream);
+
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 

@@ -27,6 +27,7 @@
 // that makes every fragment load (LDS.128 by quarter-warp, LDS.64 by half-warp) bank-conflict free.  All fragment
 // addresses are loop-invariant pointers plus immediates.
 #include "bgmm_common.cuh"
+#include "bgmm_mma.cuh"
 #include <math.h>
 
 namespace bgmm {
@@ -36,18 +37,6 @@ constexpr int DM_TILE = 32;          // samples per sub-tile = 4 m-blocks (one p
 constexpr int DM_NXS = 4;            // stages of the X ring (TMA)
 constexpr int DM_XPAD = 4;           // doubles of slack after each X stage (vector loads past the last row)
 constexpr int DM_MAXG = 64;          // entries of the Phi-expansion group table
-
-__device__ __forceinline__ void dmma(double& c0, double& c1, const double a, const double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// element (row, physical column c) of a swizzled tile with row pitch `pitch` doubles (pitch % 16 == 0)
-__device__ __forceinline__ int swz(int row, int c, int pitch) {
-    return row * pitch + (c ^ (((row & 1) << 3) | ((row & 2) << 1)));
-}
-// logical feature -> physical column
-__device__ __forceinline__ int phys_col(int p) { return (p & ~7) | ((p & 3) << 1) | ((p >> 2) & 1); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,38 +60,10 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ int fsw(int row) { return ((row & 1) << 3) | ((row & 2) << 1); }
-__device__ __forceinline__ double2 lds2(const double* p) { return *reinterpret_cast<const double2*>(p); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
-// exp(z) for finite z <= 0, branch-free: z = n ln2 + f, |f| <= ln2/2, degree-12 Taylor (truncation 1.7e-16 relative),
-// scaled by adding n to the exponent field.  Below z = -700 the result is flushed to 0 (true value < 1e-304).
-__device__ __forceinline__ double exp_nonpos(double z) {
-    const double magic = 6755399441055744.0;                    // 1.5 * 2^52: rint() by addition
-    const double t = fma(z, 1.4426950408889634074, magic);
-    const int n = __double2loint(t);
-    const double nd = t - magic;
-    double f = fma(nd, -6.93147180369123816490e-01, z);         // ln2 split (Cody-Waite)
-    f = fma(nd, -1.90821492927058770002e-10, f);
-    double p = 1.0 / 479001600.0;
-    p = fma(p, f, 1.0 / 39916800.0);
-    p = fma(p, f, 1.0 / 3628800.0);
-    p = fma(p, f, 1.0 / 362880.0);
-    p = fma(p, f, 1.0 / 40320.0);
-    p = fma(p, f, 1.0 / 5040.0);
-    p = fma(p, f, 1.0 / 720.0);
-    p = fma(p, f, 1.0 / 120.0);
-    p = fma(p, f, 1.0 / 24.0);
-    p = fma(p, f, 1.0 / 6.0);
-    p = fma(p, f, 0.5);
-    p = fma(p, f, 1.0);
-    p = fma(p, f, 1.0);
-    const double r = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-    return z < -700.0 ? 0.0 : r;
-}
 
 template <int KB, int SP, int NPS>
 __global__ void __launch_bounds__(DM_THREADS, 1)
@@ -485,6 +446,13 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 }
 
 // ---- host side ----
+void launch_reduce_partials(const PassArgs& a, const Layout& L, int nparts, cudaStream_t stream) {
+    const int64_t len = L.stats_len;
+    reduce_partials_kernel<<<(int)((len + 31) / 32), 256, 0, stream>>>(
+        a.workspace, nparts, len, a.state + L.stats, (int64_t)L.K * L.pitch + 1, (double)a.n, a.accumulate,
+        reinterpret_cast<const int*>(a.state + L.ctrl), a.force);
+}
+
 struct DmmaPlan {
     bool ok;
     int KB, SP, RP, NPS;
@@ -535,10 +503,7 @@ static int launch_cfg(const PassArgs& a, const Layout& L, const DmmaPlan& p, cud
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_dmma)");
     const int grid = dmma_grid(a.n);
     kern<<<grid, DM_THREADS, p.smem, stream>>>(a, L);
-    const int64_t len = L.stats_len;
-    reduce_partials_kernel<<<(int)((len + 31) / 32), 256, 0, stream>>>(
-        a.workspace, grid, len, a.state + L.stats, (int64_t)L.K * L.pitch + 1, (double)a.n, a.accumulate,
-        reinterpret_cast<const int*>(a.state + L.ctrl), a.force);
+    launch_reduce_partials(a, L, grid, stream);
     return check_cuda(cudaGetLastError(), "pass_dmma_kernel launch");
 }
 

@@ -1,0 +1,341 @@
+// bgmm_pass, large K*P regime (BGMM_PASS_LARGE): fp64, any D <= 128, K <= 64 — BASELINE configs C4 (D=128, K=64) and
+// C5 (D=32, K=16), where the K x P statistics accumulators (P = 1 + D + D(D+1)/2) no longer fit on one SM.
+//
+// Two tiled GEMM kernels on the FP64 tensor pipe (mma.sync.m8n8k4.f64 = DMMA.8x8x4), the feature tile Phi generated on the
+// fly in 64-column chunks from the X tile held in shared memory (Phi itself never exists in HBM):
+//   e_large_kernel : ln rho[64 rows][K] = sum over chunks Phi_chunk . coef_chunk^T  (coefficient chunks streamed from L2),
+//                    softmax in the accumulator fragments, entropy term, r written to HBM ([N][K] fp64, the only
+//                    intermediate that leaves the chip: K*8 bytes per sample against (D^2+3D) K flops),
+//   m_large_kernel : raw[K][128-feature chunk] += R^T . Phi_chunk, output-stationary: a CTA owns one feature chunk for a
+//                    contiguous range of rows (grid = chunks x row splits), accumulators in registers,
+// then reduce_partials_kernel sums the row splits in a fixed order (deterministic).
+// Same shared-memory fragment layout (k-step-pair permutation + XOR swizzle) as the fused kernel (bgmm_mma.cuh).
+// Replaces `_update_q_z` :772-784, `_calc_n_x_bar_s` :725-732, `xlogy` :704 of the reference GMM file for these shapes.
+#include "bgmm_common.cuh"
+#include "bgmm_mma.cuh"
+#include <math.h>
+
+namespace bgmm {
+
+constexpr int LG_THREADS = 256;
+constexpr int LG_ETILE = 64;      // rows per E tile (8 m-blocks, one per warp)
+constexpr int LG_CW = 64;         // E: feature columns per chunk
+constexpr int LG_MSUB = 32;       // M: rows per step
+constexpr int LG_MCW = 128;       // M: feature columns owned by one CTA
+
+// logical feature p -> kind/indices: 0 constant, 1 linear (i), 2 quadratic (i >= j), 3 padding (zero)
+__device__ __forceinline__ void feat_decode(int p, int D, int P, int& kind, int& i, int& j) {
+    i = 0; j = 0;
+    if (p >= P) { kind = 3; return; }
+    if (p == 0) { kind = 0; return; }
+    if (p <= D) { kind = 1; i = p - 1; return; }
+    const int q = p - 1 - D;
+    int r = (int)((sqrtf(8.0f * q + 1.0f) - 1.0f) * 0.5f);
+    while (r * (r + 1) / 2 > q) --r;
+    while ((r + 1) * (r + 2) / 2 <= q) ++r;
+    kind = 2; i = r; j = q - r * (r + 1) / 2;
+}
+__device__ __forceinline__ double feat_value(int kind, int i, int j, const double* xr) {
+    return kind == 2 ? xr[i] * xr[j] : (kind == 1 ? xr[i] : (kind == 0 ? 1.0 : 0.0));
+}
+
+template <int KB>
+__global__ void __launch_bounds__(LG_THREADS, 1)
+e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int K = L.K, D = L.D, P = L.P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
+    if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
+    const double* __restrict__ coef_g = a.state + L.params[ctrl[BGMM_CTRL_CUR]] + L.p_coef;
+    const double* __restrict__ x = static_cast<const double*>(a.x);
+
+    double* phiS = reinterpret_cast<double*>(smem_raw);        // [64][64] swizzled
+    double* coefS = phiS + LG_ETILE * LG_CW;                   // [8*KB][64] swizzled
+    double* xs = coefS + 8 * KB * LG_CW;                       // [64][D]
+    double* red = xs + LG_ETILE * D;                           // [40]
+
+    const int nchunk = (P + LG_CW - 1) / LG_CW;
+    const int64_t ntiles = (a.n + LG_ETILE - 1) / LG_ETILE;
+    const int fg = fsw(g);
+    const int lrow = 8 * warp + g;
+    const double* eA = phiS + lrow * LG_CW;
+    const double* eB = coefS + g * LG_CW;
+    const int eo0 = (2 * q) ^ fg, eo1 = (8 + 2 * q) ^ fg;
+    const int fcol = tid & (LG_CW - 1), frow0 = tid >> 6;      // Phi generation: one column, rows frow0 + 4s
+    const int fphys = phys_col(fcol);
+    double ent = 0.0, sprod = 1.0;
+    int it = 0;
+
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int64_t row0 = t * LG_ETILE;
+        const int rows = (int)min((int64_t)LG_ETILE, a.n - row0);
+        __syncthreads();
+        for (int e = tid; e < LG_ETILE * D; e += LG_THREADS) xs[e] = (e < rows * D) ? x[row0 * D + e] : 0.0;
+        double acc[2][KB][2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) { acc[m][kb][0] = 0.0; acc[m][kb][1] = 0.0; }
+
+        for (int c = 0; c < nchunk; ++c) {
+            __syncthreads();                                   // xs ready (c == 0) / previous chunk's GEMM finished
+            int kind, fi, fj;
+            feat_decode(LG_CW * c + fcol, D, P, kind, fi, fj);
+#pragma unroll 4
+            for (int s = 0; s < LG_ETILE / 4; ++s) {
+                const int r = frow0 + 4 * s;
+                phiS[r * LG_CW + (fphys ^ fsw(r))] = feat_value(kind, fi, fj, xs + r * D);
+            }
+            for (int e = tid; e < 8 * KB * LG_CW; e += LG_THREADS) {
+                const int k = e >> 6, f2 = e & (LG_CW - 1), p2 = LG_CW * c + f2;
+                double v = 0.0;
+                if (k < K) { if (p2 < P) v = coef_g[(int64_t)k * L.pitch + p2]; }
+                else if (p2 == 0) v = -1.0e300;                // padded components: r == 0 exactly
+                coefS[k * LG_CW + (phys_col(f2) ^ fsw(k))] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < LG_CW / 16; ++w) {
+                const double2 a0 = lds2(eA + 16 * w + eo0), a1 = lds2(eA + 16 * w + eo1);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    const double2 b0 = lds2(eB + kb * 8 * LG_CW + 16 * w + eo0);
+                    const double2 b1 = lds2(eB + kb * 8 * LG_CW + 16 * w + eo1);
+                    dmma(acc[0][kb][0], acc[0][kb][1], a0.x, b0.x);
+                    dmma(acc[1][kb][0], acc[1][kb][1], a0.y, b0.y);
+                    dmma(acc[0][kb][0], acc[0][kb][1], a1.x, b1.x);
+                    dmma(acc[1][kb][0], acc[1][kb][1], a1.y, b1.y);
+                }
+            }
+        }
+        double lr[KB][2];
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+            lr[kb][0] = acc[0][kb][0] + acc[1][kb][0];
+            lr[kb][1] = acc[0][kb][1] + acc[1][kb][1];
+        }
+        // ---- softmax over k for row lrow; this thread holds components 8kb + 2q + {0,1} ----
+        const int64_t grow = row0 + lrow;
+        const bool valid = lrow < rows;
+        double mx = -INFINITY;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) mx = fmax(mx, fmax(lr[kb][0], lr[kb][1]));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        if (a.lnrho_out != nullptr && valid) {
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = 8 * kb + 2 * q + e;
+                    if (k < K) a.lnrho_out[grow * K + k] = lr[kb][e];
+                }
+        }
+        double sum = 0.0, dot = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double z = lr[kb][e] - mx;
+                const double ex = exp_nonpos(z);
+                lr[kb][e] = ex;
+                sum += ex;
+                dot = fma(ex, z, dot);
+            }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+        const double inv = valid ? 1.0 / sum : 0.0;
+        if (valid && q == 0) { ent = fma(dot, inv, ent); sprod *= sum; }
+        if ((it & 7) == 7) { ent -= log(sprod); sprod = 1.0; }
+        int best = 0x7fffffff;
+        double bestv = -1.0;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double r = lr[kb][e] * inv;
+                const int k = 8 * kb + 2 * q + e;
+                if (r > bestv) { bestv = r; best = k; }
+                if (valid && k < K) a.r_out[grow * K + k] = r;      // r_out is mandatory in this regime (the M kernel's input)
+            }
+        if (a.argmax_out != nullptr) {
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, best, o);
+                if (ov > bestv || (ov == bestv && ok < best)) { bestv = ov; best = ok; }
+            }
+            if (valid && q == 0) a.argmax_out[grow] = best;
+        }
+    }
+    ent -= log(sprod);
+    ent = block_sum(ent, red);
+    if (tid == 0) ews[blockIdx.x] = ent;
+}
+
+template <int KB>
+__global__ void __launch_bounds__(LG_THREADS, 2)
+m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews, const int n_ews, const int nsplit) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int RP = (8 * KB < 16) ? 16 : 8 * KB;
+    const int K = L.K, D = L.D, P = L.P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
+    if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
+    const double* __restrict__ x = static_cast<const double*>(a.x);
+    const double* __restrict__ rws = a.r_out;
+
+    double* phiS = reinterpret_cast<double*>(smem_raw);        // [32][128] swizzled
+    double* rS = phiS + LG_MSUB * LG_MCW;                      // [32][RP] swizzled
+    double* xs = rS + LG_MSUB * RP;                            // [32][D]
+
+    const int cx = blockIdx.x, ry = blockIdx.y;
+    const int64_t nsub = (a.n + LG_MSUB - 1) / LG_MSUB;
+    const int64_t per = (nsub + nsplit - 1) / nsplit;
+    const int64_t s_begin = ry * per, s_end = min(nsub, s_begin + per);
+
+    // this thread's Phi column (fixed for the whole kernel) and rows r0 + 2s
+    const int fcol = tid & (LG_MCW - 1), frow0 = tid >> 7;
+    int kind, fi, fj;
+    feat_decode(LG_MCW * cx + fcol, D, P, kind, fi, fj);
+    const int fphys = phys_col(fcol);
+    for (int e = tid; e < LG_MSUB * RP; e += LG_THREADS) rS[e] = 0.0;     // padded components stay zero
+
+    double macc[2][KB][2];
+#pragma unroll
+    for (int l = 0; l < 2; ++l)
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) { macc[l][kb][0] = 0.0; macc[l][kb][1] = 0.0; }
+    const int fq = fsw(q);
+    const double* mR = rS + q * RP + ((2 * g) ^ fq);
+    const double* mP0 = phiS + q * LG_MCW + ((8 * (2 * warp) + g) ^ fq);
+    const double* mP1 = phiS + q * LG_MCW + ((8 * (2 * warp + 1) + g) ^ fq);
+
+    for (int64_t sb = s_begin; sb < s_end; ++sb) {
+        const int64_t row0 = sb * LG_MSUB;
+        const int rows = (int)min((int64_t)LG_MSUB, a.n - row0);
+        __syncthreads();                                       // previous step's GEMM finished
+        for (int e = tid; e < LG_MSUB * D; e += LG_THREADS) xs[e] = (e < rows * D) ? x[row0 * D + e] : 0.0;
+        for (int e = tid; e < LG_MSUB * K; e += LG_THREADS) {
+            const int r = e / K, k = e - r * K;
+            const double v = (r < rows) ? rws[(row0 + r) * K + k] : 0.0;
+            const int kb = k >> 3, cc = k & 7;
+            rS[r * RP + ((16 * (kb >> 1) + 2 * cc + (kb & 1)) ^ fsw(r))] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int s = 0; s < LG_MSUB / 2; ++s) {
+            const int r = frow0 + 2 * s;
+            phiS[r * LG_MCW + (fphys ^ fsw(r))] = feat_value(kind, fi, fj, xs + r * D);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < LG_MSUB / 4; ++ks) {
+            double ra[KB];
+            if constexpr (KB >= 2) {
+#pragma unroll
+                for (int v = 0; v < KB / 2; ++v) {
+                    const double2 r2 = lds2(mR + ks * 4 * RP + 16 * v);
+                    ra[2 * v] = r2.x;
+                    ra[2 * v + 1] = r2.y;
+                }
+            } else {
+                ra[0] = mR[ks * 4 * RP];
+            }
+            const double b0 = mP0[ks * 4 * LG_MCW], b1 = mP1[ks * 4 * LG_MCW];
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                dmma(macc[0][kb][0], macc[0][kb][1], ra[kb], b0);
+                dmma(macc[1][kb][0], macc[1][kb][1], ra[kb], b1);
+            }
+        }
+    }
+
+    // ---- partial of this row split (logical layout [K][pitch]); split 0 also carries the entropy term ----
+    const int64_t len = L.stats_len;
+    double* part = a.workspace + (int64_t)ry * len;
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const int b = 2 * warp + l;
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 8 * kb + g;
+                const int p = LG_MCW * cx + 8 * b + 4 * e + q;          // physical 8b + 2q + e <-> logical 8b + 4e + q
+                if (k < K && p < L.pitch) part[(int64_t)k * L.pitch + p] = macc[l][kb][e];
+            }
+    }
+    if (cx == 0 && tid < 8) {
+        double v = 0.0;
+        if (tid == 0 && ry == 0)
+            for (int i = 0; i < n_ews; ++i) v += ews[i];                // fixed order: deterministic
+        part[(int64_t)K * L.pitch + tid] = v;
+    }
+}
+
+// ---- host side ----
+static int large_kb(int K) { return K <= 8 ? 1 : (K <= 16 ? 2 : (K <= 32 ? 4 : 8)); }
+
+bool large_supported(int K, int D, int dtype) { return dtype == BGMM_F64 && K >= 1 && K <= 64 && D >= 1 && D <= 128; }
+
+static void large_plan(int K, int D, int64_t n, int& grid_e, int& n_chunks, int& nsplit) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t ntiles = (n + LG_ETILE - 1) / LG_ETILE;
+    grid_e = (int)(ntiles < 1 ? 1 : (ntiles < sms ? ntiles : sms));
+    n_chunks = (feat_pitch(D) + LG_MCW - 1) / LG_MCW;
+    const int64_t nsub = (n + LG_MSUB - 1) / LG_MSUB;
+    int64_t s = (2 * sms + n_chunks - 1) / n_chunks;                    // about two resident waves of CTAs
+    if (s > 64) s = 64;
+    if (s > nsub) s = nsub;
+    if (s < 1) s = 1;
+    nsplit = (int)s;
+}
+
+int64_t large_workspace_doubles(int K, int D) {
+    if (K > 64 || D > 128) return 0;
+    return (int64_t)64 * ((int64_t)K * feat_pitch(D) + 8) + 256;        // <= 64 row splits + E-kernel entropy partials
+}
+
+template <int KB>
+static int launch_large_t(const PassArgs& a, const Layout& L, cudaStream_t stream) {
+    int grid_e, n_chunks, nsplit;
+    large_plan(L.K, L.D, a.n, grid_e, n_chunks, nsplit);
+    const int64_t len = L.stats_len;
+    double* ews = a.workspace + (int64_t)64 * len;
+    const size_t smem_e = sizeof(double) * ((size_t)LG_ETILE * LG_CW + (size_t)8 * KB * LG_CW + (size_t)LG_ETILE * L.D + 40) + 128;
+    constexpr int RP = (8 * KB < 16) ? 16 : 8 * KB;
+    const size_t smem_m = sizeof(double) * ((size_t)LG_MSUB * LG_MCW + (size_t)LG_MSUB * RP + (size_t)LG_MSUB * L.D) + 128;
+    cudaError_t e = cudaFuncSetAttribute(e_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(e_large)");
+    e = cudaFuncSetAttribute(m_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(m_large)");
+    e_large_kernel<KB><<<grid_e, LG_THREADS, smem_e, stream>>>(a, L, ews);
+    m_large_kernel<KB><<<dim3(n_chunks, nsplit), LG_THREADS, smem_m, stream>>>(a, L, ews, grid_e, nsplit);
+    launch_reduce_partials(a, L, nsplit, stream);
+    return check_cuda(cudaGetLastError(), "pass_large launch");
+}
+
+int launch_pass_large(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream) {
+    if (!large_supported(K, D, dtype)) {
+        set_error("bgmm_pass(large): unsupported shape K=%d D=%d dtype=%d", K, D, dtype);
+        return BGMM_ENOSUP;
+    }
+    if (a.r_out == nullptr) {
+        set_error("bgmm_pass(large): r_out ([n][K] float64) is required in this regime (it is the M kernel's input)");
+        return BGMM_EINVAL;
+    }
+    const Layout L = make_layout(K, D, 1);
+    switch (large_kb(K)) {
+        case 1: return launch_large_t<1>(a, L, stream);
+        case 2: return launch_large_t<2>(a, L, stream);
+        case 4: return launch_large_t<4>(a, L, stream);
+        default: return launch_large_t<8>(a, L, stream);
+    }
+}
+
+}  // namespace bgmm

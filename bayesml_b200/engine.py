@@ -54,7 +54,7 @@ class VBEngine:
         self.group = group
         env = os.environ.get("BAYESML_B200_PASS_VARIANT", "").lower()     # debugging / tests: force a kernel variant
         if env:
-            variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "f32": _lib.PASS_F32}[env]
+            variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "f32": _lib.PASS_F32, "large": _lib.PASS_LARGE}[env]
         self.variant = variant
         self.hist_len = 0
         self.state = None
@@ -70,6 +70,7 @@ class VBEngine:
                                          device=self.device)
         self._alloc_state(2)
         self.r_dev = self.lnrho_dev = self.argmax_dev = None
+        self._r_scratch = None
         # multi-GPU exchange: peer memory (fused into bgmm_small) when the ranks share a box, else ncclAllReduce
         self.comm_desc = None
         self._comm_base, self._comm_peers = None, []
@@ -243,6 +244,12 @@ class VBEngine:
 
     def _pass(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0):
         ptr = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731
+        if r_out is None and r_in is None and self.lib.bgmm_pass_resolve(
+                self.K, self.D, self.x_code, self.variant, 0) == _lib.PASS_LARGE:
+            # large K*P regime: r is the hand-over between the E and the M kernel and lives in HBM ([n][K] fp64)
+            if self._r_scratch is None or self._r_scratch.shape[0] != self.n_local:
+                self._r_scratch = torch.empty((self.n_local, self.K), dtype=torch.float64, device=self.device)
+            r_out = self._r_scratch
         _lib.check(self.lib.bgmm_pass(ptr(self.x), self.n_local, self.K, self.D, self.x_code, self.state.data_ptr(),
                                       self.workspace.data_ptr(), ptr(r_out), ptr(lnrho_out), ptr(argmax_out),
                                       ptr(r_in), self.variant if r_in is None else _lib.PASS_SIMPLE, force, 0,

@@ -50,6 +50,8 @@ extern "C" {
 #define BGMM_PASS_SIMPLE 1 /* generic scalar-FMA kernel: any K, D */
 #define BGMM_PASS_DMMA 2   /* fp64 tensor-pipe kernel (mma.sync.m8n8k4.f64): K*PITCH accumulators on chip */
 #define BGMM_PASS_F32 3    /* fp32-mode streaming kernel: X float32, D <= 3, K <= 8 (fp64 accumulation of partials) */
+#define BGMM_PASS_LARGE 4  /* fp64 large K*P regime (D <= 128, K <= 64): E kernel (r -> HBM) + output-stationary M kernel;
+                              needs r_out != NULL */
 
 /* bgmm_small `mode` */
 #define BGMM_SMALL_FEATURES 0 /* features + coef of params[cur] from (alpha, m, kappa, nu, W^-1); no statistics used */
@@ -141,8 +143,10 @@ int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, double* state, 
               double* r_out, double* lnrho_out, int32_t* argmax_out, const double* r_in,
               int variant, int force, int accumulate, void* stream);
 
-/* 1 when `variant` (BGMM_PASS_SIMPLE / BGMM_PASS_DMMA) can run this shape, else 0 */
+/* 1 when `variant` (BGMM_PASS_SIMPLE / _DMMA / _F32 / _LARGE) can run this shape, else 0 */
 int bgmm_pass_supported(int K, int D, int dtype, int variant);
+/* the concrete variant BGMM_PASS_AUTO resolves to (has_r_in: statistics of given responsibilities) */
+int bgmm_pass_resolve(int K, int D, int dtype, int variant, int has_r_in);
 
 /* bgmm_small: everything that is O(K D^3): replaces `_update_q_mu_lambda` (:758-770), `_update_q_pi` (:741-743),
  *   `_calc_q_pi_features` (:738-739), `_calc_q_lambda_features` (:745-756), the K-sized terms of `_calc_vl`

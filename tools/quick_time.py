@@ -26,7 +26,7 @@ def main():
     x = synth(n, d, k, dtype=torch.float64 if prec == "float64" else torch.float32)
     xh_sub = x[:200000].double().cpu().numpy()
     for vname in variants:
-        code = {"simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "auto": 0, "f32": _lib.PASS_F32}[vname]
+        code = {"simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "auto": 0, "f32": _lib.PASS_F32, "large": _lib.PASS_LARGE}[vname]
         if not _lib.load().bgmm_pass_supported(k, d, _lib.F64 if prec == "float64" else _lib.F32, code):
             print(vname, "unsupported"); continue
         eng = VBEngine(k, d, variant=code, precision=prec)
