@@ -243,6 +243,11 @@ class VBEngine:
         self.small_launches += 1
 
     def _pass(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0):
+        self.pass_only(r_out, lnrho_out, argmax_out, r_in, force)
+        self.exchange(force)
+
+    def pass_only(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0):
+        """One bgmm_pass launch (E-step + local statistics) without the cross-rank exchange."""
         ptr = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731
         if r_out is None and r_in is None and self.lib.bgmm_pass_resolve(
                 self.K, self.D, self.x_code, self.variant, 0) == _lib.PASS_LARGE:
@@ -255,7 +260,6 @@ class VBEngine:
                                       ptr(r_in), self.variant if r_in is None else _lib.PASS_SIMPLE, force, 0,
                                       self._stream()), "bgmm_pass")
         self.passes += 1
-        self.exchange(force)
 
     def exchange(self, force=0):
         """The per-iteration exchange of the statistics between row shards: publish to peer memory (the reduction is

@@ -217,7 +217,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", default="auto", choices=["auto", "simple", "dmma"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "simple", "dmma", "f32", "large"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -247,7 +247,8 @@ def main():
     xdtype = torch.float64 if precision == "float64" else torch.float32
     x_dev = synth_device(n_local, d, k, 1234 + idx, rank, device, xdtype)
 
-    variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA}[args.variant]
+    variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "f32": _lib.PASS_F32,
+               "large": _lib.PASS_LARGE}[args.variant]
     eng = VBEngine(k, d, device=device, precision=precision, group=group, variant=variant)
     eng.load_data(x_dev)                       # centres into the engine's own buffer
     del x_dev
@@ -299,10 +300,8 @@ def main():
     e0.record()
     for i in range(args.steps):
         pass_ev[i][0].record()
-        _lib.check(eng.lib.bgmm_pass(eng.x.data_ptr(), eng.n_local, k, d, eng.x_code, eng.state.data_ptr(),
-                                     eng.workspace.data_ptr(), 0, 0, 0, 0, eng.variant, 0, 0, eng._stream()), "bgmm_pass")
+        eng.pass_only()
         pass_ev[i][1].record()
-        eng.passes += 1
         eng.exchange()
         eng._small(_lib.SMALL_ITERATE, big, 0.0)
     e1.record()
@@ -337,12 +336,9 @@ def main():
         traffic = tr.get(f"{args.config}_n{world}")
     except Exception:
         pass
-    if eng.lib.bgmm_pass_supported(k, d, eng.x_code, _lib.PASS_DMMA) and args.variant in ("auto", "dmma"):
-        kname = "bgmm::pass_dmma_kernel"
-    elif eng.lib.bgmm_pass_supported(k, d, eng.x_code, _lib.PASS_F32) and args.variant == "auto":
-        kname = "bgmm::pass_f32_kernel"
-    else:
-        kname = "bgmm::pass_simple_kernel"
+    kname = {_lib.PASS_DMMA: "bgmm::pass_dmma_kernel", _lib.PASS_F32: "bgmm::pass_f32_kernel",
+             _lib.PASS_LARGE: "bgmm::e_large_kernel + bgmm::m_large_kernel", _lib.PASS_SIMPLE: "bgmm::pass_simple_kernel"}[
+        eng.lib.bgmm_pass_resolve(k, d, eng.x_code, eng.variant, 0)]
     roofline = {
         "bound": "tensor", "achieved": ach_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
         "frac": ach_tflops / FP64_PEAK_TFLOPS, "traffic": traffic,
