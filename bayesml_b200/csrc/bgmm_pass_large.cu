@@ -39,28 +39,51 @@ __device__ __forceinline__ double feat_value(int kind, int i, int j, const doubl
     return kind == 2 ? xr[i] * xr[j] : (kind == 1 ? xr[i] : (kind == 0 ? 1.0 : 0.0));
 }
 
+// Coefficient image for the E kernel: chunk c = the [8*KB][64] shared-memory tile (k-step-pair permutation + swizzle, zero /
+// -1e300 padding applied) stored contiguously, so that the E kernel fetches a chunk with ONE TMA bulk copy.
+template <int KB>
+__global__ void __launch_bounds__(LG_THREADS) coef_pack_kernel(const double* __restrict__ st, const Layout L,
+                                                               double* __restrict__ packed, const int force) {
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    const double* __restrict__ coef_g = st + L.params[ctrl[BGMM_CTRL_CUR]] + L.p_coef;
+    const int c = blockIdx.x;
+    double* out = packed + (int64_t)c * 8 * KB * LG_CW;
+    for (int e = threadIdx.x; e < 8 * KB * LG_CW; e += LG_THREADS) {
+        const int k = e >> 6, f2 = e & (LG_CW - 1), p2 = LG_CW * c + f2;
+        double v = 0.0;
+        if (k < L.K) { if (p2 < L.P) v = coef_g[(int64_t)k * L.pitch + p2]; }
+        else if (p2 == 0) v = -1.0e300;                        // padded components: r == 0 exactly
+        out[k * LG_CW + (phys_col(f2) ^ fsw(k))] = v;
+    }
+}
+
 template <int KB>
 __global__ void __launch_bounds__(LG_THREADS, 1)
-e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews) {
+e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const double* __restrict__ packed) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = L.K, D = L.D, P = L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
     if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
-    const double* __restrict__ coef_g = a.state + L.params[ctrl[BGMM_CTRL_CUR]] + L.p_coef;
     const double* __restrict__ x = static_cast<const double*>(a.x);
 
     double* phiS = reinterpret_cast<double*>(smem_raw);        // [64][64] swizzled
-    double* coefS = phiS + LG_ETILE * LG_CW;                   // [8*KB][64] swizzled
-    double* xs = coefS + 8 * KB * LG_CW;                       // [64][D]
+    double* coefS = phiS + LG_ETILE * LG_CW;                   // [2 stages][8*KB][64] swizzled (TMA destination)
+    double* xs = coefS + 2 * 8 * KB * LG_CW;                   // [64][D]
     double* red = xs + LG_ETILE * D;                           // [40]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 40);    // [2]
+    constexpr uint32_t kChunkBytes = 8 * KB * LG_CW * sizeof(double);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    uint32_t ph[2] = {0u, 0u};
 
     const int nchunk = (P + LG_CW - 1) / LG_CW;
     const int64_t ntiles = (a.n + LG_ETILE - 1) / LG_ETILE;
     const int fg = fsw(g);
     const int lrow = 8 * warp + g;
     const double* eA = phiS + lrow * LG_CW;
-    const double* eB = coefS + g * LG_CW;
     const int eo0 = (2 * q) ^ fg, eo1 = (8 + 2 * q) ^ fg;
     const int fcol = tid & (LG_CW - 1), frow0 = tid >> 6;      // Phi generation: one column, rows frow0 + 4s
     const int fphys = phys_col(fcol);
@@ -70,7 +93,11 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews) {
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
         const int64_t row0 = t * LG_ETILE;
         const int rows = (int)min((int64_t)LG_ETILE, a.n - row0);
-        __syncthreads();
+        __syncthreads();                                       // previous tile's GEMMs done: xs / coefS[0] are free
+        if (tid == 0) {                                        // chunk 0 of the coefficient image -> stage 0
+            mbar_expect_tx(&bars[0], kChunkBytes);
+            tma_load_1d(coefS, packed, kChunkBytes, &bars[0]);
+        }
         for (int e = tid; e < LG_ETILE * D; e += LG_THREADS) xs[e] = (e < rows * D) ? x[row0 * D + e] : 0.0;
         double acc[2][KB][2];
 #pragma unroll
@@ -80,6 +107,11 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews) {
 
         for (int c = 0; c < nchunk; ++c) {
             __syncthreads();                                   // xs ready (c == 0) / previous chunk's GEMM finished
+            if (tid == 0 && c + 1 < nchunk) {                  // prefetch the next coefficient chunk into the other stage
+                const int nb = (c + 1) & 1;
+                mbar_expect_tx(&bars[nb], kChunkBytes);
+                tma_load_1d(coefS + nb * 8 * KB * LG_CW, packed + (int64_t)(c + 1) * 8 * KB * LG_CW, kChunkBytes, &bars[nb]);
+            }
             int kind, fi, fj;
             feat_decode(LG_CW * c + fcol, D, P, kind, fi, fj);
 #pragma unroll 4
@@ -87,14 +119,10 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews) {
                 const int r = frow0 + 4 * s;
                 phiS[r * LG_CW + (fphys ^ fsw(r))] = feat_value(kind, fi, fj, xs + r * D);
             }
-            for (int e = tid; e < 8 * KB * LG_CW; e += LG_THREADS) {
-                const int k = e >> 6, f2 = e & (LG_CW - 1), p2 = LG_CW * c + f2;
-                double v = 0.0;
-                if (k < K) { if (p2 < P) v = coef_g[(int64_t)k * L.pitch + p2]; }
-                else if (p2 == 0) v = -1.0e300;                // padded components: r == 0 exactly
-                coefS[k * LG_CW + (phys_col(f2) ^ fsw(k))] = v;
-            }
+            mbar_wait(&bars[c & 1], ph[c & 1]);
+            ph[c & 1] ^= 1u;
             __syncthreads();
+            const double* eB = coefS + (c & 1) * 8 * KB * LG_CW + g * LG_CW;
 #pragma unroll
             for (int w = 0; w < LG_CW / 16; ++w) {
                 const double2 a0 = lds2(eA + 16 * w + eo0), a1 = lds2(eA + 16 * w + eo1);
@@ -190,7 +218,13 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
 
     double* phiS = reinterpret_cast<double*>(smem_raw);        // [32][128] swizzled
     double* rS = phiS + LG_MSUB * LG_MCW;                      // [32][RP] swizzled
-    double* xs = rS + LG_MSUB * RP;                            // [32][D]
+    double* xs = rS + LG_MSUB * RP;                            // [32][D]   TMA destination
+    double* rst = xs + LG_MSUB * D;                            // [32][K]   TMA destination (row-major, as in HBM)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(rst + ((LG_MSUB * K + 1) & ~1));
+    const uint32_t xbytes = (uint32_t)(LG_MSUB * D * sizeof(double)), rbytes = (uint32_t)(LG_MSUB * K * sizeof(double));
+    if (tid == 0) mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint32_t ph = 0u;
 
     const int cx = blockIdx.x, ry = blockIdx.y;
     const int64_t nsub = (a.n + LG_MSUB - 1) / LG_MSUB;
@@ -214,24 +248,41 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
     const double* mP0 = phiS + q * LG_MCW + ((8 * (2 * warp) + g) ^ fq);
     const double* mP1 = phiS + q * LG_MCW + ((8 * (2 * warp + 1) + g) ^ fq);
 
+    // full 32-row steps arrive by TMA, issued one step ahead (the staging tiles are free as soon as Phi and the swizzled r
+    // tile have been built); a ragged last step uses plain loads
+    auto issue = [&](int64_t sb) {
+        const int64_t row0 = sb * LG_MSUB;
+        if (sb < s_end && row0 + LG_MSUB <= a.n) {
+            mbar_expect_tx(bar, xbytes + rbytes);
+            tma_load_1d(xs, x + row0 * D, xbytes, bar);
+            tma_load_1d(rst, rws + row0 * K, rbytes, bar);
+        }
+    };
+    __syncthreads();
+    if (tid == 0) issue(s_begin);
     for (int64_t sb = s_begin; sb < s_end; ++sb) {
         const int64_t row0 = sb * LG_MSUB;
         const int rows = (int)min((int64_t)LG_MSUB, a.n - row0);
-        __syncthreads();                                       // previous step's GEMM finished
-        for (int e = tid; e < LG_MSUB * D; e += LG_THREADS) xs[e] = (e < rows * D) ? x[row0 * D + e] : 0.0;
+        if (rows == LG_MSUB) {
+            mbar_wait(bar, ph);
+            ph ^= 1u;
+        } else {
+            for (int e = tid; e < LG_MSUB * D; e += LG_THREADS) xs[e] = (e < rows * D) ? x[row0 * D + e] : 0.0;
+            for (int e = tid; e < LG_MSUB * K; e += LG_THREADS) rst[e] = (e < rows * K) ? rws[row0 * K + e] : 0.0;
+            __syncthreads();
+        }
         for (int e = tid; e < LG_MSUB * K; e += LG_THREADS) {
             const int r = e / K, k = e - r * K;
-            const double v = (r < rows) ? rws[(row0 + r) * K + k] : 0.0;
             const int kb = k >> 3, cc = k & 7;
-            rS[r * RP + ((16 * (kb >> 1) + 2 * cc + (kb & 1)) ^ fsw(r))] = v;
+            rS[r * RP + ((16 * (kb >> 1) + 2 * cc + (kb & 1)) ^ fsw(r))] = rst[e];
         }
-        __syncthreads();
 #pragma unroll 4
         for (int s = 0; s < LG_MSUB / 2; ++s) {
             const int r = frow0 + 2 * s;
             phiS[r * LG_MCW + (fphys ^ fsw(r))] = feat_value(kind, fi, fj, xs + r * D);
         }
         __syncthreads();
+        if (tid == 0) issue(sb + 1);                           // staging tiles consumed: prefetch the next step
 #pragma unroll
         for (int ks = 0; ks < LG_MSUB / 4; ++ks) {
             double ra[KB];
@@ -252,6 +303,7 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
                 dmma(macc[1][kb][0], macc[1][kb][1], ra[kb], b1);
             }
         }
+        __syncthreads();                                       // GEMM finished: rS / phiS may be rebuilt
     }
 
     // ---- partial of this row split (logical layout [K][pitch]); split 0 also carries the entropy term ----
@@ -298,7 +350,9 @@ static void large_plan(int K, int D, int64_t n, int& grid_e, int& n_chunks, int&
 
 int64_t large_workspace_doubles(int K, int D) {
     if (K > 64 || D > 128) return 0;
-    return (int64_t)64 * ((int64_t)K * feat_pitch(D) + 8) + 256;        // <= 64 row splits + E-kernel entropy partials
+    const int64_t nchunk = (feat_count(D) + LG_CW - 1) / LG_CW;
+    // <= 64 row splits + E-kernel entropy partials + the packed coefficient image (nchunk x [8*KB][64])
+    return (int64_t)64 * ((int64_t)K * feat_pitch(D) + 8) + 256 + nchunk * 64 * LG_CW;
 }
 
 template <int KB>
@@ -307,14 +361,19 @@ static int launch_large_t(const PassArgs& a, const Layout& L, cudaStream_t strea
     large_plan(L.K, L.D, a.n, grid_e, n_chunks, nsplit);
     const int64_t len = L.stats_len;
     double* ews = a.workspace + (int64_t)64 * len;
-    const size_t smem_e = sizeof(double) * ((size_t)LG_ETILE * LG_CW + (size_t)8 * KB * LG_CW + (size_t)LG_ETILE * L.D + 40) + 128;
+    double* packed = ews + 256;
+    const int nchunk_e = (L.P + LG_CW - 1) / LG_CW;
+    const size_t smem_e = sizeof(double) * ((size_t)LG_ETILE * LG_CW + (size_t)2 * 8 * KB * LG_CW + (size_t)LG_ETILE * L.D + 40) +
+                          2 * sizeof(uint64_t) + 128;
     constexpr int RP = (8 * KB < 16) ? 16 : 8 * KB;
-    const size_t smem_m = sizeof(double) * ((size_t)LG_MSUB * LG_MCW + (size_t)LG_MSUB * RP + (size_t)LG_MSUB * L.D) + 128;
+    const size_t smem_m = sizeof(double) * ((size_t)LG_MSUB * LG_MCW + (size_t)LG_MSUB * RP + (size_t)LG_MSUB * L.D +
+                                            (size_t)LG_MSUB * L.K + 2) + sizeof(uint64_t) + 128;
     cudaError_t e = cudaFuncSetAttribute(e_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(e_large)");
     e = cudaFuncSetAttribute(m_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(m_large)");
-    e_large_kernel<KB><<<grid_e, LG_THREADS, smem_e, stream>>>(a, L, ews);
+    coef_pack_kernel<KB><<<nchunk_e, LG_THREADS, 0, stream>>>(a.state, L, packed, a.force);
+    e_large_kernel<KB><<<grid_e, LG_THREADS, smem_e, stream>>>(a, L, ews, packed);
     m_large_kernel<KB><<<dim3(n_chunks, nsplit), LG_THREADS, smem_m, stream>>>(a, L, ews, grid_e, nsplit);
     launch_reduce_partials(a, L, nsplit, stream);
     return check_cuda(cudaGetLastError(), "pass_large launch");
