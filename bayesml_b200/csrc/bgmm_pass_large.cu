@@ -341,7 +341,7 @@ static void large_plan(int K, int D, int64_t n, int& grid_e, int& n_chunks, int&
     grid_e = (int)(ntiles < 1 ? 1 : (ntiles < sms ? ntiles : sms));
     n_chunks = (feat_pitch(D) + LG_MCW - 1) / LG_MCW;
     const int64_t nsub = (n + LG_MSUB - 1) / LG_MSUB;
-    int64_t s = (2 * sms + n_chunks - 1) / n_chunks;                    // about two resident waves of CTAs
+    int64_t s = (2 * sms) / n_chunks;                                   // ONE resident wave (2 CTAs per SM): no tail wave
     if (s > 64) s = 64;
     if (s > nsub) s = nsub;
     if (s < 1) s = 1;
