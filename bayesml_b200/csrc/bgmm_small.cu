@@ -14,8 +14,13 @@
 
 namespace bgmm {
 
+// The kernel below is straight-line code executed once per launch, so its running time is dominated by instruction
+// fetch (cold I-cache after the big pass kernel) unless the code stays small: the libm calls are kept out of line.
+__device__ __noinline__ double lgamma_ni(double x) { return lgamma(x); }
+__device__ __noinline__ double log_ni(double x) { return log(x); }
+
 // psi(x), x > 0: upward recurrence to x >= 10 then the asymptotic series (error < 1e-16 relative there).
-__device__ double digamma_pos(double x) {
+__device__ __noinline__ double digamma_pos(double x) {
     double r = 0.0;
     while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
     const double inv = 1.0 / x, inv2 = inv * inv;
@@ -25,7 +30,7 @@ __device__ double digamma_pos(double x) {
     s = 1.0 / 252.0 - inv2 * s;
     s = 1.0 / 120.0 - inv2 * s;
     s = 1.0 / 12.0 - inv2 * s;
-    return r + log(x) - 0.5 * inv - inv2 * s;
+    return r + log_ni(x) - 0.5 * inv - inv2 * s;
 }
 
 constexpr double LN2 = 0.693147180559945309417232121458;
@@ -55,7 +60,9 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     double* dev = xbar + D;     // [D]
     double* mnew = dev + D;     // [D]
     double* lin = mnew + D;     // [D]
-    double* scratch = lin + D;  // [40]
+    double* rdiag = lin + D;    // [D]  1 / L_jj
+    double* ldiag = rdiag + D;  // [D]  L_jj
+    double* scratch = ldiag + D;  // [40]
 
     const double* center = st + L.center;
     const double* m0 = st + L.m0 + (int64_t)k * D;
@@ -102,11 +109,12 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
         const double N = raw[0];
         double* S = st + L.smats + (int64_t)k * DD;
         if (N > 0.0) {
-            for (int i = tid; i < D; i += nt) xbar[i] = raw[1 + i] / N;
+            const double invN = 1.0 / N;
+            for (int i = tid; i < D; i += nt) xbar[i] = raw[1 + i] * invN;
             __syncthreads();
             for (int e = tid; e < DD; e += nt) {
                 const int i = e / D, j = e - i * D, hi = max(i, j), lo = min(i, j);
-                S[e] = raw[1 + D + hi * (hi + 1) / 2 + lo] / N - xbar[i] * xbar[j];
+                S[e] = raw[1 + D + hi * (hi + 1) / 2 + lo] * invN - xbar[i] * xbar[j];
             }
         } else {
             // reference :729 — x_bar_vecs[k] keeps the un-normalised sum (0 in the original frame), s_mats[k] stale
@@ -141,10 +149,10 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
             vk[0] = N * (elndet - D / kappa - nu * t_trs - nu * t_q1 - D * LN2PI) / 2.0;          // :673-683
             vk[1] = N * elnpi;                                                                     // :686
             vk[2] = (alpha0 - 1.0) * elnpi;                                                        // :689
-            vk[3] = (D * (log(kappa0) - LN2PI - kappa0 / kappa) - kappa0 * nu * t_q2 + 2.0 * lnb0
+            vk[3] = (D * (log_ni(kappa0) - LN2PI - kappa0 / kappa) - kappa0 * nu * t_q2 + 2.0 * lnb0
                      + (nu0 - D) * elndet - nu * t_tr0) / 2.0;                                     // :692-701
-            vk[4] = lgamma(alpha) - (alpha - 1.0) * digamma_pos(alpha);                            // :707 (per-k part)
-            vk[5] = (D * (1.0 + LN2PI - log(kappa)) - 2.0 * lnb - (nu - D) * elndet + nu * D) / 2.0;  // :710-715
+            vk[4] = lgamma_ni(alpha) - (alpha - 1.0) * digamma_pos(alpha);                            // :707 (per-k part)
+            vk[5] = (D * (1.0 + LN2PI - log_ni(kappa)) - 2.0 * lnb - (nu - D) * elndet + nu * D) / 2.0;  // :710-715
             vk[6] = alpha;
             vk[7] = 0.0;
         }
@@ -188,15 +196,15 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     }
     __syncthreads();
 
-    // ---- Cholesky A = L L^T (lower, in place, right-looking) ----
+    // ---- Cholesky A = L L^T (lower, in place, right-looking).  Latency-bound: every thread forms 1/sqrt(a_jj) itself
+    //      (no divide, no single-thread step), two barriers per column; rdiag keeps 1/L_jj for the inversion ----
     bool spd = true;
     for (int j = 0; j < D; ++j) {
         const double ajj = A[j * D + j];
         if (!(ajj > 0.0)) spd = false;
-        const double ljj = sqrt(ajj);
-        __syncthreads();
-        if (tid == 0) A[j * D + j] = ljj;
-        for (int i = j + 1 + tid; i < D; i += nt) A[i * D + j] /= ljj;
+        const double rs = rsqrt(ajj);
+        for (int i = j + 1 + tid; i < D; i += nt) A[i * D + j] *= rs;
+        if (tid == 0) { rdiag[j] = rs; ldiag[j] = ajj * rs; }
         __syncthreads();
         const int rem = D - j - 1;
         for (int e = tid; e < rem * rem; e += nt) {
@@ -206,13 +214,13 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
         __syncthreads();
     }
     double ld = 0.0;
-    for (int i = tid; i < D; i += nt) ld += log(A[i * D + i]);
+    for (int i = tid; i < D; i += nt) ld += log_ni(ldiag[i]);
     const double logdet = 2.0 * block_sum(ld, scratch);  // ln|W^-1|
     if (!spd && tid == 0) ctrl[BGMM_CTRL_ERROR] = 1;
 
-    // ---- L <- L^-1 in place (column sweep from the last column; lower triangular) ----
+    // ---- L <- L^-1 in place (column sweep from the last column; lower triangular; 1/L_jj from rdiag) ----
     for (int j = D - 1; j >= 0; --j) {
-        const double inv_jj = 1.0 / A[j * D + j];
+        const double inv_jj = rdiag[j];
         // x = L[j+1:, j]; new x_i = -inv_jj * sum_{l=j+1..i} Linv[i][l] * x_l
         for (int i = j + 1 + tid; i < D; i += nt) lin[i] = A[i * D + j];
         __syncthreads();
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     for (int i = tid; i < D; i += nt) {
         const double a = (nun - i) / 2.0;
         ps += digamma_pos(a);
-        gs += lgamma(a);
+        gs += lgamma_ni(a);
     }
     ps = block_sum(ps, scratch);
     gs = block_sum(gs, scratch);
@@ -297,7 +305,7 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     }
     ppi += st[L.lnc0];
     const double qz = -st[L.stats + (int64_t)K * L.pitch];                    // -sum r ln r (:704)
-    qpi += -lgamma(asum) + (asum - K) * digamma_pos(asum);                    // dirichlet entropy (:707)
+    qpi += -lgamma_ni(asum) + (asum - K) * digamma_pos(asum);                    // dirichlet entropy (:707)
     const double vl = px + pz + ppi + pml + qz + qpi + qml;                   // :717-723
     double* vt = st + L.vlterms;
     vt[0] = px; vt[1] = pz; vt[2] = ppi; vt[3] = pml; vt[4] = qz; vt[5] = qpi; vt[6] = qml; vt[7] = vl;
@@ -330,7 +338,7 @@ extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, do
         return BGMM_EINVAL;
     }
     const Layout L = make_layout(K, D, hist_len);
-    const size_t smem = sizeof(double) * ((size_t)D * D + 4 * (size_t)D + 40);
+    const size_t smem = sizeof(double) * ((size_t)D * D + 6 * (size_t)D + 40);
     if (smem > 227 * 1024) {
         set_error("bgmm_small: D=%d needs %zu B of shared memory (> 227 KiB)", D, smem);
         return BGMM_ENOSUP;
