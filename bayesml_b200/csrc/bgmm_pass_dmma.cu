@@ -4,14 +4,14 @@
 // Persistent, warp-specialised CTA (one per SM, 384 threads = 3 warpgroups) working on 32-sample sub-tiles:
 //
 //   producer warpgroup (warps 8-11)
-//     - keeps a 4-stage ring of X sub-tiles filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx),
+//     - keeps a 2-stage ring of X sub-tiles filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx),
 //     - expands each sub-tile into the feature tile Phi[32][SP] (phi = [1, x, x_i x_j (i>=j)], zero padded) in a
-//       3-stage shared-memory ring (full/empty mbarriers towards the consumers);
+//       4-stage shared-memory ring (full/empty mbarriers towards the consumers);
 //   consumer warpgroups A (warps 0-3) and B (warps 4-7), ping-pong on alternate sub-tiles, each doing
 //     - E-GEMM on the FP64 tensor pipe:  ln rho[32][K] = Phi . coef^T   (mma.sync.m8n8k4.f64 = SASS DMMA.8x8x4;
 //       warp = one 8-row m-block x all K components x the full feature range, no cross-warp reduction),
 //     - softmax over k in the accumulator fragments (quad shuffles), entropy term, optional r / ln rho / argmax
-//       stores, r tile -> shared memory (double buffered per warpgroup),
+//       stores, r tile -> shared memory (one buffer per warpgroup),
 //     - M-GEMM on the same pipe:  raw[K][SP] += R^T . Phi   with the K x SP accumulators resident in registers for
 //       the whole sweep (warp = all K components x SP/32 feature blocks).
 //   While one consumer warpgroup is in its (non-DMMA) softmax, the other one and the producer keep the DMMA pipe and
@@ -34,7 +34,7 @@ namespace bgmm {
 
 constexpr int DM_THREADS = 384;      // consumer warpgroups A, B + producer warpgroup
 constexpr int DM_TILE = 32;          // samples per sub-tile = 4 m-blocks (one per consumer warp)
-constexpr int DM_NXS = 4;            // stages of the X ring (TMA)
+constexpr int DM_NXS = 2;            // stages of the X ring (TMA); small, so that the Phi ring can have 4 stages
 constexpr int DM_XPAD = 4;           // doubles of slack after each X stage (vector loads past the last row)
 constexpr int DM_MAXG = 64;          // entries of the Phi-expansion group table
 
@@ -62,8 +62,8 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
     const int xstage = DM_TILE * D + DM_XPAD;
     double* phiS = reinterpret_cast<double*>(smem_raw);                  // [NPS][32][SP]
     double* coefS = phiS + NPS * DM_TILE * SP;                           // [8*KB][SP]
-    double* rS = coefS + 8 * KB * SP;                                    // [2 groups][2 buffers][32][RP]
-    double* xS = rS + 4 * DM_TILE * RP;                                  // [NXS][32*D + pad]
+    double* rS = coefS + 8 * KB * SP;                                    // [2 groups][32][RP]
+    double* xS = rS + 2 * DM_TILE * RP;                                  // [NXS][32*D + pad]
     double* red = xS + DM_NXS * xstage;                                  // [40]
     uint64_t* xfull = reinterpret_cast<uint64_t*>(red + 40);             // [NXS]
     uint64_t* pfull = xfull + DM_NXS;                                    // [NPS]
@@ -206,7 +206,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
             const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)j * gridDim.x) * DM_TILE;
             const int rows = (int)min((int64_t)DM_TILE, a.n - row0);
             const double* ph = phiS + ps * DM_TILE * SP;
-            double* rb = rS + (wg * 2 + (jj & 1)) * DM_TILE * RP;
+            double* rb = rS + wg * DM_TILE * RP;
             mbar_wait(&pfull[ps], (uint32_t)((j / NPS) & 1));
 
             // ---- E-GEMM: m-block wq, all KB n-blocks, all EG column groups; two accumulator sets for ILP ----
@@ -320,7 +320,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
                 }
                 if (valid && q == 0) a.argmax_out[grow] = best;
             }
-            wg_sync(2 + wg);          // r tile of this warpgroup complete (and the previous use of this buffer is over)
+            wg_sync(2 + wg);          // r tile of this warpgroup complete
 
             // ---- M-GEMM: raw[k][p] += sum_n r[n][k] phi[n][p]; A = R^T (8 comps x 4 samples), B = Phi (4 x 8) ----
             const double* mR = rb + mRo;
@@ -346,6 +346,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
                     for (int kb = 0; kb < KB; ++kb) dmma(macc[l][kb][0], macc[l][kb][1], ra[kb], bfr[l]);
             }
             mbar_arrive(&pempty[ps]);                                     // this thread is done with the Phi stage
+            wg_sync(2 + wg);          // every warp of the group has read the r tile: it may be overwritten (single buffer)
         }
 
         ent -= log(sprod);
@@ -438,7 +439,7 @@ struct DmmaPlan {
 };
 
 static size_t dmma_smem(int KB, int SP, int RP, int NPS, int D) {
-    return sizeof(double) * ((size_t)NPS * DM_TILE * SP + (size_t)8 * KB * SP + (size_t)4 * DM_TILE * RP +
+    return sizeof(double) * ((size_t)NPS * DM_TILE * SP + (size_t)8 * KB * SP + (size_t)2 * DM_TILE * RP +
                              (size_t)DM_NXS * (DM_TILE * D + DM_XPAD) + 40) +
            sizeof(uint64_t) * (DM_NXS + 2 * NPS) + sizeof(uint2) * DM_MAXG + 128;
 }
@@ -452,7 +453,7 @@ static DmmaPlan plan_dmma(int K, int D) {
     int ng = (D + 3) / 4;
     for (int i = 0; i < D; ++i) ng += i / 4 + 1;
     const size_t cap = 227 * 1024 - 512;
-    p.NPS = dmma_smem(p.KB, p.SP, p.RP, 3, D) <= cap ? 3 : 2;
+    p.NPS = dmma_smem(p.KB, p.SP, p.RP, 4, D) <= cap ? 4 : (dmma_smem(p.KB, p.SP, p.RP, 3, D) <= cap ? 3 : 2);
     p.smem = dmma_smem(p.KB, p.SP, p.RP, p.NPS, D);
     p.ok = ng <= DM_MAXG && ng <= 128 && (p.KB == 1 || p.KB == 2 || p.KB == 4) && p.SP <= 192 && p.smem <= cap &&
            (D * sizeof(double) * DM_TILE) % 16 == 0;
@@ -497,8 +498,8 @@ int launch_pass_dmma(const PassArgs& a, int K, int D, int dtype, cudaStream_t st
     }
     const Layout L = make_layout(K, D, 1);
 #define BGMM_DM_CASE(kb, sp, nps) if (p.KB == kb && p.SP == sp && p.NPS == nps) return launch_cfg<kb, sp, nps>(a, L, p, stream);
-#define BGMM_DM_ROW(kb) BGMM_DM_CASE(kb, 32, 3) BGMM_DM_CASE(kb, 64, 3) BGMM_DM_CASE(kb, 96, 3) BGMM_DM_CASE(kb, 128, 3) \
-                        BGMM_DM_CASE(kb, 160, 3) BGMM_DM_CASE(kb, 192, 3) BGMM_DM_CASE(kb, 192, 2)
+#define BGMM_DM_ROW(kb) BGMM_DM_CASE(kb, 32, 4) BGMM_DM_CASE(kb, 64, 4) BGMM_DM_CASE(kb, 96, 4) BGMM_DM_CASE(kb, 128, 4) \
+                        BGMM_DM_CASE(kb, 160, 4) BGMM_DM_CASE(kb, 192, 4) BGMM_DM_CASE(kb, 192, 3) BGMM_DM_CASE(kb, 160, 3)
     BGMM_DM_ROW(1) BGMM_DM_ROW(2) BGMM_DM_ROW(4)
 #undef BGMM_DM_ROW
 #undef BGMM_DM_CASE
