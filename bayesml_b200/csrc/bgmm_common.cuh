@@ -89,6 +89,20 @@ struct CommDesc {
     double* xchg[BGMM_MAX_RANKS];      // exchange block of every rank as mapped in THIS process ([rank] = own block)
 };
 
+// Four block-wide sums with one set of barriers (deterministic; results valid in every thread, written back in place).
+// The four partials of warp w go to scratch[4w .. 4w+3] (<= 32 doubles for <= 8 warps); every thread then adds them in warp order.
+__device__ __forceinline__ void block_sum4(double& a, double& b, double& c, double& d, double* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+    __syncthreads();
+    if (lane == 0) { scratch[4 * warp] = a; scratch[4 * warp + 1] = b; scratch[4 * warp + 2] = c; scratch[4 * warp + 3] = d; }
+    __syncthreads();
+    double ta = 0.0, tb = 0.0, tc = 0.0, td = 0.0;
+    for (int w = 0; w < nwarp; ++w) { ta += scratch[4 * w]; tb += scratch[4 * w + 1]; tc += scratch[4 * w + 2]; td += scratch[4 * w + 3]; }
+    __syncthreads();
+    a = ta; b = tb; c = tc; d = td;
+}
+
 // Arguments of one pass launch (see bgmm_pass in include/bgmm.h).
 struct PassArgs {
     const void* x;

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     double* lin = mnew + D;     // [D]
     double* rdiag = lin + D;    // [D]  1 / L_jj
     double* ldiag = rdiag + D;  // [D]  L_jj
-    double* scratch = ldiag + D;  // [40]
+    double* scratch = ldiag + D;  // [48]: [0..33] block reductions, [34..37] special-function values
 
     const double* center = st + L.center;
     const double* m0 = st + L.m0 + (int64_t)k * D;
@@ -130,32 +130,42 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
         const double elnpi = Pc[L.p_elnpi + k], elndet = Pc[L.p_elndet + k], lnb = Pc[L.p_lnb + k];
         const double* W = Pc + L.p_w + (int64_t)k * DD;
         const double* m = Pc + L.p_m + (int64_t)k * D;
+        // the deviations (x_bar - m), (m - m0) go to shared memory first so the D x D loop only streams W and W0^-1
+        for (int i = tid; i < D; i += nt) { dev[i] = xbar[i] - m[i]; lin[i] = m[i] - m0[i]; }
+        // the four special-function values of the ELBO terms, one per lane, while the loads of the loop are in flight
+        double sf = 0.0;
+        if (tid == 0) sf = log_ni(kappa0);
+        else if (tid == 1) sf = log_ni(kappa);
+        else if (tid == 2) sf = lgamma_ni(alpha);
+        else if (tid == 3) sf = digamma_pos(alpha);
+        if (tid < 4) scratch[34 + tid] = sf;
+        __syncthreads();
         double t_trs = 0.0, t_q1 = 0.0, t_q2 = 0.0, t_tr0 = 0.0;
+#pragma unroll 4
         for (int e = tid; e < DD; e += nt) {
             const int i = e / D, j = e - i * D;
             const double w = W[e];
             t_trs += S[e] * w;
-            t_q1 += (xbar[i] - m[i]) * w * (xbar[j] - m[j]);
-            t_q2 += (m[i] - m0[i]) * w * (m[j] - m0[j]);
+            t_q1 += dev[i] * w * dev[j];
+            t_q2 += lin[i] * w * lin[j];
             t_tr0 += w0inv[e] * w;
         }
-        t_trs = block_sum(t_trs, scratch);
-        t_q1 = block_sum(t_q1, scratch);
-        t_q2 = block_sum(t_q2, scratch);
-        t_tr0 = block_sum(t_tr0, scratch);
+        block_sum4(t_trs, t_q1, t_q2, t_tr0, scratch);
         if (tid == 0) {
             double* vk = st + L.vlk + (int64_t)k * 8;
             const double lnb0 = st[L.lnb0 + k];
+            const double ln_kappa0 = scratch[34], ln_kappa = scratch[35], lg_alpha = scratch[36], psi_alpha = scratch[37];
             vk[0] = N * (elndet - D / kappa - nu * t_trs - nu * t_q1 - D * LN2PI) / 2.0;          // :673-683
             vk[1] = N * elnpi;                                                                     // :686
             vk[2] = (alpha0 - 1.0) * elnpi;                                                        // :689
-            vk[3] = (D * (log_ni(kappa0) - LN2PI - kappa0 / kappa) - kappa0 * nu * t_q2 + 2.0 * lnb0
+            vk[3] = (D * (ln_kappa0 - LN2PI - kappa0 / kappa) - kappa0 * nu * t_q2 + 2.0 * lnb0
                      + (nu0 - D) * elndet - nu * t_tr0) / 2.0;                                     // :692-701
-            vk[4] = lgamma_ni(alpha) - (alpha - 1.0) * digamma_pos(alpha);                            // :707 (per-k part)
-            vk[5] = (D * (1.0 + LN2PI - log_ni(kappa)) - 2.0 * lnb - (nu - D) * elndet + nu * D) / 2.0;  // :710-715
+            vk[4] = lg_alpha - (alpha - 1.0) * psi_alpha;                                          // :707 (per-k part)
+            vk[5] = (D * (1.0 + LN2PI - ln_kappa) - 2.0 * lnb - (nu - D) * elndet + nu * D) / 2.0;  // :710-715
             vk[6] = alpha;
             vk[7] = 0.0;
         }
+        __syncthreads();       // dev / lin are reused by the M-step below
 
         // ---- M-step (:758-768, :742) into the other parameter set ----
         kn = kappa0 + N; nun = nu0 + N; an = alpha0 + N;
@@ -338,7 +348,7 @@ extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, do
         return BGMM_EINVAL;
     }
     const Layout L = make_layout(K, D, hist_len);
-    const size_t smem = sizeof(double) * ((size_t)D * D + 6 * (size_t)D + 40);
+    const size_t smem = sizeof(double) * ((size_t)D * D + 6 * (size_t)D + 48);
     if (smem > 227 * 1024) {
         set_error("bgmm_small: D=%d needs %zu B of shared memory (> 227 KiB)", D, smem);
         return BGMM_ENOSUP;

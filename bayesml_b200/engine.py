@@ -51,6 +51,10 @@ class VBEngine:
             raise ValueError(f"precision must be 'float64' or 'float32', got {precision!r}")
         self.precision = precision
         self.x_code, self.x_torch_dtype = _DTYPES[precision]
+        if precision == "float32" and not self.lib.bgmm_pass_supported(self.K, self.D, _lib.F32, _lib.PASS_F32):
+            # the fp32 streaming kernel covers small D, K only; elsewhere the fp64 tensor-pipe kernels are the fast path
+            # (compute-bound, so the wider X costs nothing): keep X in fp64 on the device
+            self.x_code, self.x_torch_dtype = _DTYPES["float64"]
         self.group = group
         env = os.environ.get("BAYESML_B200_PASS_VARIANT", "").lower()     # debugging / tests: force a kernel variant
         if env:

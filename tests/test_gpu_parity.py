@@ -280,3 +280,23 @@ def test_high_dimension_shape(variant, monkeypatch):
     for f in ("hn_alpha_vec", "hn_m_vecs", "hn_nus", "hn_w_mats_inv", "ns", "x_bar_vecs"):
         _close(getattr(m, f), getattr(o, f), what=f)
     assert np.array_equal(np.argmax(m.r_vecs, axis=1), np.argmax(o.r_vecs, axis=1))
+
+
+def test_fp32_precision_request_on_a_shape_without_fp32_kernel_uses_the_fp64_path():
+    """precision='float32' with D=16 (no fp32 streaming kernel): X is promoted on upload and the fused fp64 kernel runs —
+    results then meet the fp64 bar against the oracle on the same float32 array."""
+    from bayesml_b200 import _lib, gaussianmixture
+    from oracle.gmm_vb_oracle import OracleGMM, fit
+    rng = np.random.default_rng(3)
+    n, d, k = 8000, 16, 6
+    x32 = (rng.normal(size=(n, d)) + 4.0 * rng.normal(size=(k, d))[rng.integers(0, k, size=n)]).astype(np.float32)
+    m = gaussianmixture.LearnModel(k, d, seed=2, precision="float32")
+    o = OracleGMM(k, d, seed=2)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m.update_posterior(x32, max_itr=5, num_init=1, tolerance=0.0)
+    fit(o, x32, max_itr=5, num_init=1, tolerance=0.0)
+    assert m._engine().x.dtype.is_floating_point and m._engine().x.element_size() == 8
+    _close(m.vl, o.vl, what="vl")
+    _close(m.hn_m_vecs, o.hn_m_vecs, what="hn_m_vecs")
+    assert np.allclose(m.r_vecs, o.r_vecs, rtol=RTOL, atol=1e-300)
