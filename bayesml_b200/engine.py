@@ -67,7 +67,9 @@ class VBEngine:
         self.n_global = 0
         self.center = np.zeros(self.D)
         self.timing = {} if os.environ.get("BAYESML_B200_TIMING") else None
-        self.passes = 0                       # pass launches (for gpu_launches accounting)
+        self.passes = 0                       # bgmm_pass calls
+        self.kernel_launches = 0              # kernels launched by this engine (pass + reduction + publish + small ...)
+        self._pending = None
         self.small_launches = 0
         with torch.cuda.device(self.device):
             self.workspace = torch.empty(int(self.lib.bgmm_workspace_doubles(self.K, self.D)), dtype=torch.float64,
@@ -179,9 +181,16 @@ class VBEngine:
     # ------------------------------------------------------------------ data
     def load_data(self, x):
         """Upload the local rows of X ((n, D) numpy array or torch tensor), centre them about the global column mean."""
-        K, D = self.K, self.D
+        self.load_data_begin(x)
+        return self.load_data_finish()
+
+    def load_data_begin(self, x):
+        """Asynchronous part: host->device copy (truly async from pinned memory) and the column sums; the caller may do
+        host work (e.g. draw the initial states) before load_data_finish()."""
+        D = self.D
         with torch.cuda.device(self.device):
-            if isinstance(x, torch.Tensor):
+            own = not isinstance(x, torch.Tensor)
+            if not own:
                 xt = x.reshape(-1, D)
                 if xt.device != self.device:
                     xt = xt.to(self.device, non_blocking=True)
@@ -191,7 +200,7 @@ class VBEngine:
                 xa = np.ascontiguousarray(x).reshape(-1, D)
                 if xa.dtype not in (np.float64, np.float32):
                     xa = xa.astype(np.float64)
-                raw = torch.from_numpy(xa).to(self.device)
+                raw = torch.from_numpy(xa).to(self.device, non_blocking=True)
             raw_code = _lib.F64 if raw.dtype == torch.float64 else _lib.F32
             n = raw.shape[0]
             self.n_local = int(n)
@@ -201,12 +210,23 @@ class VBEngine:
             colsum[D] = float(n)
             if self.group is not None:
                 torch.distributed.all_reduce(colsum, group=self.group)
-            tot = colsum.cpu().numpy()
+            host = torch.empty(D + 1, dtype=torch.float64).pin_memory()
+            host.copy_(colsum, non_blocking=True)
+            self._pending = (raw, raw_code, own, host)
+        return self
+
+    def load_data_finish(self):
+        raw, raw_code, own, host = self._pending
+        self._pending = None
+        D, n = self.D, self.n_local
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()
+            tot = host.numpy()
             self.n_global = int(round(tot[D]))
             self.center = tot[:D] / max(self.n_global, 1)
             cview = self._view("center", D)
             self._put(cview, self.center)
-            if raw.dtype == self.x_torch_dtype and not isinstance(x, torch.Tensor):
+            if raw.dtype == self.x_torch_dtype and own:
                 out = raw          # our own upload buffer: centre in place
             else:
                 out = torch.empty((n, D), dtype=self.x_torch_dtype, device=self.device)
@@ -245,6 +265,7 @@ class VBEngine:
         _lib.check(self.lib.bgmm_small(self.K, self.D, self.state.data_ptr(), mode, int(max_itr), float(tol),
                                        self.hist_len, comm, self._stream()), "bgmm_small")
         self.small_launches += 1
+        self.kernel_launches += 1
 
     def _pass(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0):
         self.pass_only(r_out, lnrho_out, argmax_out, r_in, force)
@@ -264,6 +285,8 @@ class VBEngine:
                                       ptr(r_in), self.variant if r_in is None else _lib.PASS_SIMPLE, force, 0,
                                       self._stream()), "bgmm_pass")
         self.passes += 1
+        self.kernel_launches += {_lib.PASS_DMMA: 2, _lib.PASS_LARGE: 4}.get(
+            self.lib.bgmm_pass_resolve(self.K, self.D, self.x_code, self.variant, int(r_in is not None)), 1)
 
     def exchange(self, force=0):
         """The per-iteration exchange of the statistics between row shards: publish to peer memory (the reduction is
@@ -271,6 +294,7 @@ class VBEngine:
         if self.comm_desc is not None:
             _lib.check(self.lib.bgmm_publish(self.K, self.D, self.state.data_ptr(), self.comm_desc.data_ptr(), int(force),
                                              self._stream()), "bgmm_publish")
+            self.kernel_launches += 1
         elif self.group is not None:
             torch.distributed.all_reduce(self.stats, group=self.group)
 

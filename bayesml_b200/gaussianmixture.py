@@ -340,16 +340,14 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         """
         x = self._check_x(x)
         eng = self._engine()
-        with eng.phase("upload+centre"):
-            eng.load_data(x)
+        eng.load_data_begin(x)                   # async upload + column sums; the host draws the initial states meanwhile
         offset, n_total = self._shard_layout(x.shape[0])
-        self._push_prior(eng)
         self._lazy_r.set_host(None)
         self._lazy_ln_rho.set_host(None)
 
         best_vl = 0.0
         best = {name: np.array(getattr(self, name)) for name in _HN_NAMES}      # :838-844
-        with eng.phase("host_init"):
+        with eng.phase("host_init(+upload)"):
             inits = []
             for i in range(num_init):
                 self.reset_hn_params()
@@ -366,6 +364,9 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
                 inits.append({"alpha": self.hn_alpha_vec.copy(), "m": self.hn_m_vecs.copy(),
                               "kappa": self.hn_kappas.copy(), "nu": self.hn_nus.copy(),
                               "winv": self.hn_w_mats_inv.copy(), "r_init": r_init})
+        with eng.phase("centre"):
+            eng.load_data_finish()
+            self._push_prior(eng)
         with eng.phase("vb_loop"):
             results = self._run_restarts(eng, inits, max_itr, tolerance)
 
