@@ -307,22 +307,21 @@ def main():
     e1.record()
     launches = eng.kernel_launches - launches0
     barrier()
-    # nvidia-smi cannot sample faster than ~100 ms and the timed region may be shorter than that: keep the SAME iteration
-    # running (untimed) for another ~1.5 s so that the clock / throttle record is taken under this load
-    t_tail = time.perf_counter()
-    while time.perf_counter() - t_tail < 1.5:
-        for _ in range(8):
-            vb_iteration()
-        torch.cuda.synchronize(device)
-    clocks = sampler.stop() if rank == 0 else None
-    if clocks is not None:
-        clocks["sampled"] = "timed region + 1.5 s of the identical, untimed iteration (nvidia-smi -lms 100)"
-    barrier()
     ms_total = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
     pass_ms = torch.tensor([np.mean([a.elapsed_time(b) for a, b in pass_ev])], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
         dist.all_reduce(pass_ms, op=dist.ReduceOp.MAX)
+    # nvidia-smi cannot sample faster than ~100 ms and the timed region may be shorter than that: keep the SAME iteration
+    # running (untimed) for another ~1.5 s so that the clock / throttle record is taken under this load.  The number of
+    # tail iterations is derived from the max-reduced time, so every rank runs the same count (the exchange needs that).
+    n_tail = int(1500.0 / max(float(ms_total.item()) / args.steps, 1e-3)) + 1
+    for _ in range(min(n_tail, 4000)):
+        vb_iteration()
+    torch.cuda.synchronize(device)
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["sampled"] = "timed region + ~1.5 s of the identical, untimed iteration (nvidia-smi -lms 100)"
     ms_total, pass_ms = float(ms_total.item()), float(pass_ms.item())
     ms_per_step = ms_total / args.steps
     value = n_total * k / (ms_per_step * 1e-3)
