@@ -104,3 +104,39 @@ def test_two_rank_sharding_matches_single_process(tmp_path):
     assert np.allclose(smats, o.s_mats, rtol=1e-10, atol=1e-12)
     assert got[0]["stats"][k * P + 1] == x_full.shape[0]
     assert np.isclose(got[0]["stats"][k * P], np.sum(o.r_vecs * np.log(np.maximum(o.r_vecs, 1e-300))), rtol=1e-10)
+
+
+def _restart_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from bayesml_b200 import gaussianmixture
+        k, d, max_itr, n_restarts = 3, 2, 6, 5
+        m = gaussianmixture.LearnModel(k, d, seed=1, restart_group=dist.group.WORLD)
+        rng = np.random.default_rng(100)                      # every rank fabricates the same "device results"
+        all_res = {}
+        for i in range(n_restarts):
+            n_h = 2 + (i % 4)
+            state = {key: rng.normal(size=shape) for key, shape in
+                     [("alpha", (k,)), ("m", (k, d)), ("kappa", (k,)), ("nu", (k,)), ("w", (k, d, d)), ("winv", (k, d, d)),
+                      ("e_ln_pi", (k,)), ("e_ln_lambda_dets", (k,)), ("ln_b", (k,)), ("vl_terms", (8,)), ("ns", (k,)),
+                      ("x_bar", (k, d)), ("s_mats", (k, d, d))]}
+            all_res[i] = {"hist": rng.normal(size=n_h), "converged": bool(i % 2), "state": state}
+        mine = {i: r for i, r in all_res.items() if i % world == rank}          # round-robin ownership, as _run_restarts
+        full = m._gather_restarts(mine, n_restarts, max_itr, rank, world)
+        ok = sorted(full) == list(range(n_restarts))
+        for i in range(n_restarts):
+            ok &= np.array_equal(full[i]["hist"], all_res[i]["hist"]) and full[i]["converged"] == all_res[i]["converged"]
+            ok &= all(np.array_equal(full[i]["state"][key], all_res[i]["state"][key]) for key in all_res[i]["state"])
+        open(os.path.join(out_dir, f"restart_rank{rank}.txt"), "w").write("ok" if ok else "mismatch")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_restart_results_are_gathered_in_restart_order(tmp_path):
+    """`restart_group`: restart i runs on rank i % world; the all-gather hands every rank every restart's ELBO history,
+    convergence flag and final state bit-for-bit, so the reference's in-order selection rule (:873) can be applied."""
+    port = _free_port()
+    mp.spawn(_restart_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert [open(tmp_path / f"restart_rank{r}.txt").read() for r in range(2)] == ["ok", "ok"]
