@@ -15,8 +15,8 @@
 //     - M-GEMM on the same pipe:  raw[K][SP] += R^T . Phi   with the K x SP accumulators resident in registers for
 //       the whole sweep (warp = all K components x SP/32 feature blocks).
 //   While one consumer warpgroup is in its (non-DMMA) softmax, the other one and the producer keep the DMMA pipe and
-//   the LSU busy.  At the end every consumer warpgroup writes its partial statistics once and the last CTA reduces
-//   all partials in a fixed order (deterministic).
+//   the LSU busy.  At the end the two consumer warpgroups merge their accumulators through shared memory, the CTA
+//   writes ONE partial statistics buffer, and reduce_partials_kernel sums the partials in a fixed order (deterministic).
 //
 // Replaces `_update_q_z` :772-784 (incl. the K-loop of N x D temporaries), `_calc_n_x_bar_s` :725-732 and the
 // `xlogy` term :704 of /root/reference/bayesml/gaussianmixture/_gaussianmixture.py.
