@@ -38,11 +38,6 @@ constexpr int DM_NXS = 2;            // stages of the X ring (TMA); small, so th
 constexpr int DM_XPAD = 4;           // doubles of slack after each X stage (vector loads past the last row)
 constexpr int DM_MAXG = 64;          // entries of the Phi-expansion group table
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
 template <int KB, int SP, int NPS>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 pass_dmma_kernel(const PassArgs a, const Layout L) {

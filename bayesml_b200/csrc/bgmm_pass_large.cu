@@ -3,7 +3,9 @@
 //
 // Two tiled GEMM kernels on the FP64 tensor pipe (mma.sync.m8n8k4.f64 = DMMA.8x8x4), the feature tile Phi generated on the
 // fly in 64-column chunks from the X tile held in shared memory (Phi itself never exists in HBM):
-//   e_large_kernel : ln rho[64 rows][K] = sum over chunks Phi_chunk . coef_chunk^T  (coefficient chunks streamed from L2),
+//   e_large_kernel : ln rho[64 rows][K] = sum over 64-feature chunks Phi_chunk . coef_chunk^T; the A (Phi) fragments are
+//                    built in registers from the X tile (each 8-row block belongs to one warp), the coefficient chunks
+//                    come by TMA from a pre-swizzled image (one extra warp, two stages),
 //                    softmax in the accumulator fragments, entropy term, r written to HBM ([N][K] fp64, the only
 //                    intermediate that leaves the chip: K*8 bytes per sample against (D^2+3D) K flops),
 //   m_large_kernel : raw[K][128-feature chunk] += R^T . Phi_chunk, output-stationary: a CTA owns one feature chunk for a
@@ -58,9 +60,26 @@ __global__ void __launch_bounds__(LG_THREADS) coef_pack_kernel(const double* __r
     }
 }
 
+constexpr int LG_ETHREADS = 288;   // E kernel: 8 GEMM warps + 1 warp that streams the coefficient chunks by TMA
+
+// (i, j) of every logical feature, packed (i << 8) | j; kinds: 0xFFFF constant 1, 0xFE00 | i linear, 0xFFFE padding (zero).
+__global__ void __launch_bounds__(256) feat_table_kernel(unsigned short* __restrict__ tab, const int D, const int P,
+                                                         const int n) {
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= n) return;
+    int kind, i, j;
+    feat_decode(p, D, P, kind, i, j);
+    tab[p] = kind == 2 ? (unsigned short)((i << 8) | j) : (kind == 1 ? (unsigned short)(0xFE00 | i) : (kind == 0 ? 0xFFFF : 0xFFFE));
+}
+
+// In the E-GEMM every 8-row block of Phi is consumed by exactly one warp, so Phi is never staged in shared memory: each
+// thread builds its A fragments (row g of its block, the features of its quad lane q) from the X tile in registers, one
+// in-stream DMUL per fragment.  (A separate producer starves: its DMULs queue behind the GEMM warps' DMMAs on the in-order
+// FP64 pipe, ~250 cycles each — measured, profiles/.)  The X tile has a padded row pitch (conflict-free column reads).
 template <int KB>
-__global__ void __launch_bounds__(LG_THREADS, 1)
-e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const double* __restrict__ packed) {
+__global__ void __launch_bounds__(LG_ETHREADS, 1)
+e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const double* __restrict__ packed,
+               const unsigned short* __restrict__ ftab) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = L.K, D = L.D, P = L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -68,138 +87,161 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
     if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
     const double* __restrict__ x = static_cast<const double*>(a.x);
 
-    double* phiS = reinterpret_cast<double*>(smem_raw);        // [64][64] swizzled
-    double* coefS = phiS + LG_ETILE * LG_CW;                   // [2 stages][8*KB][64] swizzled (TMA destination)
-    double* xs = coefS + 2 * 8 * KB * LG_CW;                   // [64][D]
-    double* red = xs + LG_ETILE * D;                           // [40]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 40);    // [2]
-    constexpr uint32_t kChunkBytes = 8 * KB * LG_CW * sizeof(double);
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    uint32_t ph[2] = {0u, 0u};
-
     const int nchunk = (P + LG_CW - 1) / LG_CW;
+    const int XP = D + 2;                                      // padded pitch: 8 rows x same column -> 8 distinct bank groups
+    double* coefS = reinterpret_cast<double*>(smem_raw);       // [2 stages][8*KB][64] swizzled (TMA destination)
+    double* xs = coefS + 2 * 8 * KB * LG_CW;                   // [64][D + 2]
+    double* red = xs + LG_ETILE * XP;                          // [40]
+    uint64_t* cfull = reinterpret_cast<uint64_t*>(red + 40);   // [2]  coefficient chunk landed (TMA tx)
+    uint64_t* cempty = cfull + 2;                              // [2]  stage consumed (256 arrivals)
+    unsigned short* tabS = reinterpret_cast<unsigned short*>(cempty + 2);   // [nchunk * 64]
+    constexpr uint32_t kChunkBytes = 8 * KB * LG_CW * sizeof(double);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&cfull[i], 1); mbar_init(&cempty[i], 256); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int p = tid; p < nchunk * LG_CW; p += LG_ETHREADS) tabS[p] = ftab[p];
+    __syncthreads();
+
     const int64_t ntiles = (a.n + LG_ETILE - 1) / LG_ETILE;
-    const int fg = fsw(g);
-    const int lrow = 8 * warp + g;
-    const double* eA = phiS + lrow * LG_CW;
-    const int eo0 = (2 * q) ^ fg, eo1 = (8 + 2 * q) ^ fg;
-    const int fcol = tid & (LG_CW - 1), frow0 = tid >> 6;      // Phi generation: one column, rows frow0 + 4s
-    const int fphys = phys_col(fcol);
-    double ent = 0.0, sprod = 1.0;
-    int it = 0;
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    double ent = 0.0;
 
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-        const int64_t row0 = t * LG_ETILE;
-        const int rows = (int)min((int64_t)LG_ETILE, a.n - row0);
-        __syncthreads();                                       // previous tile's GEMMs done: xs / coefS[0] are free
-        if (tid == 0) {                                        // chunk 0 of the coefficient image -> stage 0
-            mbar_expect_tx(&bars[0], kChunkBytes);
-            tma_load_1d(coefS, packed, kChunkBytes, &bars[0]);
+    if (warp == 8) {
+        // =========================== TMA WARP: coefficient chunks, two stages ===========================
+        // the whole warp walks the loop (convergent at the final block barrier); lane 0 issues the copies
+        const int64_t total = my_tiles * nchunk;
+        int c = 0;
+        for (int64_t cc = 0; cc < total; ++cc) {
+            const int b = (int)(cc & 1);
+            if (cc >= 2) mbar_wait(&cempty[b], (uint32_t)(((cc >> 1) - 1) & 1));
+            if (lane == 0) {
+                mbar_expect_tx(&cfull[b], kChunkBytes);
+                tma_load_1d(coefS + b * 8 * KB * LG_CW, packed + (int64_t)c * 8 * KB * LG_CW, kChunkBytes, &cfull[b]);
+            }
+            __syncwarp();
+            if (++c == nchunk) c = 0;
         }
-        for (int e = tid; e < LG_ETILE * D; e += LG_THREADS) xs[e] = (e < rows * D) ? x[row0 * D + e] : 0.0;
-        double acc[2][KB][2];
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb) { acc[m][kb][0] = 0.0; acc[m][kb][1] = 0.0; }
-
-        for (int c = 0; c < nchunk; ++c) {
-            __syncthreads();                                   // xs ready (c == 0) / previous chunk's GEMM finished
-            if (tid == 0 && c + 1 < nchunk) {                  // prefetch the next coefficient chunk into the other stage
-                const int nb = (c + 1) & 1;
-                mbar_expect_tx(&bars[nb], kChunkBytes);
-                tma_load_1d(coefS + nb * 8 * KB * LG_CW, packed + (int64_t)(c + 1) * 8 * KB * LG_CW, kChunkBytes, &bars[nb]);
+    } else {
+        // =========================== GEMM WARPS ===========================
+        const int fg = fsw(g);
+        const int lrow = 8 * warp + g;
+        const int eo0 = (2 * q) ^ fg, eo1 = (8 + 2 * q) ^ fg;
+        const double* xr = xs + lrow * XP;                     // this thread's row of the X tile
+        double sprod = 1.0;
+        int64_t cc = 0;
+        int it = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int64_t row0 = t * LG_ETILE;
+            const int rows = (int)min((int64_t)LG_ETILE, a.n - row0);
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // every GEMM warp is done with the previous X tile
+            for (int e = tid; e < LG_ETILE * D; e += 256) {
+                const int r = e / D, c = e - r * D;
+                xs[r * XP + c] = (e < rows * D) ? x[row0 * D + e] : 0.0;
             }
-            int kind, fi, fj;
-            feat_decode(LG_CW * c + fcol, D, P, kind, fi, fj);
-#pragma unroll 4
-            for (int s = 0; s < LG_ETILE / 4; ++s) {
-                const int r = frow0 + 4 * s;
-                phiS[r * LG_CW + (fphys ^ fsw(r))] = feat_value(kind, fi, fj, xs + r * D);
-            }
-            mbar_wait(&bars[c & 1], ph[c & 1]);
-            ph[c & 1] ^= 1u;
-            __syncthreads();
-            const double* eB = coefS + (c & 1) * 8 * KB * LG_CW + g * LG_CW;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            double acc[2][KB][2];
 #pragma unroll
-            for (int w = 0; w < LG_CW / 16; ++w) {
-                const double2 a0 = lds2(eA + 16 * w + eo0), a1 = lds2(eA + 16 * w + eo1);
+            for (int m = 0; m < 2; ++m)
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    const double2 b0 = lds2(eB + kb * 8 * LG_CW + 16 * w + eo0);
-                    const double2 b1 = lds2(eB + kb * 8 * LG_CW + 16 * w + eo1);
-                    dmma(acc[0][kb][0], acc[0][kb][1], a0.x, b0.x);
-                    dmma(acc[1][kb][0], acc[1][kb][1], a0.y, b0.y);
-                    dmma(acc[0][kb][0], acc[0][kb][1], a1.x, b1.x);
-                    dmma(acc[1][kb][0], acc[1][kb][1], a1.y, b1.y);
+                for (int kb = 0; kb < KB; ++kb) { acc[m][kb][0] = 0.0; acc[m][kb][1] = 0.0; }
+            for (int c = 0; c < nchunk; ++c, ++cc) {
+                const int b = (int)(cc & 1);
+                // A fragments of this chunk: logical features 64c + 16w + {q, 4+q, 8+q, 12+q}, w = 0..3
+                double af[4][4];
+                const unsigned short* tb = tabS + LG_CW * c + q;
+#pragma unroll
+                for (int w = 0; w < 4; ++w)
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const unsigned int code = tb[16 * w + 4 * h];
+                        const int fi = code >> 8, fj = code & 0xFF;
+                        double v;
+                        if (fi < 0xFE) v = xr[fi] * xr[fj];
+                        else if (fi == 0xFE) v = xr[fj];
+                        else v = (fj == 0xFF) ? 1.0 : 0.0;
+                        af[w][h] = v;
+                    }
+                mbar_wait(&cfull[b], (uint32_t)((cc >> 1) & 1));
+                const double* eB = coefS + b * 8 * KB * LG_CW + g * LG_CW;
+#pragma unroll
+                for (int w = 0; w < LG_CW / 16; ++w) {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const double2 b0 = lds2(eB + kb * 8 * LG_CW + 16 * w + eo0);
+                        const double2 b1 = lds2(eB + kb * 8 * LG_CW + 16 * w + eo1);
+                        dmma(acc[0][kb][0], acc[0][kb][1], af[w][0], b0.x);      // feature 16w + q
+                        dmma(acc[1][kb][0], acc[1][kb][1], af[w][1], b0.y);      // feature 16w + 4 + q
+                        dmma(acc[0][kb][0], acc[0][kb][1], af[w][2], b1.x);      // feature 16w + 8 + q
+                        dmma(acc[1][kb][0], acc[1][kb][1], af[w][3], b1.y);      // feature 16w + 12 + q
+                    }
                 }
+                mbar_arrive(&cempty[b]);
             }
-        }
-        double lr[KB][2];
+            double lr[KB][2];
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-            lr[kb][0] = acc[0][kb][0] + acc[1][kb][0];
-            lr[kb][1] = acc[0][kb][1] + acc[1][kb][1];
-        }
-        // ---- softmax over k for row lrow; this thread holds components 8kb + 2q + {0,1} ----
-        const int64_t grow = row0 + lrow;
-        const bool valid = lrow < rows;
-        double mx = -INFINITY;
+            for (int kb = 0; kb < KB; ++kb) {
+                lr[kb][0] = acc[0][kb][0] + acc[1][kb][0];
+                lr[kb][1] = acc[0][kb][1] + acc[1][kb][1];
+            }
+            // ---- softmax over k for row lrow; this thread holds components 8kb + 2q + {0,1} ----
+            const int64_t grow = row0 + lrow;
+            const bool valid = lrow < rows;
+            double mx = -INFINITY;
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) mx = fmax(mx, fmax(lr[kb][0], lr[kb][1]));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        if (a.lnrho_out != nullptr && valid) {
+            for (int kb = 0; kb < KB; ++kb) mx = fmax(mx, fmax(lr[kb][0], lr[kb][1]));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            if (a.lnrho_out != nullptr && valid) {
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int k = 8 * kb + 2 * q + e;
+                        if (k < K) a.lnrho_out[grow * K + k] = lr[kb][e];
+                    }
+            }
+            double sum = 0.0, dot = 0.0;
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int k = 8 * kb + 2 * q + e;
-                    if (k < K) a.lnrho_out[grow * K + k] = lr[kb][e];
+                    const double z = lr[kb][e] - mx;
+                    const double ex = exp_nonpos(z);
+                    lr[kb][e] = ex;
+                    sum += ex;
+                    dot = fma(ex, z, dot);
                 }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+            dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+            const double inv = valid ? 1.0 / sum : 0.0;
+            if (valid && q == 0) { ent = fma(dot, inv, ent); sprod *= sum; }
+            if ((it & 7) == 7) { ent -= log(sprod); sprod = 1.0; }
+            int best = 0x7fffffff;
+            double bestv = -1.0;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double r = lr[kb][e] * inv;
+                    const int k = 8 * kb + 2 * q + e;
+                    if (r > bestv) { bestv = r; best = k; }
+                    if (valid && k < K) a.r_out[grow * K + k] = r;      // r_out is mandatory in this regime (the M kernel's input)
+                }
+            if (a.argmax_out != nullptr) {
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+                    const int ok = __shfl_xor_sync(0xffffffffu, best, o);
+                    if (ov > bestv || (ov == bestv && ok < best)) { bestv = ov; best = ok; }
+                }
+                if (valid && q == 0) a.argmax_out[grow] = best;
+            }
         }
-        double sum = 0.0, dot = 0.0;
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double z = lr[kb][e] - mx;
-                const double ex = exp_nonpos(z);
-                lr[kb][e] = ex;
-                sum += ex;
-                dot = fma(ex, z, dot);
-            }
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-        const double inv = valid ? 1.0 / sum : 0.0;
-        if (valid && q == 0) { ent = fma(dot, inv, ent); sprod *= sum; }
-        if ((it & 7) == 7) { ent -= log(sprod); sprod = 1.0; }
-        int best = 0x7fffffff;
-        double bestv = -1.0;
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double r = lr[kb][e] * inv;
-                const int k = 8 * kb + 2 * q + e;
-                if (r > bestv) { bestv = r; best = k; }
-                if (valid && k < K) a.r_out[grow * K + k] = r;      // r_out is mandatory in this regime (the M kernel's input)
-            }
-        if (a.argmax_out != nullptr) {
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bestv, o);
-                const int ok = __shfl_xor_sync(0xffffffffu, best, o);
-                if (ov > bestv || (ov == bestv && ok < best)) { bestv = ov; best = ok; }
-            }
-            if (valid && q == 0) a.argmax_out[grow] = best;
-        }
+        ent -= log(sprod);
     }
-    ent -= log(sprod);
     ent = block_sum(ent, red);
     if (tid == 0) ews[blockIdx.x] = ent;
 }
@@ -351,8 +393,8 @@ static void large_plan(int K, int D, int64_t n, int& grid_e, int& n_chunks, int&
 int64_t large_workspace_doubles(int K, int D) {
     if (K > 64 || D > 128) return 0;
     const int64_t nchunk = (feat_count(D) + LG_CW - 1) / LG_CW;
-    // <= 64 row splits + E-kernel entropy partials + the packed coefficient image (nchunk x [8*KB][64])
-    return (int64_t)64 * ((int64_t)K * feat_pitch(D) + 8) + 256 + nchunk * 64 * LG_CW;
+    // <= 64 row splits + E-kernel entropy partials + the packed coefficient image (nchunk x [8*KB][64]) + the (i, j) table
+    return (int64_t)64 * ((int64_t)K * feat_pitch(D) + 8) + 256 + nchunk * 64 * LG_CW + (nchunk * LG_CW + 3) / 4 + 8;
 }
 
 template <int KB>
@@ -363,8 +405,9 @@ static int launch_large_t(const PassArgs& a, const Layout& L, cudaStream_t strea
     double* ews = a.workspace + (int64_t)64 * len;
     double* packed = ews + 256;
     const int nchunk_e = (L.P + LG_CW - 1) / LG_CW;
-    const size_t smem_e = sizeof(double) * ((size_t)LG_ETILE * LG_CW + (size_t)2 * 8 * KB * LG_CW + (size_t)LG_ETILE * L.D + 40) +
-                          2 * sizeof(uint64_t) + 128;
+    unsigned short* ftab = reinterpret_cast<unsigned short*>(packed + (int64_t)nchunk_e * 8 * KB * LG_CW);
+    const size_t smem_e = sizeof(double) * ((size_t)2 * 8 * KB * LG_CW + (size_t)LG_ETILE * (L.D + 2) + 40) + 4 * sizeof(uint64_t) +
+                          sizeof(unsigned short) * (size_t)nchunk_e * LG_CW + 128;
     constexpr int RP = (8 * KB < 16) ? 16 : 8 * KB;
     const size_t smem_m = sizeof(double) * ((size_t)LG_MSUB * LG_MCW + (size_t)LG_MSUB * RP + (size_t)LG_MSUB * L.D +
                                             (size_t)LG_MSUB * L.K + 2) + sizeof(uint64_t) + 128;
@@ -373,7 +416,8 @@ static int launch_large_t(const PassArgs& a, const Layout& L, cudaStream_t strea
     e = cudaFuncSetAttribute(m_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(m_large)");
     coef_pack_kernel<KB><<<nchunk_e, LG_THREADS, 0, stream>>>(a.state, L, packed, a.force);
-    e_large_kernel<KB><<<grid_e, LG_THREADS, smem_e, stream>>>(a, L, ews, packed);
+    feat_table_kernel<<<(nchunk_e * LG_CW + 255) / 256, 256, 0, stream>>>(ftab, L.D, L.P, nchunk_e * LG_CW);
+    e_large_kernel<KB><<<grid_e, LG_ETHREADS, smem_e, stream>>>(a, L, ews, packed, ftab);
     m_large_kernel<KB><<<dim3(n_chunks, nsplit), LG_THREADS, smem_m, stream>>>(a, L, ews, grid_e, nsplit);
     launch_reduce_partials(a, L, nsplit, stream);
     return check_cuda(cudaGetLastError(), "pass_large launch");
