@@ -9,7 +9,8 @@
 //                    softmax in the accumulator fragments, entropy term, r written to HBM ([N][K] fp64, the only
 //                    intermediate that leaves the chip: K*8 bytes per sample against (D^2+3D) K flops),
 //   m_large_kernel : raw[K][128-feature chunk] += R^T . Phi_chunk, output-stationary: a CTA owns one feature chunk for a
-//                    contiguous range of rows (grid = chunks x row splits), accumulators in registers,
+//                    contiguous range of rows (grid = chunks x row splits), accumulators in registers, the B (Phi)
+//                    fragments built in registers from TMA-prefetched X tiles,
 // then reduce_partials_kernel sums the row splits in a fixed order (deterministic).
 // Same shared-memory fragment layout (k-step-pair permutation + XOR swizzle) as the fused kernel (bgmm_mma.cuh).
 // Replaces `_update_q_z` :772-784, `_calc_n_x_bar_s` :725-732, `xlogy` :704 of the reference GMM file for these shapes.
@@ -246,6 +247,10 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
     if (tid == 0) ews[blockIdx.x] = ent;
 }
 
+// Output-stationary statistics GEMM.  A CTA owns the 128-feature chunk cx for the rows of split ry; warp w owns the
+// feature blocks 2w, 2w+1 and thread column g of each, i.e. two FIXED features per thread, whose Phi values (the B
+// fragments) it forms in registers from the X tile: two in-stream DMULs per 2*KB DMMAs, no Phi tile in shared memory.
+// X tiles (double buffered) and r tiles arrive by TMA one step ahead; r is re-laid out into the swizzled A-fragment tile.
 template <int KB>
 __global__ void __launch_bounds__(LG_THREADS, 2)
 m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews, const int n_ews, const int nsplit) {
@@ -258,26 +263,24 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
     const double* __restrict__ x = static_cast<const double*>(a.x);
     const double* __restrict__ rws = a.r_out;
 
-    double* phiS = reinterpret_cast<double*>(smem_raw);        // [32][128] swizzled
-    double* rS = phiS + LG_MSUB * LG_MCW;                      // [32][RP] swizzled
-    double* xs = rS + LG_MSUB * RP;                            // [32][D]   TMA destination
-    double* rst = xs + LG_MSUB * D;                            // [32][K]   TMA destination (row-major, as in HBM)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(rst + ((LG_MSUB * K + 1) & ~1));
+    double* rS = reinterpret_cast<double*>(smem_raw);          // [32][RP] swizzled A-fragment tile
+    double* xs = rS + LG_MSUB * RP;                            // [2 stages][32][D]   TMA destination
+    double* rst = xs + 2 * LG_MSUB * D;                        // [32][K]             TMA destination (row-major, as in HBM)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rst + ((LG_MSUB * K + 1) & ~1));   // [2]
     const uint32_t xbytes = (uint32_t)(LG_MSUB * D * sizeof(double)), rbytes = (uint32_t)(LG_MSUB * K * sizeof(double));
-    if (tid == 0) mbar_init(bar, 1);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    uint32_t ph = 0u;
+    uint32_t ph[2] = {0u, 0u};
 
     const int cx = blockIdx.x, ry = blockIdx.y;
     const int64_t nsub = (a.n + LG_MSUB - 1) / LG_MSUB;
     const int64_t per = (nsub + nsplit - 1) / nsplit;
     const int64_t s_begin = ry * per, s_end = min(nsub, s_begin + per);
 
-    // this thread's Phi column (fixed for the whole kernel) and rows r0 + 2s
-    const int fcol = tid & (LG_MCW - 1), frow0 = tid >> 7;
-    int kind, fi, fj;
-    feat_decode(LG_MCW * cx + fcol, D, P, kind, fi, fj);
-    const int fphys = phys_col(fcol);
+    // this thread's two features (logical order: B column g of block b is feature 128cx + 8b + g)
+    int kind0, i0, j0, kind1, i1, j1;
+    feat_decode(LG_MCW * cx + 8 * (2 * warp) + g, D, P, kind0, i0, j0);
+    feat_decode(LG_MCW * cx + 8 * (2 * warp + 1) + g, D, P, kind1, i1, j1);
     for (int e = tid; e < LG_MSUB * RP; e += LG_THREADS) rS[e] = 0.0;     // padded components stay zero
 
     double macc[2][KB][2];
@@ -287,29 +290,28 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
         for (int kb = 0; kb < KB; ++kb) { macc[l][kb][0] = 0.0; macc[l][kb][1] = 0.0; }
     const int fq = fsw(q);
     const double* mR = rS + q * RP + ((2 * g) ^ fq);
-    const double* mP0 = phiS + q * LG_MCW + ((8 * (2 * warp) + g) ^ fq);
-    const double* mP1 = phiS + q * LG_MCW + ((8 * (2 * warp + 1) + g) ^ fq);
 
-    // full 32-row steps arrive by TMA, issued one step ahead (the staging tiles are free as soon as Phi and the swizzled r
-    // tile have been built); a ragged last step uses plain loads
-    auto issue = [&](int64_t sb) {
+    auto issue = [&](int64_t sb, int b) {                      // full 32-row steps only; a ragged last step uses plain loads
         const int64_t row0 = sb * LG_MSUB;
         if (sb < s_end && row0 + LG_MSUB <= a.n) {
-            mbar_expect_tx(bar, xbytes + rbytes);
-            tma_load_1d(xs, x + row0 * D, xbytes, bar);
-            tma_load_1d(rst, rws + row0 * K, rbytes, bar);
+            mbar_expect_tx(&bars[b], xbytes + rbytes);
+            tma_load_1d(xs + b * LG_MSUB * D, x + row0 * D, xbytes, &bars[b]);
+            tma_load_1d(rst, rws + row0 * K, rbytes, &bars[b]);
         }
     };
     __syncthreads();
-    if (tid == 0) issue(s_begin);
-    for (int64_t sb = s_begin; sb < s_end; ++sb) {
+    if (tid == 0) issue(s_begin, 0);
+    int it = 0;
+    for (int64_t sb = s_begin; sb < s_end; ++sb, ++it) {
+        const int b = it & 1;
         const int64_t row0 = sb * LG_MSUB;
         const int rows = (int)min((int64_t)LG_MSUB, a.n - row0);
+        double* xt = xs + b * LG_MSUB * D;
         if (rows == LG_MSUB) {
-            mbar_wait(bar, ph);
-            ph ^= 1u;
+            mbar_wait(&bars[b], ph[b]);
+            ph[b] ^= 1u;
         } else {
-            for (int e = tid; e < LG_MSUB * D; e += LG_THREADS) xs[e] = (e < rows * D) ? x[row0 * D + e] : 0.0;
+            for (int e = tid; e < LG_MSUB * D; e += LG_THREADS) xt[e] = (e < rows * D) ? x[row0 * D + e] : 0.0;
             for (int e = tid; e < LG_MSUB * K; e += LG_THREADS) rst[e] = (e < rows * K) ? rws[row0 * K + e] : 0.0;
             __syncthreads();
         }
@@ -318,13 +320,8 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
             const int kb = k >> 3, cc = k & 7;
             rS[r * RP + ((16 * (kb >> 1) + 2 * cc + (kb & 1)) ^ fsw(r))] = rst[e];
         }
-#pragma unroll 4
-        for (int s = 0; s < LG_MSUB / 2; ++s) {
-            const int r = frow0 + 2 * s;
-            phiS[r * LG_MCW + (fphys ^ fsw(r))] = feat_value(kind, fi, fj, xs + r * D);
-        }
-        __syncthreads();
-        if (tid == 0) issue(sb + 1);                           // staging tiles consumed: prefetch the next step
+        __syncthreads();                                       // rS built, rst free; every warp finished the previous GEMM
+        if (tid == 0) issue(sb + 1, b ^ 1);                    // prefetch the next step (other X stage, the r staging tile)
 #pragma unroll
         for (int ks = 0; ks < LG_MSUB / 4; ++ks) {
             double ra[KB];
@@ -338,14 +335,15 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
             } else {
                 ra[0] = mR[ks * 4 * RP];
             }
-            const double b0 = mP0[ks * 4 * LG_MCW], b1 = mP1[ks * 4 * LG_MCW];
+            const double* xr = xt + (4 * ks + q) * D;
+            const double b0 = feat_value(kind0, i0, j0, xr), b1 = feat_value(kind1, i1, j1, xr);
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
                 dmma(macc[0][kb][0], macc[0][kb][1], ra[kb], b0);
                 dmma(macc[1][kb][0], macc[1][kb][1], ra[kb], b1);
             }
         }
-        __syncthreads();                                       // GEMM finished: rS / phiS may be rebuilt
+        __syncthreads();                                       // GEMM finished: rS may be rebuilt, this X stage refilled
     }
 
     // ---- partial of this row split (logical layout [K][pitch]); split 0 also carries the entropy term ----
@@ -353,13 +351,13 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
     double* part = a.workspace + (int64_t)ry * len;
 #pragma unroll
     for (int l = 0; l < 2; ++l) {
-        const int b = 2 * warp + l;
+        const int bb = 2 * warp + l;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int k = 8 * kb + g;
-                const int p = LG_MCW * cx + 8 * b + 4 * e + q;          // physical 8b + 2q + e <-> logical 8b + 4e + q
+                const int k = 8 * kb + g;                              // C fragment: row g = component, cols 2q+e = feature 8bb + 2q + e
+                const int p = LG_MCW * cx + 8 * bb + 2 * q + e;
                 if (k < K && p < L.pitch) part[(int64_t)k * L.pitch + p] = macc[l][kb][e];
             }
     }
@@ -409,8 +407,8 @@ static int launch_large_t(const PassArgs& a, const Layout& L, cudaStream_t strea
     const size_t smem_e = sizeof(double) * ((size_t)2 * 8 * KB * LG_CW + (size_t)LG_ETILE * (L.D + 2) + 40) + 4 * sizeof(uint64_t) +
                           sizeof(unsigned short) * (size_t)nchunk_e * LG_CW + 128;
     constexpr int RP = (8 * KB < 16) ? 16 : 8 * KB;
-    const size_t smem_m = sizeof(double) * ((size_t)LG_MSUB * LG_MCW + (size_t)LG_MSUB * RP + (size_t)LG_MSUB * L.D +
-                                            (size_t)LG_MSUB * L.K + 2) + sizeof(uint64_t) + 128;
+    const size_t smem_m = sizeof(double) * ((size_t)LG_MSUB * RP + (size_t)2 * LG_MSUB * L.D + (size_t)LG_MSUB * L.K + 2) +
+                          2 * sizeof(uint64_t) + 128;
     cudaError_t e = cudaFuncSetAttribute(e_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(e_large)");
     e = cudaFuncSetAttribute(m_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
