@@ -20,15 +20,20 @@ def reference_available() -> bool:
 
 def load_reference_gaussianmixture():
     """Returns the reference's `bayesml.gaussianmixture` module (GenModel, LearnModel)."""
+    return load_reference_module("gaussianmixture")
+
+
+def load_reference_module(name):
+    """Returns the reference's `bayesml.<name>` sub-package (gaussianmixture, hiddenmarkovnormal, multivariate_normal)."""
     if not reference_available():
         raise ImportError(f"reference tree not found under {REFERENCE_ROOT}")
-    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors"):
-        if name not in sys.modules:
-            sys.modules[name] = mock.MagicMock(name=name)
+    for mod in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors"):
+        if mod not in sys.modules:
+            sys.modules[mod] = mock.MagicMock(name=mod)
     sys.dont_write_bytecode = True  # the reference mount is read-only
     if "bayesml" not in sys.modules:
         pkg = types.ModuleType("bayesml")
         pkg.__path__ = [os.path.join(REFERENCE_ROOT, "bayesml")]
         sys.modules["bayesml"] = pkg
-    from bayesml import gaussianmixture  # noqa: E402
-    return gaussianmixture
+    import importlib
+    return importlib.import_module("bayesml." + name)
