@@ -1,6 +1,6 @@
-"""Argument validators used by the drop-in gaussianmixture API.
+"""Argument validators used by the drop-in gaussianmixture / hiddenmarkovnormal API.
 
-Only the validators on the gaussianmixture.LearnModel path are provided; each has the contract of the
+Only the validators on the LearnModel paths are provided; each has the contract of the
 reference function of the same name in bayesml/_check.py (cited per function): return the (possibly
 float-cast) value or raise `exception_class(<name> + message)`.
 """
@@ -70,3 +70,23 @@ def pos_def_sym_mats(val, val_name, exception_class):
             raise exception_class(
                 val_name + " must be a positive definite symmetric 2-dimensional numpy.ndarray.") from None
     raise exception_class(val_name + " must be a symmetric 2-dimensional numpy.ndarray.")
+
+
+def floats(val, val_name, exception_class):
+    """Real scalar, or numeric ndarray; integers are cast to float (reference _check.py:163-173)."""
+    if _is_float(val):
+        return val
+    if _is_int(val):
+        return float(val)
+    if _is_array_of(val, np.integer):
+        return val.astype(float)
+    if _is_array_of(val, np.floating):
+        return val
+    raise exception_class(val_name + " must be float or a numpy.ndarray.")
+
+
+def shape_consistency(val, val_name, correct, correct_name, exception_class):
+    """`val` (a dimension) must equal `correct` (reference _check.py:268-272)."""
+    if val != correct:
+        raise exception_class(f"{val_name} must coincide with {correct_name}: "
+                              f"{val_name} = {val}, {correct_name} = {correct}")

@@ -20,6 +20,9 @@ POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb"
 CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR, CTRL_SEQ = range(8)
 MAX_RANKS = 16
 N_CTRL = 16
+HMM_OFF_NAMES = ("zeta0", "lncz0", "set0", "set1", "set_zeta", "set_lna", "set_at", "set_misc", "ms", "g0", "sc", "vlx",
+                 "total")
+HMM_FULL, HMM_STATS_FROM_GAMMA = 0, 1
 
 _lib = None
 
@@ -67,6 +70,16 @@ def load():
     lib.bgmm_comm_free.argtypes = [vp]
     lib.bgmm_publish.restype = i32
     lib.bgmm_publish.argtypes = [i32, i32, vp, vp, i32, vp]
+    lib.bgmm_hmm_layout.restype = i32
+    lib.bgmm_hmm_layout.argtypes = [i32, ctypes.POINTER(i64)]
+    lib.bgmm_hmm_supported.restype = i32
+    lib.bgmm_hmm_supported.argtypes = [i32, i32]
+    lib.bgmm_hmm_scan_workspace_doubles.restype = i64
+    lib.bgmm_hmm_scan_workspace_doubles.argtypes = [i32, i64]
+    lib.bgmm_hmm_pass.restype = i32
+    lib.bgmm_hmm_pass.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.bgmm_hmm_small.restype = i32
+    lib.bgmm_hmm_small.argtypes = [i32, i32, vp, vp, i32, i32, f64, i32, vp]
     if lib.bgmm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"libbgmm ABI {lib.bgmm_abi_version()} != binding ABI {ABI_VERSION}; rebuild the library")
     _lib = lib
@@ -86,3 +99,11 @@ def layout(K, D, hist_len):
     poff = (ctypes.c_int64 * len(POFF_NAMES))()
     check(lib.bgmm_layout(K, D, hist_len, off, poff), "bgmm_layout")
     return dict(zip(OFF_NAMES, off)), dict(zip(POFF_NAMES, poff))
+
+
+def hmm_layout(K):
+    """Offsets (in doubles) of the hidden-Markov extension block; see include/bgmm.h."""
+    lib = load()
+    off = (ctypes.c_int64 * len(HMM_OFF_NAMES))()
+    check(lib.bgmm_hmm_layout(K, off), "bgmm_hmm_layout")
+    return dict(zip(HMM_OFF_NAMES, off))

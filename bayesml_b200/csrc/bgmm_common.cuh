@@ -114,7 +114,33 @@ struct PassArgs {
     int32_t* argmax_out;
     const double* r_in;
     int force, accumulate;
+    int lnrho_only = 0;   // large-regime E kernel: write ln rho only (no softmax / r / entropy): the HMM emission pass
 };
+
+// HMM extension block ("hst", doubles) next to the state block: transition-matrix hyperparameters and features, the
+// statistics the forward-backward scan produces, and the HMM-specific ELBO terms (include/bgmm.h: bgmm_hmm_layout).
+struct HmmLayout {
+    int K;
+    int64_t KK, zeta0, lncz0, set[2], s_zeta, s_lna, s_at, s_misc, ms, g0, sc, vlx, total;
+};
+__host__ __device__ inline HmmLayout make_hmm_layout(int K) {
+    HmmLayout H;
+    H.K = K;
+    H.KK = align8((int64_t)K * K);
+    H.s_zeta = 0; H.s_lna = H.KK; H.s_at = 2 * H.KK; H.s_misc = 3 * H.KK;   // misc: [0] max ln a~, [1] ln C(zeta) sum
+    const int64_t setlen = 3 * H.KK + 8;
+    int64_t o = 0;
+    H.zeta0 = o; o += H.KK;
+    H.lncz0 = o; o += 8;
+    H.set[0] = o; o += setlen;
+    H.set[1] = o; o += setlen;
+    H.ms = o; o += H.KK;
+    H.g0 = o; o += align8(K);
+    H.sc = o; o += 8;        // [0] sum ln c_i   [1] sum gamma . ln rho
+    H.vlx = o; o += 8;       // [0] E ln p(z)  [1] E ln p(A)  [2] -E ln q(z)  [3] -E ln q(A)
+    H.total = o;
+    return H;
+}
 
 // sum of `nparts` per-CTA partial statistics buffers (workspace) into state.STATS, fixed order (bgmm_pass_dmma.cu)
 void launch_reduce_partials(const PassArgs& a, const Layout& L, int nparts, cudaStream_t stream);

@@ -1,0 +1,442 @@
+// bgmm_hmm_pass: the E-step of the variational-Bayes hidden-Markov model with Gaussian emissions on one B200.
+//
+// Replaces, in /root/reference/bayesml/hiddenmarkovnormal/_hiddenmarkovnormal.py, `_update_q_z` :1020-1026 =
+//   _calc_rho :988-997          ln rho[n][k] (emission log density under q)        -> e_large_kernel, ln-rho-only mode
+//   _forward :999-1006          alpha_i = rho_i o (alpha_{i-1} A~) / c_i            -> fwd_basis / fwd_seq / fwd_chunk
+//   _backward :1008-1011        beta_i = A~ (rho_{i+1} o beta_{i+1}) / c_{i+1}       -> bwd_basis / bwd_seq / bwd_chunk
+//   _update_gamma :1013-1014    gamma = alpha o beta                                 -> bwd_chunk
+//   _update_xi :1016-1018       xi_i = alpha_{i-1} rho_i A~ beta_i / c_i; only sum_i xi_i (= ms, :839) is formed
+//   _calc_n_m_x_bar_s :837-845  N_k, x_bar_k, S_k with gamma as weights              -> m_large_kernel + reduction
+//
+// The reference runs both recursions sequentially over the sequence (a Python loop).  Here the sequence is cut into
+// chunks and each recursion becomes three phases (numpy model + test: tools/hmm_scan_model.py):
+//   A  (parallel over chunk x start state): the recursion from each unit vector -> chunk transfer matrix, every row
+//      normalised with its log scale kept;
+//   B  (one warp, sequential over chunks): propagate the boundary vector through the transfer matrices;
+//   C  (parallel over chunks): the reference's exact recursion from the chunk's boundary vector, writing alpha, c
+//      (forward) or gamma, sum xi, sum gamma ln rho (backward).
+// Phase A costs K times phase C (N K^3 flops); everything is FP64 CUDA-core work on small per-state vectors: a group
+// of KP = 2^ceil(log2 K) lanes owns one chunk (32 / KP chunks per warp), state vectors are exchanged through a per-warp
+// shared-memory line (one STS + K/2 broadcast LDS.128 per step).  All sums are in a fixed order (deterministic).
+#include "bgmm_common.cuh"
+#include <math.h>
+
+namespace bgmm {
+
+int launch_pass_large_part(const PassArgs& a, int K, int D, int dtype, int which, cudaStream_t stream);
+bool large_supported(int K, int D, int dtype);
+
+constexpr int HW = 4;            // warps per CTA in the scan kernels
+constexpr int HT = 32 * HW;
+
+struct ScanPlan {
+    int64_t n;
+    int K, L, nch;
+};
+
+__host__ __device__ inline int hmm_chunk_len(int64_t n) {
+    int64_t L = (n + 8191) / 8192;
+    if (L < 32) L = 32;
+    return (int)((L + 7) & ~int64_t(7));
+}
+
+template <int KP>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = KP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// every lane publishes `v`; returns nothing — the caller then reads the KP values of its group from `line`
+template <int KP>
+__device__ __forceinline__ void publish(double* line, int lane, double v) {
+    line[lane] = v;
+    __syncwarp();
+}
+
+// dot of the group's published vector with this lane's K-vector `m`, four independent partial sums
+template <int KP>
+__device__ __forceinline__ double group_dot(const double* line, int gbase, const double (&m)[KP]) {
+    double s0 = 0.0, s1 = 0.0;
+    if (KP >= 2) {
+        const double2* p = reinterpret_cast<const double2*>(line + gbase);
+#pragma unroll
+        for (int j = 0; j < KP / 2; ++j) {
+            const double2 v = p[j];
+            s0 = fma(v.x, m[2 * j], s0);
+            s1 = fma(v.y, m[2 * j + 1], s1);
+        }
+    }
+    return s0 + s1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward recursion over one chunk from a given start vector.  BASIS: start = unit vector j, keep the normalised end
+// vector and its log scale (phase A).  Otherwise: start = boundary vector v[c]; write alpha, c, sum ln c (phase C).
+// Lane kk of a group owns state kk and column kk of A~.
+struct ScanBufs {
+    const double* lnrho;   // [n][K]
+    double* alpha;         // [n][K]
+    double* gamma;         // [n][K]
+    double* cs;            // [n]
+    double* beta_out;      // [n][K] or NULL
+    double* tf;            // [nch][K][K] transfer matrices (forward, then reused backward)
+    double* ls;            // [nch][K]    their log scales
+    double* vb;            // [nch][K]    chunk boundary vectors (forward, then reused backward)
+    double* ps;            // [nch][K][K] xi-sum partials
+    double* plc;           // [nch]       sum ln c partials
+    double* pgl;           // [nch]       sum gamma ln rho partials
+};
+
+__device__ __forceinline__ const double* current_at(const double* st, const Layout& L, const double* hst, const HmmLayout& H) {
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    return hst + H.set[ctrl[BGMM_CTRL_CUR]] + H.s_at;
+}
+
+template <int KP, bool BASIS>
+__global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                     const double* __restrict__ hst, const HmmLayout H, const int force,
+                                                     const ScanBufs B) {
+    __shared__ __align__(16) double lines[HW][2][32];
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    constexpr int G = 32 / KP;
+    const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
+    const double* at = current_at(st, L, hst, H);
+    const double* __restrict__ lnrho = B.lnrho;
+    const int64_t item = ((int64_t)blockIdx.x * HW + warp) * G + grp;
+    const int64_t nitems = BASIS ? (int64_t)(sp.nch - 1) * K : sp.nch;
+    const int c = BASIS ? (int)(item / K) : (int)item;
+    const int j0 = BASIS ? (int)(item - (int64_t)c * K) : 0;
+    const bool live = item < nitems, mine = live && kk < K;
+    double acol[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) acol[j] = (mine && j < K) ? at[j * K + kk] : 0.0;
+    double a = 0.0;
+    if (mine) a = BASIS ? (kk == j0 ? 1.0 : 0.0) : B.vb[(int64_t)c * K + kk];
+    const int64_t i0 = (int64_t)c * sp.L;
+    double slog = 0.0;
+    // emission values are fetched two steps ahead and exponentiated one step ahead of the dependent chain
+    auto LR = [&](int64_t i, int s) { return (mine && s < sp.L && i < sp.n) ? lnrho[i * K + kk] : -INFINITY; };
+    double rho1 = exp(LR(i0, 0));
+    double ln2 = LR(i0 + 1, 1);
+    for (int s = 0; s < sp.L; ++s) {
+        const int64_t i = i0 + s;
+        const double rho = rho1;
+        rho1 = exp(ln2);
+        ln2 = LR(i + 2, s + 2);
+        double* line = lines[warp][s & 1];
+        publish<KP>(line, lane, a);
+        const double dot = group_dot<KP>(line, grp * KP, acol);
+        const double u = rho * (i == 0 ? a : dot);                 // :1000 — the first element has no transition
+        const double sum = group_sum<KP>(u);
+        if (live && i < sp.n) {
+            if (BASIS && !(sum > 0.0)) {
+                // the start state of this basis run is impossible (its emission value underflowed to exactly 0): its
+                // response is exactly zero — not 0/0 — and weighs nothing in phase B (log scale -inf)
+                a = 0.0;
+                slog = -INFINITY;
+            } else {
+                a = u / sum;
+                slog += log(sum);
+            }
+            if (!BASIS) {
+                if (mine) B.alpha[i * K + kk] = a;
+                if (kk == 0) B.cs[i] = sum;
+            }
+        }
+    }
+    if (BASIS) {
+        if (mine) B.tf[((int64_t)c * K + j0) * K + kk] = a;
+        if (live && kk == 0) B.ls[(int64_t)c * K + j0] = slog;
+    } else if (live && kk == 0) {
+        B.plc[c] = slog;
+    }
+}
+
+// phase B forward: v[0] = pi~ = exp(ln pi~ - max) (:849, :1000); v[c+1] = normalise(sum_j v[c][j] e^{ls_j} T_c[j][:])
+template <int KP>
+__global__ void __launch_bounds__(32) hmm_fwd_seq_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                         const int force, const ScanBufs B) {
+    __shared__ __align__(16) double lines[2][32];
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    const int K = sp.K, lane = threadIdx.x, kk = lane;
+    const bool mine = kk < K;
+    const double* Pc = st + L.params[ctrl[BGMM_CTRL_CUR]];
+    double pmax = -INFINITY;
+    for (int k = 0; k < K; ++k) pmax = fmax(pmax, Pc[L.p_elnpi + k]);
+    double a = mine ? exp(Pc[L.p_elnpi + kk] - pmax) : 0.0;
+    if (mine) B.vb[kk] = a;
+    double tcol[KP], tnext[KP];
+    double ls = -INFINITY, lsn = -INFINITY;
+    auto fetch = [&](int c, double (&dst)[KP], double& l) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) dst[j] = (mine && j < K) ? B.tf[((int64_t)c * K + j) * K + kk] : 0.0;
+        l = mine ? B.ls[(int64_t)c * K + kk] : -INFINITY;
+    };
+    if (sp.nch > 1) fetch(0, tnext, lsn);
+    for (int c = 0; c + 1 < sp.nch; ++c) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) tcol[j] = tnext[j];
+        ls = lsn;
+        if (c + 2 < sp.nch) fetch(c + 1, tnext, lsn);
+        double mx = ls;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const double w = mine ? a * exp(ls - mx) : 0.0;
+        double* line = lines[c & 1];
+        line[lane] = w;
+        __syncwarp();
+        double nv = 0.0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) nv = fma(line[j], tcol[j], nv);
+        double sum = nv;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        a = nv / sum;
+        if (mine) B.vb[(int64_t)(c + 1) * K + kk] = a;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward recursion over one chunk (descending i).  Lane kk owns state kk and ROW kk of A~.
+// BASIS (phase A'): from unit vector j at the chunk's last element to the previous chunk's last element.
+// Otherwise (phase C'): from the boundary vector w[c]; gamma, the xi sum S[j][k] = sum_i alpha_{i-1}[j] rho_i[k]
+// beta_i[k] / c_i (A~ is applied once at the end), sum gamma ln rho, gamma_0, optionally beta.
+template <int KP, bool BASIS>
+__global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                     double* __restrict__ hst, const HmmLayout H, const int force,
+                                                     const ScanBufs B) {
+    __shared__ __align__(16) double lines[HW][2][32];
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    constexpr int G = 32 / KP;
+    const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
+    const double* at = current_at(st, L, hst, H);
+    const double* __restrict__ lnrho = B.lnrho;
+    const double* __restrict__ alpha = B.alpha;
+    const double* __restrict__ cs = B.cs;
+    const int64_t item = ((int64_t)blockIdx.x * HW + warp) * G + grp;
+    const int64_t nitems = BASIS ? (int64_t)(sp.nch - 1) * K : sp.nch;
+    const int c = BASIS ? 1 + (int)(item / K) : (int)item;              // basis runs: chunks 1 .. nch-1
+    const int j0 = BASIS ? (int)(item % K) : 0;
+    const bool live = item < nitems, mine = live && kk < K;
+    double arow[KP], srow[BASIS ? 1 : KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) arow[k] = (mine && k < K) ? at[kk * K + k] : 0.0;
+    if constexpr (!BASIS) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) srow[k] = 0.0;
+    }
+    const int64_t i0 = (int64_t)c * sp.L;
+    const int64_t i1 = (i0 + sp.L < sp.n ? i0 + sp.L : sp.n) - 1;        // last element of the chunk
+    double b = 0.0;
+    if (mine) b = BASIS ? (kk == j0 ? 1.0 : 0.0) : B.vb[(int64_t)c * K + kk];
+    double slog = 0.0, gl = 0.0;
+    // loads run two steps ahead, exp / reciprocal one step ahead of the dependent chain (which runs through b only)
+    auto LR = [&](int64_t i) { return (mine && i >= i0) ? lnrho[i * K + kk] : -INFINITY; };
+    auto CI = [&](int64_t i) { return (live && i >= i0) ? cs[i] : 1.0; };
+    auto AL = [&](int64_t i) { return (!BASIS && mine && i >= 0) ? alpha[i * K + kk] : 0.0; };
+    double lr_c = LR(i1), rho_c = exp(lr_c), inv_c = 1.0 / CI(i1);
+    double lr_n = LR(i1 - 1), ci_n = CI(i1 - 1);
+    double al_c = AL(i1), al_p = AL(i1 - 1), al_pp = AL(i1 - 2);
+    for (int s = 0; s < sp.L; ++s) {
+        const int64_t i = i1 - s;
+        const bool in = live && i >= i0, on = mine && i >= i0;
+        const double lr = lr_c, rho = rho_c, inv = inv_c, al = al_c, aprev = al_p;
+        lr_c = lr_n; rho_c = exp(lr_n); inv_c = 1.0 / ci_n;
+        lr_n = LR(i - 2); ci_n = CI(i - 2);
+        al_c = al_p; al_p = al_pp; al_pp = AL(i - 3);
+        const double rb = on ? rho * b : 0.0;                          // rho_i[k] beta_i[k]
+        if (!BASIS && on) {
+            const double g = al * b;                                   // :1014
+            B.gamma[i * K + kk] = g;
+            if (B.beta_out != nullptr) B.beta_out[i * K + kk] = b;
+            gl = fma(g, lr, gl);
+            if (i == 0) hst[H.g0 + kk] = g;
+        }
+        double* line = lines[warp][s & 1];
+        publish<KP>(line, lane, rb);
+        const double dot = group_dot<KP>(line, grp * KP, arow);        // (A~ (rho o beta))[kk]
+        if constexpr (!BASIS) {
+            const double f = (on && i >= 1) ? aprev * inv : 0.0;       // alpha_{i-1}[kk] / c_i   (:1017-1018)
+            const double2* p = reinterpret_cast<const double2*>(line + grp * KP);
+#pragma unroll
+            for (int k2 = 0; k2 < KP / 2; ++k2) {
+                const double2 vv = p[k2];
+                srow[2 * k2] = fma(f, vv.x, srow[2 * k2]);
+                srow[2 * k2 + 1] = fma(f, vv.y, srow[2 * k2 + 1]);
+            }
+        }
+        if (BASIS) {
+            const double nb = dot * inv;
+            const double sum = group_sum<KP>(nb);
+            if (in) {
+                if (sum > 0.0) { b = nb / sum; slog += log(sum); }
+                else { b = 0.0; slog = -INFINITY; }                    // impossible end state: zero response (see forward)
+            }
+        } else if (in) {
+            b = dot * inv;                                             // :1010-1011
+        }
+    }
+    if (BASIS) {
+        if (mine) B.tf[((int64_t)c * K + j0) * K + kk] = b;
+        if (live && kk == 0) B.ls[(int64_t)c * K + j0] = slog;
+    }
+    if constexpr (!BASIS) {
+        if (mine) {
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) B.ps[((int64_t)c * K + kk) * K + k] = srow[k];
+        }
+        const double t = group_sum<KP>(gl);
+        if (live && kk == 0) B.pgl[c] = t;
+    }
+}
+
+// phase B' backward: w[nch-1] = 1 (:939 beta init); w[c-1][k] = sum_j w[c][j] e^{ls_j} U_c[j][k]   (true scale kept)
+template <int KP>
+__global__ void __launch_bounds__(32) hmm_bwd_seq_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                         const int force, const ScanBufs B) {
+    __shared__ __align__(16) double lines[2][32];
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    const int K = sp.K, lane = threadIdx.x, kk = lane;
+    const bool mine = kk < K;
+    double b = mine ? 1.0 : 0.0;
+    if (mine) B.vb[(int64_t)(sp.nch - 1) * K + kk] = b;
+    double ucol[KP], unext[KP];
+    double ls = 0.0, lsn = 0.0;
+    auto fetch = [&](int c, double (&dst)[KP], double& l) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) dst[j] = (mine && j < K) ? B.tf[((int64_t)c * K + j) * K + kk] : 0.0;
+        l = mine ? B.ls[(int64_t)c * K + kk] : 0.0;
+    };
+    if (sp.nch > 1) fetch(sp.nch - 1, unext, lsn);
+    for (int c = sp.nch - 1; c >= 1; --c) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) ucol[j] = unext[j];
+        ls = lsn;
+        if (c >= 2) fetch(c - 1, unext, lsn);
+        const double coef = (mine && b > 0.0) ? exp(ls + log(b)) : 0.0;
+        double* line = lines[c & 1];
+        line[lane] = coef;
+        __syncwarp();
+        double nb = 0.0;
+#pragma unroll
+        for (int j = 0; j < KP; ++j) nb = fma(line[j], ucol[j], nb);
+        b = nb;
+        if (mine) B.vb[(int64_t)(c - 1) * K + kk] = b;
+    }
+}
+
+// ms[j][k] = A~[j][k] * sum_c S_c[j][k] (:839 with :1017), sc[0] = sum_i ln c_i, sc[1] = sum gamma ln rho; fixed order.
+__global__ void __launch_bounds__(256) hmm_reduce_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                         double* __restrict__ hst, const HmmLayout H, const int force,
+                                                         const ScanBufs B) {
+    __shared__ double part[8][32];
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    const double* at = current_at(st, L, hst, H);
+    const int KK = sp.K * sp.K, e = blockIdx.x * 32 + (threadIdx.x & 31), sl = threadIdx.x >> 5;
+    double acc = 0.0;
+    if (e < KK) {
+        for (int c = sl; c < sp.nch; c += 8) acc += B.ps[(int64_t)c * KK + e];
+    } else if (e == KK) {
+        for (int c = sl; c < sp.nch; c += 8) acc += B.plc[c];
+    } else if (e == KK + 1) {
+        for (int c = sl; c < sp.nch; c += 8) acc += B.pgl[c];
+    }
+    part[sl][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (sl == 0) {
+        double t = 0.0;
+        for (int s = 0; s < 8; ++s) t += part[s][threadIdx.x];
+        if (e < KK) hst[H.ms + e] = at[e] * t;
+        else if (e == KK) hst[H.sc + 0] = t;
+        else if (e == KK + 1) hst[H.sc + 1] = t;
+    }
+}
+
+static int64_t scan_ws_doubles(int K, int64_t n) {
+    const int L = hmm_chunk_len(n);
+    const int64_t nch = (n + L - 1) / L;
+    const int64_t KK = (int64_t)K * K;
+    // transfer matrices + log scales + boundary vectors + S partials + the two scalar partial arrays
+    return nch * KK + nch * K + nch * K + nch * KK + 2 * nch + 64;
+}
+
+template <int KP>
+static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* hst, const HmmLayout& H, int force,
+                       const ScanBufs& B, cudaStream_t stream) {
+    constexpr int G = 32 / KP;
+    const int per_cta = HW * G;
+    const int64_t nbasis = (int64_t)(sp.nch - 1) * sp.K;
+    const unsigned gb = (unsigned)((nbasis + per_cta - 1) / per_cta), gc = (unsigned)((sp.nch + per_cta - 1) / per_cta);
+    if (sp.nch > 1) hmm_fwd_kernel<KP, true><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_fwd_seq_kernel<KP><<<1, 32, 0, stream>>>(sp, st, L, force, B);
+    hmm_fwd_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    if (sp.nch > 1) hmm_bwd_kernel<KP, true><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_bwd_seq_kernel<KP><<<1, 32, 0, stream>>>(sp, st, L, force, B);
+    hmm_bwd_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_reduce_kernel<<<(sp.K * sp.K + 2 + 31) / 32, 256, 0, stream>>>(sp, st, L, hst, H, force, B);
+    return check_cuda(cudaGetLastError(), "hmm scan launch");
+}
+
+}  // namespace bgmm
+
+extern "C" int64_t bgmm_hmm_scan_workspace_doubles(int K, int64_t n) {
+    if (K <= 0 || K > 32 || n <= 0) return 0;
+    return bgmm::scan_ws_doubles(K, n);
+}
+
+extern "C" int bgmm_hmm_supported(int K, int D) {
+    return (K >= 1 && K <= 32 && bgmm::large_supported(K, D, BGMM_F64)) ? 1 : 0;
+}
+
+extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* state, double* hst, double* workspace,
+                             double* scan_ws, double* lnrho, double* alpha, double* gamma, double* cs, double* beta_out,
+                             int mode, int force, void* stream) {
+    using namespace bgmm;
+    if (!bgmm_hmm_supported(K, D)) {
+        set_error("bgmm_hmm_pass: unsupported shape K=%d D=%d (float64, K <= 32, D <= 128)", K, D);
+        return BGMM_ENOSUP;
+    }
+    if (x == nullptr || n <= 0 || state == nullptr || hst == nullptr || workspace == nullptr || gamma == nullptr ||
+        (mode == BGMM_HMM_FULL && (scan_ws == nullptr || lnrho == nullptr || alpha == nullptr || cs == nullptr))) {
+        set_error("bgmm_hmm_pass: NULL buffer or n <= 0");
+        return BGMM_EINVAL;
+    }
+    if (mode != BGMM_HMM_FULL && mode != BGMM_HMM_STATS_FROM_GAMMA) {
+        set_error("bgmm_hmm_pass: unknown mode %d", mode);
+        return BGMM_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const Layout L = make_layout(K, D, 1);
+    const HmmLayout H = make_hmm_layout(K);
+    PassArgs a{x, n, state, workspace, nullptr, lnrho, nullptr, nullptr, force, 0};
+    int rc;
+    if (mode == BGMM_HMM_FULL) {
+        a.lnrho_only = 1;
+        rc = launch_pass_large_part(a, K, D, BGMM_F64, 1, s);
+        if (rc) return rc;
+        ScanPlan sp;
+        sp.n = n; sp.K = K; sp.L = hmm_chunk_len(n); sp.nch = (int)((n + sp.L - 1) / sp.L);
+        const int64_t KK = (int64_t)K * K, nch = sp.nch;
+        ScanBufs B;
+        B.lnrho = lnrho; B.alpha = alpha; B.gamma = gamma; B.cs = cs; B.beta_out = beta_out;
+        B.tf = scan_ws; B.ls = B.tf + nch * KK; B.vb = B.ls + nch * K; B.ps = B.vb + nch * K;
+        B.plc = B.ps + nch * KK; B.pgl = B.plc + nch;
+        if (K <= 2) rc = launch_scan<2>(sp, state, L, hst, H, force, B, s);
+        else if (K <= 4) rc = launch_scan<4>(sp, state, L, hst, H, force, B, s);
+        else if (K <= 8) rc = launch_scan<8>(sp, state, L, hst, H, force, B, s);
+        else if (K <= 16) rc = launch_scan<16>(sp, state, L, hst, H, force, B, s);
+        else rc = launch_scan<32>(sp, state, L, hst, H, force, B, s);
+        if (rc) return rc;
+    }
+    a.lnrho_only = 0;
+    a.lnrho_out = nullptr;
+    a.r_out = gamma;
+    return launch_pass_large_part(a, K, D, BGMM_F64, 2, s);
+}

@@ -202,6 +202,7 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
                         if (k < K) a.lnrho_out[grow * K + k] = lr[kb][e];
                     }
             }
+            if (a.lnrho_only) continue;                     // HMM emission pass: the scan kernels take over from ln rho
             double sum = 0.0, dot = 0.0;
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
@@ -395,8 +396,9 @@ int64_t large_workspace_doubles(int K, int D) {
     return (int64_t)64 * ((int64_t)K * feat_pitch(D) + 8) + 256 + nchunk * 64 * LG_CW + (nchunk * LG_CW + 3) / 4 + 8;
 }
 
+// which = 1: E kernel (+ coefficient image / feature table), 2: M kernel (+ reduction over the row splits), 3: both
 template <int KB>
-static int launch_large_t(const PassArgs& a, const Layout& L, cudaStream_t stream) {
+static int launch_large_t(const PassArgs& a, const Layout& L, int which, cudaStream_t stream) {
     int grid_e, n_chunks, nsplit;
     large_plan(L.K, L.D, a.n, grid_e, n_chunks, nsplit);
     const int64_t len = L.stats_len;
@@ -404,39 +406,47 @@ static int launch_large_t(const PassArgs& a, const Layout& L, cudaStream_t strea
     double* packed = ews + 256;
     const int nchunk_e = (L.P + LG_CW - 1) / LG_CW;
     unsigned short* ftab = reinterpret_cast<unsigned short*>(packed + (int64_t)nchunk_e * 8 * KB * LG_CW);
-    const size_t smem_e = sizeof(double) * ((size_t)2 * 8 * KB * LG_CW + (size_t)LG_ETILE * (L.D + 2) + 40) + 4 * sizeof(uint64_t) +
-                          sizeof(unsigned short) * (size_t)nchunk_e * LG_CW + 128;
-    constexpr int RP = (8 * KB < 16) ? 16 : 8 * KB;
-    const size_t smem_m = sizeof(double) * ((size_t)LG_MSUB * RP + (size_t)2 * LG_MSUB * L.D + (size_t)LG_MSUB * L.K + 2) +
-                          2 * sizeof(uint64_t) + 128;
-    cudaError_t e = cudaFuncSetAttribute(e_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(e_large)");
-    e = cudaFuncSetAttribute(m_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(m_large)");
-    coef_pack_kernel<KB><<<nchunk_e, LG_THREADS, 0, stream>>>(a.state, L, packed, a.force);
-    feat_table_kernel<<<(nchunk_e * LG_CW + 255) / 256, 256, 0, stream>>>(ftab, L.D, L.P, nchunk_e * LG_CW);
-    e_large_kernel<KB><<<grid_e, LG_ETHREADS, smem_e, stream>>>(a, L, ews, packed, ftab);
-    m_large_kernel<KB><<<dim3(n_chunks, nsplit), LG_THREADS, smem_m, stream>>>(a, L, ews, grid_e, nsplit);
-    launch_reduce_partials(a, L, nsplit, stream);
+    if (which & 1) {
+        const size_t smem_e = sizeof(double) * ((size_t)2 * 8 * KB * LG_CW + (size_t)LG_ETILE * (L.D + 2) + 40) +
+                              4 * sizeof(uint64_t) + sizeof(unsigned short) * (size_t)nchunk_e * LG_CW + 128;
+        cudaError_t e = cudaFuncSetAttribute(e_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(e_large)");
+        coef_pack_kernel<KB><<<nchunk_e, LG_THREADS, 0, stream>>>(a.state, L, packed, a.force);
+        feat_table_kernel<<<(nchunk_e * LG_CW + 255) / 256, 256, 0, stream>>>(ftab, L.D, L.P, nchunk_e * LG_CW);
+        e_large_kernel<KB><<<grid_e, LG_ETHREADS, smem_e, stream>>>(a, L, ews, packed, ftab);
+    }
+    if (which & 2) {
+        constexpr int RP = (8 * KB < 16) ? 16 : 8 * KB;
+        const size_t smem_m = sizeof(double) * ((size_t)LG_MSUB * RP + (size_t)2 * LG_MSUB * L.D + (size_t)LG_MSUB * L.K + 2) +
+                              2 * sizeof(uint64_t) + 128;
+        cudaError_t e = cudaFuncSetAttribute(m_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(m_large)");
+        m_large_kernel<KB><<<dim3(n_chunks, nsplit), LG_THREADS, smem_m, stream>>>(a, L, ews, grid_e, nsplit);
+        launch_reduce_partials(a, L, nsplit, stream);
+    }
     return check_cuda(cudaGetLastError(), "pass_large launch");
 }
 
-int launch_pass_large(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream) {
+int launch_pass_large_part(const PassArgs& a, int K, int D, int dtype, int which, cudaStream_t stream) {
     if (!large_supported(K, D, dtype)) {
         set_error("bgmm_pass(large): unsupported shape K=%d D=%d dtype=%d", K, D, dtype);
         return BGMM_ENOSUP;
     }
-    if (a.r_out == nullptr) {
+    if ((which & 2) && a.r_out == nullptr) {
         set_error("bgmm_pass(large): r_out ([n][K] float64) is required in this regime (it is the M kernel's input)");
         return BGMM_EINVAL;
     }
     const Layout L = make_layout(K, D, 1);
     switch (large_kb(K)) {
-        case 1: return launch_large_t<1>(a, L, stream);
-        case 2: return launch_large_t<2>(a, L, stream);
-        case 4: return launch_large_t<4>(a, L, stream);
-        default: return launch_large_t<8>(a, L, stream);
+        case 1: return launch_large_t<1>(a, L, which, stream);
+        case 2: return launch_large_t<2>(a, L, which, stream);
+        case 4: return launch_large_t<4>(a, L, which, stream);
+        default: return launch_large_t<8>(a, L, which, stream);
     }
+}
+
+int launch_pass_large(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream) {
+    return launch_pass_large_part(a, K, D, dtype, 3, stream);
 }
 
 }  // namespace bgmm

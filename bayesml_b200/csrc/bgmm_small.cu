@@ -45,7 +45,8 @@ __device__ __forceinline__ double ld_peer(const double* p) {     // peer / excha
 
 __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, const Layout L, const int mode,
                                                     const int max_itr, const double tol,
-                                                    const CommDesc* __restrict__ cd) {
+                                                    const CommDesc* __restrict__ cd,
+                                                    const double* __restrict__ hmm_vlx) {
     extern __shared__ double sm[];
     const int K = L.K, D = L.D, DD = D * D, k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
@@ -282,7 +283,8 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     for (int i = tid; i < D; i += nt) mq += mnew[i] * lin[i];
     mq = block_sum(mq, scratch);
     double* coef = Pn + L.p_coef + (int64_t)k * L.pitch;
-    if (tid == 0) coef[0] = elnpi_n + (elndet_n - D * LN2PI - D / kn) / 2.0 - 0.5 * mq;
+    // hidden-Markov emission density (_hiddenmarkovnormal.py:988-992): no E[ln pi] term in ln rho
+    if (tid == 0) coef[0] = (hmm_vlx != nullptr ? 0.0 : elnpi_n) + (elndet_n - D * LN2PI - D / kn) / 2.0 - 0.5 * mq;
     for (int i = tid; i < D; i += nt) coef[1 + i] = lin[i];
     const int nq = D * (D + 1) / 2;
     for (int q = tid; q < nq; q += nt) {
@@ -314,9 +316,15 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
         qpi += vk[j * 8 + 4]; qml += vk[j * 8 + 5]; asum += vk[j * 8 + 6];
     }
     ppi += st[L.lnc0];
-    const double qz = -st[L.stats + (int64_t)K * L.pitch];                    // -sum r ln r (:704)
+    double qz = -st[L.stats + (int64_t)K * L.pitch];                          // -sum r ln r (:704)
     qpi += -lgamma_ni(asum) + (asum - K) * digamma_pos(asum);                    // dirichlet entropy (:707)
-    const double vl = px + pz + ppi + pml + qz + qpi + qml;                   // :717-723
+    double extra = 0.0;
+    if (hmm_vlx != nullptr) {      // hidden-Markov ELBO (_hiddenmarkovnormal.py:869-932): terms from hmm_trans_kernel
+        pz = hmm_vlx[0];
+        qz = hmm_vlx[2];
+        extra = hmm_vlx[1] + hmm_vlx[3];
+    }
+    const double vl = px + pz + ppi + pml + qz + qpi + qml + extra;           // :717-723
     double* vt = st + L.vlterms;
     vt[0] = px; vt[1] = pz; vt[2] = ppi; vt[3] = pml; vt[4] = qz; vt[5] = qpi; vt[6] = qml; vt[7] = vl;
     const int iter = ctrl[BGMM_CTRL_ITER];
@@ -334,7 +342,127 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     ctrl[BGMM_CTRL_TICKET] = 0;
 }
 
+// Transition-matrix part of the hidden-Markov VB step, one CTA.  Replaces, in
+// /root/reference/bayesml/hiddenmarkovnormal/_hiddenmarkovnormal.py:
+//   _update_q_a :984-986 (zeta = zeta0 + M), _calc_q_a_features :851-854 (ln a~, a~ = exp(ln a~ - max), ln C(zeta)),
+//   and the ELBO terms that involve A, xi, gamma_0 and the scaling constants: _vl_p_z :886, _vl_p_a :892,
+//   _vl_q_z :906-909, _vl_q_a :915.
+// It runs BEFORE small_kernel in every iteration: it reads ctrl.cur (small_kernel's finaliser flips it afterwards),
+// evaluates the ELBO terms under the CURRENT set and writes the new set into the other slot.
+__global__ void __launch_bounds__(256) hmm_trans_kernel(double* __restrict__ st, const Layout L, double* __restrict__ hst,
+                                                        const HmmLayout H, const int mode) {
+    __shared__ double red[40];
+    __shared__ double rowsum[64];
+    const int K = H.K, KK = K * K, tid = threadIdx.x, nt = blockDim.x;
+    volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
+    const bool iterate = (mode == BGMM_SMALL_ITERATE);
+    if (iterate && ctrl[BGMM_CTRL_DONE]) return;
+    const int cur = ctrl[BGMM_CTRL_CUR];
+    double* Sc = hst + H.set[cur];
+    double* Sn = iterate ? hst + H.set[cur ^ 1] : Sc;
+    if (iterate) {
+        const double* Pc = st + L.params[cur];
+        const double* ms = hst + H.ms;
+        const double* zeta0 = hst + H.zeta0;
+        const double amax = Sc[H.s_misc + 0], lncz = Sc[H.s_misc + 1];
+        double pmax = -INFINITY;
+        for (int k = 0; k < K; ++k) pmax = fmax(pmax, Pc[L.p_elnpi + k]);
+        double t_pz = 0.0, t_pa = 0.0, t_qz = 0.0, t_qa = 0.0;
+        for (int e = tid; e < KK; e += nt) {
+            const double la = Sc[H.s_lna + e], m = ms[e];
+            t_pz += m * la;
+            t_pa += (zeta0[e] - 1.0) * la;
+            t_qz += m * (la - amax);
+            t_qa += (Sc[H.s_zeta + e] - 1.0) * la;
+        }
+        for (int k = tid; k < K; k += nt) {
+            const double g0 = hst[H.g0 + k], lp = Pc[L.p_elnpi + k];
+            t_pz += g0 * lp;
+            t_qz += g0 * (lp - pmax);
+        }
+        block_sum4(t_pz, t_pa, t_qz, t_qa, red);
+        if (tid == 0) {
+            double* vlx = hst + H.vlx;
+            vlx[0] = t_pz;
+            vlx[1] = hst[H.lncz0] + t_pa;
+            vlx[2] = -hst[H.sc + 1] - t_qz + hst[H.sc + 0];
+            vlx[3] = -lncz - t_qa;
+        }
+        __syncthreads();
+        for (int e = tid; e < KK; e += nt) Sn[H.s_zeta + e] = zeta0[e] + ms[e];
+        __syncthreads();
+    }
+    // features of the (new) set
+    for (int r = tid; r < K; r += nt) {
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s += Sn[H.s_zeta + r * K + k];
+        rowsum[r] = s;
+    }
+    __syncthreads();
+    double mx = -INFINITY, lc = 0.0;
+    for (int e = tid; e < KK; e += nt) {
+        const int r = e / K;
+        const double z = Sn[H.s_zeta + e];
+        const double la = digamma_pos(z) - digamma_pos(rowsum[r]);
+        Sn[H.s_lna + e] = la;
+        mx = fmax(mx, la);
+        lc -= lgamma_ni(z);
+    }
+    for (int r = tid; r < K; r += nt) lc += lgamma_ni(rowsum[r]);
+    // block max, then block sum
+    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (nt >> 5); ++w) mx = fmax(mx, red[w]);
+    __syncthreads();
+    lc = block_sum(lc, red);
+    for (int e = tid; e < KK; e += nt) Sn[H.s_at + e] = exp(Sn[H.s_lna + e] - mx);
+    if (tid == 0) { Sn[H.s_misc + 0] = mx; Sn[H.s_misc + 1] = lc; }
+}
+
 }  // namespace bgmm
+
+extern "C" int bgmm_hmm_layout(int K, int64_t* off) {
+    using namespace bgmm;
+    if (K <= 0 || off == nullptr) { set_error("bgmm_hmm_layout: bad argument"); return BGMM_EINVAL; }
+    const HmmLayout H = make_hmm_layout(K);
+    const int64_t v[BGMM_HMM_OFF_COUNT] = {H.zeta0, H.lncz0, H.set[0], H.set[1], H.s_zeta, H.s_lna, H.s_at, H.s_misc,
+                                           H.ms, H.g0, H.sc, H.vlx, H.total};
+    for (int i = 0; i < BGMM_HMM_OFF_COUNT; ++i) off[i] = v[i];
+    return BGMM_OK;
+}
+
+extern "C" int bgmm_hmm_small(int K, int D, double* state, double* hst, int mode, int max_itr, double tol, int hist_len,
+                              void* stream) {
+    using namespace bgmm;
+    if (K <= 0 || K > 64 || D <= 0 || state == nullptr || hst == nullptr || hist_len < 1) {
+        set_error("bgmm_hmm_small: bad argument (K=%d D=%d state=%p hst=%p hist_len=%d)", K, D, (void*)state, (void*)hst,
+                  hist_len);
+        return BGMM_EINVAL;
+    }
+    if (mode != BGMM_SMALL_FEATURES && mode != BGMM_SMALL_ITERATE && mode != BGMM_SMALL_STATS) {
+        set_error("bgmm_hmm_small: unknown mode %d", mode);
+        return BGMM_EINVAL;
+    }
+    const Layout L = make_layout(K, D, hist_len);
+    const HmmLayout H = make_hmm_layout(K);
+    const size_t smem = sizeof(double) * ((size_t)D * D + 6 * (size_t)D + 48);
+    if (smem > 227 * 1024) {
+        set_error("bgmm_hmm_small: D=%d needs %zu B of shared memory (> 227 KiB)", D, smem);
+        return BGMM_ENOSUP;
+    }
+    if (smem > 48 * 1024) {
+        int rc = check_cuda(cudaFuncSetAttribute(small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(small_kernel)");
+        if (rc) return rc;
+    }
+    if (mode != BGMM_SMALL_STATS) hmm_trans_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, L, hst, H, mode);
+    const int nt = D <= 16 ? 32 : (D <= 32 ? 64 : (D <= 64 ? 128 : 256));
+    small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol, nullptr, hst + H.vlx);
+    return check_cuda(cudaGetLastError(), "hmm small launch");
+}
 
 extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, double tol, int hist_len,
                           const void* comm_desc, void* stream) {
@@ -361,6 +489,6 @@ extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, do
     // latency-bound kernel full of block barriers: one warp per component while the D x D work is tiny
     const int nt = D <= 16 ? 32 : (D <= 32 ? 64 : (D <= 64 ? 128 : 256));
     small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol,
-                                                        static_cast<const CommDesc*>(comm_desc));
+                                                        static_cast<const CommDesc*>(comm_desc), nullptr);
     return check_cuda(cudaGetLastError(), "small_kernel launch");
 }

@@ -404,3 +404,121 @@ class VBEngine:
             self._small(_lib.SMALL_STATS, 0, 0.0)
             host = self.state.cpu().numpy()
         return self._stats_from_host(host)
+
+
+class HMMEngine(VBEngine):
+    """Device engine of the VB hidden-Markov (Gaussian emission) fit: the mixture engine's state block (alpha plays eta)
+    plus the transition-matrix block `hst` and the per-element buffers of the forward-backward scan.
+
+    Reference call sites replaced (bayesml/hiddenmarkovnormal/_hiddenmarkovnormal.py): the VB loop :1102-1113 —
+    `_update_q_mu_lambda`/`_update_q_pi`/`_update_q_a` -> bgmm_hmm_small, `_update_q_z` -> bgmm_hmm_pass, `_calc_vl`
+    and the convergence test -> bgmm_hmm_small; one sequence on one GPU (the recursions couple all elements)."""
+
+    def __init__(self, K, D, device=None):
+        super().__init__(K, D, device=device, precision="float64", group=None, variant=_lib.PASS_LARGE)
+        if not self.lib.bgmm_hmm_supported(self.K, self.D):
+            raise RuntimeError(f"bayesml_b200 hidden-Markov path: unsupported shape K={K}, D={D} "
+                               "(float64, K <= 32, D <= 128); there is no CPU fallback")
+        self.hoff = _lib.hmm_layout(self.K)
+        self.hst = torch.zeros(self.hoff["total"], dtype=torch.float64, device=self.device)
+        self.lnrho_buf = self.alpha_buf = self.gamma_buf = self.cs_buf = self.beta_buf = self.scan_ws = None
+
+    def _hview(self, name, length, which=None):
+        o = self.hoff[name] if which is None else self.hoff[f"set{which}"] + self.hoff[name]
+        return self.hst[o:o + length]
+
+    def load_data_finish(self):
+        super().load_data_finish()
+        n, K = self.n_local, self.K
+        with torch.cuda.device(self.device):
+            if self.lnrho_buf is None or self.lnrho_buf.shape[0] != n:
+                mk = lambda *shape: torch.empty(shape, dtype=torch.float64, device=self.device)  # noqa: E731
+                self.lnrho_buf, self.alpha_buf, self.gamma_buf, self.cs_buf = mk(n, K), mk(n, K), mk(n, K), mk(n)
+                self.scan_ws = mk(int(self.lib.bgmm_hmm_scan_workspace_doubles(K, n)))
+            self.beta_buf = None
+        return self
+
+    def set_hmm_prior(self, eta0, zeta0, m0, kappa0, nu0, w0inv, ln_b_h0, ln_c_h0_eta, ln_c_h0_zeta_sum):
+        self.set_prior(eta0, m0, kappa0, nu0, w0inv, ln_b_h0, ln_c_h0_eta)
+        self._put(self._hview("zeta0", self.K * self.K), zeta0)
+        self._put(self._hview("lncz0", 1), [ln_c_h0_zeta_sum])
+
+    def set_hmm_params(self, eta, zeta, m, kappa, nu, winv):
+        """Load (eta, zeta, m, kappa, nu, W^-1) as parameter set 0, reset the control words, compute all features."""
+        self._put(self._hview("set_zeta", self.K * self.K, which=0), zeta)
+        self.set_params(eta, m, kappa, nu, winv)
+
+    def _small(self, mode, max_itr, tol):
+        _lib.check(self.lib.bgmm_hmm_small(self.K, self.D, self.state.data_ptr(), self.hst.data_ptr(), mode, int(max_itr),
+                                           float(tol), self.hist_len, self._stream()), "bgmm_hmm_small")
+        self.small_launches += 1
+        self.kernel_launches += 1 if mode == _lib.SMALL_STATS else 2
+
+    def _pass(self, mode=_lib.HMM_FULL, force=0, beta_out=None):
+        ptr = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731
+        _lib.check(self.lib.bgmm_hmm_pass(self.x.data_ptr(), self.n_local, self.K, self.D, self.state.data_ptr(),
+                                          self.hst.data_ptr(), self.workspace.data_ptr(), ptr(self.scan_ws),
+                                          ptr(self.lnrho_buf), ptr(self.alpha_buf), ptr(self.gamma_buf), ptr(self.cs_buf),
+                                          ptr(beta_out), mode, force, self._stream()), "bgmm_hmm_pass")
+        self.passes += 1
+        self.kernel_launches += 12 if mode == _lib.HMM_FULL else 2
+
+    def begin(self, max_itr, tol, init=None):
+        """Post-init E-step + ELBO (:1092-1101) and the first M-step.  `init` = (gamma [n][K], ms [K][K]) for the
+        'random_responsibility' initialisation (:944-952): the statistics of the given gamma / xi, with ln rho = 0
+        and c = 1 as `_init_fb_params` (:934-942) leaves them."""
+        self._max_itr, self._tol, self._launched = int(max_itr), float(tol), 0
+        with torch.cuda.device(self.device):
+            self._alloc_state(self._max_itr + 1)
+            if init is not None:
+                gamma, ms = init
+                self.gamma_buf.copy_(torch.as_tensor(np.ascontiguousarray(gamma, dtype=np.float64)))
+                self._put(self._hview("ms", self.K * self.K), ms)
+                self._put(self._hview("g0", self.K), gamma[0])
+                self._hview("sc", 8).zero_()
+                self._pass(mode=_lib.HMM_STATS_FROM_GAMMA, force=1)
+            else:
+                self._pass()
+            self._small(_lib.SMALL_ITERATE, self._max_itr, self._tol)
+
+    def run(self, max_itr, tol, init=None, chunk=None):
+        self.begin(max_itr, tol, init)
+        step = 4 if chunk is None else int(chunk)
+        done = self._max_itr == 0
+        while not done:
+            t0 = time.perf_counter()
+            todo = self.enqueue(step)
+            torch.cuda.current_stream(self.device).synchronize()
+            done = self.finished()
+            if chunk is None:
+                per = (time.perf_counter() - t0) / max(todo, 1)
+                step = int(min(64, max(1, 0.03 / max(per, 1e-6))))
+        return self.finish()
+
+    def fetch_params(self):
+        out = super().fetch_params()
+        K = self.K
+        h = self.hst.cpu().numpy()
+        cur = int(self.ctrl.cpu().numpy()[_lib.CTRL_CUR])
+        base = self.hoff[f"set{cur}"]
+        g = lambda name: h[base + self.hoff[name]: base + self.hoff[name] + K * K].reshape(K, K).copy()  # noqa: E731
+        out.update({"zeta": g("set_zeta"), "ln_a_tilde": g("set_lna"), "a_tilde": g("set_at"),
+                    "ln_c_zeta_sum": float(h[base + self.hoff["set_misc"] + 1]),
+                    "ms": h[self.hoff["ms"]:self.hoff["ms"] + K * K].reshape(K, K).copy(),
+                    "gamma0": h[self.hoff["g0"]:self.hoff["g0"] + K].copy(),
+                    "sc": h[self.hoff["sc"]:self.hoff["sc"] + 2].copy(),
+                    "vlx": h[self.hoff["vlx"]:self.hoff["vlx"] + 4].copy()})
+        return out
+
+    def final_pass(self):
+        """`_update_q_z` with the current parameters (:1133, :1490) keeping ln rho, alpha, beta, gamma, c on the device."""
+        with torch.cuda.device(self.device):
+            self.beta_buf = torch.empty((self.n_local, self.K), dtype=torch.float64, device=self.device)
+            self._pass(force=1, beta_out=self.beta_buf)
+            self._small(_lib.SMALL_STATS, 0, 0.0)
+            host = self.state.cpu().numpy()
+            h = self.hst.cpu().numpy()
+        out = self._stats_from_host(host)
+        K = self.K
+        out["ms"] = h[self.hoff["ms"]:self.hoff["ms"] + K * K].reshape(K, K).copy()
+        return out

@@ -176,6 +176,44 @@ int bgmm_comm_close(void* peer_ptr);
 int bgmm_comm_free(void* base);
 int bgmm_publish(int K, int D, double* state, const void* comm_desc, int force, void* stream);
 
+/* ---- hidden-Markov model with Gaussian emissions -----------------------------------------------
+ * Replaces the VB loop body of /root/reference/bayesml/hiddenmarkovnormal/_hiddenmarkovnormal.py
+ * `LearnModel.update_posterior` (:1028-1134).  The Gauss-Wishart / Dirichlet(eta) part of the model is the mixture's,
+ * so it lives in the SAME state block (bgmm_layout; alpha plays eta, :981).  The transition-matrix part lives in a
+ * second block "hst" (doubles; offsets from bgmm_hmm_layout):
+ *   ZETA0 [K][K] prior h0_zeta_vecs | LNCZ0 ln C(zeta0) sum (:828) |
+ *   SET0 / SET1 (ping-pong with ctrl.cur): +SET_ZETA [K][K] hn_zeta_vecs, +SET_LNA ln a~ (:852), +SET_AT a~ = exp(ln a~
+ *   - max) (:853), +SET_MISC {max ln a~, ln C(zeta) sum (:854)} |
+ *   MS [K][K] sum_i xi_i (:839) | G0 [K] gamma_0 | SC {sum_i ln c_i, sum gamma.ln rho} |
+ *   VLX {E ln p(z) :886, E ln p(A) :892, -E ln q(z) :906-909, -E ln q(A) :915}. */
+enum {
+    BGMM_HMM_OFF_ZETA0 = 0, BGMM_HMM_OFF_LNCZ0, BGMM_HMM_OFF_SET0, BGMM_HMM_OFF_SET1, BGMM_HMM_OFF_SET_ZETA,
+    BGMM_HMM_OFF_SET_LNA, BGMM_HMM_OFF_SET_AT, BGMM_HMM_OFF_SET_MISC, BGMM_HMM_OFF_MS, BGMM_HMM_OFF_G0,
+    BGMM_HMM_OFF_SC, BGMM_HMM_OFF_VLX, BGMM_HMM_OFF_TOTAL, BGMM_HMM_OFF_COUNT
+};
+int bgmm_hmm_layout(int K, int64_t* off /* [BGMM_HMM_OFF_COUNT] */);
+/* 1 when the device path covers this shape (float64, K <= 32, D <= 128), else 0 */
+int bgmm_hmm_supported(int K, int D);
+/* doubles of scratch the scan needs for a sequence of n elements */
+int64_t bgmm_hmm_scan_workspace_doubles(int K, int64_t n);
+
+/* bgmm_hmm_pass `mode` */
+#define BGMM_HMM_FULL 0             /* `_update_q_z` :1020-1026: emission density, forward, backward, gamma, xi, statistics */
+#define BGMM_HMM_STATS_FROM_GAMMA 1 /* `_calc_n_m_x_bar_s` :837-845 of a given gamma (random_responsibility init :944-952);
+                                       the caller has written MS, G0 and SC into hst                                      */
+/* One E-step over the whole (centred, float64) sequence x[n][D] with the CURRENT parameter set:
+ *   lnrho[n][K] (:988-996), alpha[n][K] and cs[n] (:999-1006), gamma[n][K] (:1014), optionally beta_out[n][K]
+ *   (:1008-1011; NULL inside the loop), hst.MS / G0 / SC, and the gamma-weighted raw moments into state.STATS.
+ * The two recursions run as chunked three-phase scans (csrc/bgmm_hmm.cu).  `workspace`: bgmm_workspace_doubles(K, D);
+ * `scan_ws`: bgmm_hmm_scan_workspace_doubles(K, n).  No-op when ctrl.done != 0 unless `force`. */
+int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* state, double* hst, double* workspace, double* scan_ws,
+                  double* lnrho, double* alpha, double* gamma, double* cs, double* beta_out, int mode, int force,
+                  void* stream);
+/* bgmm_small for the hidden-Markov model: hmm_trans_kernel (`_update_q_a` :984-986, `_calc_q_a_features` :851-854, the
+ * ELBO terms with A / xi / gamma_0 / c) followed by the mixture's small kernel with ln rho free of E[ln pi] (:989-992)
+ * and the 9-term ELBO (:869-932).  Modes as bgmm_small. */
+int bgmm_hmm_small(int K, int D, double* state, double* hst, int mode, int max_itr, double tol, int hist_len, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
