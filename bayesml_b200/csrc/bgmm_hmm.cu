@@ -35,7 +35,7 @@ struct ScanPlan {
 };
 
 __host__ __device__ inline int hmm_chunk_len(int64_t n) {
-    int64_t L = (n + 8191) / 8192;
+    int64_t L = (n + 4095) / 4096;          // <= 4096 chunks: the length of the sequential phase B
     if (L < 32) L = 32;
     return (int)((L + 7) & ~int64_t(7));
 }
@@ -154,48 +154,138 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
     }
 }
 
-// phase B forward: v[0] = pi~ = exp(ln pi~ - max) (:849, :1000); v[c+1] = normalise(sum_j v[c][j] e^{ls_j} T_c[j][:])
-template <int KP>
-__global__ void __launch_bounds__(32) hmm_fwd_seq_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
-                                                         const int force, const ScanBufs B) {
+// Phase B (both directions): the sequential sweep over the chunk transfer matrices, one CTA.
+//   forward : v[0] = pi~ = exp(ln pi~ - max) (:849, :1000); v[c+1] = normalise(sum_j v[c][j] e^{ls_j} T_c[j][:])
+//   backward: w[nch-1] = 1 (:939);  w[c-1][k] = sum_j w[c][j] e^{ls_j} U_c[j][k]          (true scale kept)
+// Warps 1..3 stage batches of chunk matrices into shared memory (double buffered) and turn the log scales into
+// e_j = exp(ls_j - max_j ls) (+ exp(max) for the backward sweep) — everything that does not depend on the running
+// vector; warp 0 runs the recurrence from shared memory: multiply, one shared-memory exchange, K FMAs, one division.
+// The normaliser of the forward sweep is sum_j w_j (the rows of T sum to one), formed redundantly by every lane in a
+// fixed order instead of a shuffle reduction after the matrix-vector product.
+constexpr int SEQ_T = 128;
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__host__ __device__ inline int seq_batch(int K) {
+    const int per = (K * K + K + 8) * 8;
+    int b = (200 * 1024) / (2 * per);
+    return b > 64 ? 64 : (b < 1 ? 1 : b);
+}
+
+template <int KP, bool FWD>
+__global__ void __launch_bounds__(SEQ_T) hmm_seq_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                        const int force, const ScanBufs B) {
+    extern __shared__ __align__(16) double sq[];
     __shared__ __align__(16) double lines[2][32];
     const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
-    const int K = sp.K, lane = threadIdx.x, kk = lane;
-    const bool mine = kk < K;
-    const double* Pc = st + L.params[ctrl[BGMM_CTRL_CUR]];
-    double pmax = -INFINITY;
-    for (int k = 0; k < K; ++k) pmax = fmax(pmax, Pc[L.p_elnpi + k]);
-    double a = mine ? exp(Pc[L.p_elnpi + kk] - pmax) : 0.0;
-    if (mine) B.vb[kk] = a;
-    double tcol[KP], tnext[KP];
-    double ls = -INFINITY, lsn = -INFINITY;
-    auto fetch = [&](int c, double (&dst)[KP], double& l) {
-#pragma unroll
-        for (int j = 0; j < KP; ++j) dst[j] = (mine && j < K) ? B.tf[((int64_t)c * K + j) * K + kk] : 0.0;
-        l = mine ? B.ls[(int64_t)c * K + kk] : -INFINITY;
+    const int K = sp.K, KK = K * K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb_chunk = seq_batch(K);
+    const int stride = KK + K + 8;                       // per chunk: matrix [K][K] | e [K] | {exp(max), ...}
+    const int nsteps = sp.nch - 1;                       // forward: chunks 0 .. nch-2; backward: chunks nch-1 .. 1
+    const int nbatch = (nsteps + nb_chunk - 1) / nb_chunk;
+    const bool mine = lane < K;
+    double a = 0.0;
+    if (warp == 0) {
+        if (FWD) {
+            const double* Pc = st + L.params[ctrl[BGMM_CTRL_CUR]];
+            double pmax = -INFINITY;
+            for (int k = 0; k < K; ++k) pmax = fmax(pmax, Pc[L.p_elnpi + k]);
+            a = mine ? exp(Pc[L.p_elnpi + lane] - pmax) : 0.0;
+            if (mine) B.vb[lane] = a;
+        } else {
+            a = mine ? 1.0 : 0.0;
+            if (mine) B.vb[(int64_t)(sp.nch - 1) * K + lane] = a;
+        }
+    }
+    // chunk handled at sequential position s
+    auto chunk_of = [&](int s) { return FWD ? s : sp.nch - 1 - s; };
+    auto load_batch = [&](int b, int t0, int nt) {       // threads t0 .. t0+nt-1 of the CTA
+        double* dst = sq + (size_t)(b & 1) * nb_chunk * stride;
+        const int s0 = b * nb_chunk, cnt = min(nb_chunk, nsteps - s0);
+        for (int q = 0; q < cnt; ++q) {
+            const int c = chunk_of(s0 + q);
+            const double* src = B.tf + (int64_t)c * KK;
+            // asynchronous copies: a whole batch is in flight at once (a load -> store loop would serialise on latency)
+            for (int e = tid - t0; e < KK; e += nt) cp_async8(dst + q * stride + e, src + e);
+            for (int e = tid - t0; e < K; e += nt) cp_async8(dst + q * stride + KK + e, B.ls + (int64_t)c * K + e);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     };
-    if (sp.nch > 1) fetch(0, tnext, lsn);
-    for (int c = 0; c + 1 < sp.nch; ++c) {
+    auto scale_batch = [&](int b, int t0, int nt) {      // ls -> e = exp(ls - max), exp(max); one thread per chunk
+        double* dst = sq + (size_t)(b & 1) * nb_chunk * stride;
+        const int s0 = b * nb_chunk, cnt = min(nb_chunk, nsteps - s0);
+        for (int q = tid - t0; q < cnt; q += nt) {
+            double* e = dst + q * stride + KK;
+            double mx = -INFINITY;
+            for (int j = 0; j < K; ++j) mx = fmax(mx, e[j]);
+            for (int j = 0; j < K; ++j) e[j] = (mx > -INFINITY) ? exp(e[j] - mx) : 0.0;
+            e[K] = (mx > -INFINITY) ? exp(mx) : 0.0;
+        }
+    };
+    if (nbatch > 0) {
+        load_batch(0, 0, SEQ_T);
+        __syncthreads();
+        scale_batch(0, 0, SEQ_T);
+        __syncthreads();
+    }
+    for (int b = 0; b < nbatch; ++b) {
+        if (warp > 0) {
+            if (b + 1 < nbatch) {
+                load_batch(b + 1, 32, SEQ_T - 32);
+                asm volatile("bar.sync 1, 96;" ::: "memory");
+                scale_batch(b + 1, 32, SEQ_T - 32);
+            }
+        } else {
+            const double* src = sq + (size_t)(b & 1) * nb_chunk * stride;
+            const int s0 = b * nb_chunk, cnt = min(nb_chunk, nsteps - s0);
+            // column `lane` of the chunk matrix, the scale factors: fetched one step ahead of the dependent chain
+            double m[KP], mn[KP], e_c, e_n, sc_c = 0.0, sc_n = 0.0;
+            auto fetch = [&](int q, double (&dst)[KP], double& e, double& sc) {
+                const double* M = src + q * stride;
 #pragma unroll
-        for (int j = 0; j < KP; ++j) tcol[j] = tnext[j];
-        ls = lsn;
-        if (c + 2 < sp.nch) fetch(c + 1, tnext, lsn);
-        double mx = ls;
+                for (int j = 0; j < KP; ++j) dst[j] = (mine && j < K) ? M[j * K + lane] : 0.0;
+                e = mine ? M[KK + lane] : 0.0;
+                if (!FWD) sc = M[KK + K];
+            };
+            fetch(0, mn, e_n, sc_n);
+            for (int q = 0; q < cnt; ++q) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        const double w = mine ? a * exp(ls - mx) : 0.0;
-        double* line = lines[c & 1];
-        line[lane] = w;
-        __syncwarp();
-        double nv = 0.0;
+                for (int j = 0; j < KP; ++j) m[j] = mn[j];
+                e_c = e_n; sc_c = sc_n;
+                double* line = lines[q & 1];
+                line[lane] = a * e_c;
+                __syncwarp();
+                if (q + 1 < cnt) fetch(q + 1, mn, e_n, sc_n);
+                double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+                const double2* lp = reinterpret_cast<const double2*>(line);
+                if (KP >= 4) {
 #pragma unroll
-        for (int j = 0; j < KP; ++j) nv = fma(line[j], tcol[j], nv);
-        double sum = nv;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        a = nv / sum;
-        if (mine) B.vb[(int64_t)(c + 1) * K + kk] = a;
+                    for (int j = 0; j < KP / 4; ++j) {
+                        const double2 u = lp[2 * j], v = lp[2 * j + 1];
+                        n0 = fma(u.x, m[4 * j], n0);     w0 += u.x;
+                        n1 = fma(u.y, m[4 * j + 1], n1); w1 += u.y;
+                        n2 = fma(v.x, m[4 * j + 2], n2); w2 += v.x;
+                        n3 = fma(v.y, m[4 * j + 3], n3); w3 += v.y;
+                    }
+                } else {
+                    const double2 u = lp[0];
+                    n0 = fma(u.x, m[0], n0); w0 += u.x;
+                    n1 = fma(u.y, m[1], n1); w1 += u.y;
+                }
+                const double nv = (n0 + n1) + (n2 + n3);
+                const int c = chunk_of(s0 + q);
+                if (FWD) {
+                    a = nv * (1.0 / ((w0 + w1) + (w2 + w3)));          // the reciprocal runs beside the dot product
+                    if (mine) B.vb[(int64_t)(c + 1) * K + lane] = a;
+                } else {
+                    a = nv * sc_c;
+                    if (mine) B.vb[(int64_t)(c - 1) * K + lane] = a;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -295,42 +385,6 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     }
 }
 
-// phase B' backward: w[nch-1] = 1 (:939 beta init); w[c-1][k] = sum_j w[c][j] e^{ls_j} U_c[j][k]   (true scale kept)
-template <int KP>
-__global__ void __launch_bounds__(32) hmm_bwd_seq_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
-                                                         const int force, const ScanBufs B) {
-    __shared__ __align__(16) double lines[2][32];
-    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
-    if (!force && ctrl[BGMM_CTRL_DONE]) return;
-    const int K = sp.K, lane = threadIdx.x, kk = lane;
-    const bool mine = kk < K;
-    double b = mine ? 1.0 : 0.0;
-    if (mine) B.vb[(int64_t)(sp.nch - 1) * K + kk] = b;
-    double ucol[KP], unext[KP];
-    double ls = 0.0, lsn = 0.0;
-    auto fetch = [&](int c, double (&dst)[KP], double& l) {
-#pragma unroll
-        for (int j = 0; j < KP; ++j) dst[j] = (mine && j < K) ? B.tf[((int64_t)c * K + j) * K + kk] : 0.0;
-        l = mine ? B.ls[(int64_t)c * K + kk] : 0.0;
-    };
-    if (sp.nch > 1) fetch(sp.nch - 1, unext, lsn);
-    for (int c = sp.nch - 1; c >= 1; --c) {
-#pragma unroll
-        for (int j = 0; j < KP; ++j) ucol[j] = unext[j];
-        ls = lsn;
-        if (c >= 2) fetch(c - 1, unext, lsn);
-        const double coef = (mine && b > 0.0) ? exp(ls + log(b)) : 0.0;
-        double* line = lines[c & 1];
-        line[lane] = coef;
-        __syncwarp();
-        double nb = 0.0;
-#pragma unroll
-        for (int j = 0; j < KP; ++j) nb = fma(line[j], ucol[j], nb);
-        b = nb;
-        if (mine) B.vb[(int64_t)(c - 1) * K + kk] = b;
-    }
-}
-
 // ms[j][k] = A~[j][k] * sum_c S_c[j][k] (:839 with :1017), sc[0] = sum_i ln c_i, sc[1] = sum gamma ln rho; fixed order.
 __global__ void __launch_bounds__(256) hmm_reduce_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
                                                          double* __restrict__ hst, const HmmLayout H, const int force,
@@ -375,10 +429,17 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
     const int64_t nbasis = (int64_t)(sp.nch - 1) * sp.K;
     const unsigned gb = (unsigned)((nbasis + per_cta - 1) / per_cta), gc = (unsigned)((sp.nch + per_cta - 1) / per_cta);
     if (sp.nch > 1) hmm_fwd_kernel<KP, true><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
-    hmm_fwd_seq_kernel<KP><<<1, 32, 0, stream>>>(sp, st, L, force, B);
+    const size_t smem_seq = (size_t)2 * seq_batch(sp.K) * (sp.K * sp.K + sp.K + 8) * sizeof(double);
+    {   // per launch: the attribute is per device
+        cudaError_t e = cudaFuncSetAttribute(hmm_seq_kernel<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(hmm_seq_kernel<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(hmm_seq)");
+    }
+    hmm_seq_kernel<KP, true><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, force, B);
     hmm_fwd_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     if (sp.nch > 1) hmm_bwd_kernel<KP, true><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
-    hmm_bwd_seq_kernel<KP><<<1, 32, 0, stream>>>(sp, st, L, force, B);
+    hmm_seq_kernel<KP, false><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, force, B);
     hmm_bwd_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_reduce_kernel<<<(sp.K * sp.K + 2 + 31) / 32, 256, 0, stream>>>(sp, st, L, hst, H, force, B);
     return check_cuda(cudaGetLastError(), "hmm scan launch");

@@ -375,6 +375,14 @@ static int large_kb(int K) { return K <= 8 ? 1 : (K <= 16 ? 2 : (K <= 32 ? 4 : 8
 
 bool large_supported(int K, int D, int dtype) { return dtype == BGMM_F64 && K >= 1 && K <= 64 && D >= 1 && D <= 128; }
 
+// upper bound of the M kernel's row splits (= partial statistics buffers in the workspace): few feature chunks (small D)
+// need many splits to fill the GPU, many chunks need few
+static int large_max_split(int D) {
+    const int n_chunks = (feat_pitch(D) + LG_MCW - 1) / LG_MCW;
+    const int s = 320 / n_chunks;
+    return s < 4 ? 4 : s;
+}
+
 static void large_plan(int K, int D, int64_t n, int& grid_e, int& n_chunks, int& nsplit) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -383,7 +391,7 @@ static void large_plan(int K, int D, int64_t n, int& grid_e, int& n_chunks, int&
     n_chunks = (feat_pitch(D) + LG_MCW - 1) / LG_MCW;
     const int64_t nsub = (n + LG_MSUB - 1) / LG_MSUB;
     int64_t s = (2 * sms) / n_chunks;                                   // ONE resident wave (2 CTAs per SM): no tail wave
-    if (s > 64) s = 64;
+    if (s > large_max_split(D)) s = large_max_split(D);
     if (s > nsub) s = nsub;
     if (s < 1) s = 1;
     nsplit = (int)s;
@@ -393,7 +401,8 @@ int64_t large_workspace_doubles(int K, int D) {
     if (K > 64 || D > 128) return 0;
     const int64_t nchunk = (feat_count(D) + LG_CW - 1) / LG_CW;
     // <= 64 row splits + E-kernel entropy partials + the packed coefficient image (nchunk x [8*KB][64]) + the (i, j) table
-    return (int64_t)64 * ((int64_t)K * feat_pitch(D) + 8) + 256 + nchunk * 64 * LG_CW + (nchunk * LG_CW + 3) / 4 + 8;
+    return (int64_t)large_max_split(D) * ((int64_t)K * feat_pitch(D) + 8) + 256 + nchunk * 64 * LG_CW +
+           (nchunk * LG_CW + 3) / 4 + 8;
 }
 
 // which = 1: E kernel (+ coefficient image / feature table), 2: M kernel (+ reduction over the row splits), 3: both
@@ -402,7 +411,7 @@ static int launch_large_t(const PassArgs& a, const Layout& L, int which, cudaStr
     int grid_e, n_chunks, nsplit;
     large_plan(L.K, L.D, a.n, grid_e, n_chunks, nsplit);
     const int64_t len = L.stats_len;
-    double* ews = a.workspace + (int64_t)64 * len;
+    double* ews = a.workspace + (int64_t)large_max_split(L.D) * len;
     double* packed = ews + 256;
     const int nchunk_e = (L.P + LG_CW - 1) / LG_CW;
     unsigned short* ftab = reinterpret_cast<unsigned short*>(packed + (int64_t)nchunk_e * 8 * KB * LG_CW);
