@@ -115,6 +115,8 @@ struct PassArgs {
     const double* r_in;
     int force, accumulate;
     int lnrho_only = 0;   // large-regime E kernel: write ln rho only (no softmax / r / entropy): the HMM emission pass
+    double* rhohat_out = nullptr;   // with lnrho_only: exp(ln rho - row max) [n][K] and the row max [n] (scan inputs)
+    double* rowmax_out = nullptr;
 };
 
 // HMM extension block ("hst", doubles) next to the state block: transition-matrix hyperparameters and features, the

@@ -76,6 +76,9 @@ __device__ __forceinline__ double group_dot(const double* line, int gbase, const
 // Lane kk of a group owns state kk and column kk of A~.
 struct ScanBufs {
     const double* lnrho;   // [n][K]
+    const double* rhohat;  // [n][K] exp(ln rho - row max): what the recursions multiply by (rho_i / c_i = rhohat_i / chat_i)
+    const double* rowmax;  // [n]    max_k ln rho
+    double* chat;          // [n]    c_i exp(-row max): the normaliser in rhohat units
     double* alpha;         // [n][K]
     double* gamma;         // [n][K]
     double* cs;            // [n]
@@ -103,7 +106,8 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
     constexpr int G = 32 / KP;
     const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
     const double* at = current_at(st, L, hst, H);
-    const double* __restrict__ lnrho = B.lnrho;
+    const double* __restrict__ rhohat = B.rhohat;
+    const double* __restrict__ rowmax = B.rowmax;
     const int64_t item = ((int64_t)blockIdx.x * HW + warp) * G + grp;
     const int64_t nitems = BASIS ? (int64_t)(sp.nch - 1) * K : sp.nch;
     const int c = BASIS ? (int)(item / K) : (int)item;
@@ -116,33 +120,46 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
     if (mine) a = BASIS ? (kk == j0 ? 1.0 : 0.0) : B.vb[(int64_t)c * K + kk];
     const int64_t i0 = (int64_t)c * sp.L;
     double slog = 0.0;
-    // emission values are fetched two steps ahead and exponentiated one step ahead of the dependent chain
-    auto LR = [&](int64_t i, int s) { return (mine && s < sp.L && i < sp.n) ? lnrho[i * K + kk] : -INFINITY; };
-    double rho1 = exp(LR(i0, 0));
-    double ln2 = LR(i0 + 1, 1);
+    // emission values are fetched two steps ahead of the dependent chain (which runs through `a` only)
+    auto RH = [&](int64_t i, int s) { return (mine && s < sp.L && i < sp.n) ? rhohat[i * K + kk] : 0.0; };
+    auto MX = [&](int64_t i, int s) { return (!BASIS && live && s < sp.L && i < sp.n) ? rowmax[i] : 0.0; };
+    double rho_c = RH(i0, 0), rho_n = RH(i0 + 1, 1);
+    double mx_c = MX(i0, 0), mx_n = MX(i0 + 1, 1);
     for (int s = 0; s < sp.L; ++s) {
         const int64_t i = i0 + s;
-        const double rho = rho1;
-        rho1 = exp(ln2);
-        ln2 = LR(i + 2, s + 2);
+        const double rho = rho_c, mx = mx_c;
+        rho_c = rho_n; mx_c = mx_n;
+        rho_n = RH(i + 2, s + 2); mx_n = MX(i + 2, s + 2);
         double* line = lines[warp][s & 1];
         publish<KP>(line, lane, a);
         const double dot = group_dot<KP>(line, grp * KP, acol);
         const double u = rho * (i == 0 ? a : dot);                 // :1000 — the first element has no transition
-        const double sum = group_sum<KP>(u);
-        if (live && i < sp.n) {
-            if (BASIS && !(sum > 0.0)) {
-                // the start state of this basis run is impossible (its emission value underflowed to exactly 0): its
-                // response is exactly zero — not 0/0 — and weighs nothing in phase B (log scale -inf)
-                a = 0.0;
-                slog = -INFINITY;
-            } else {
-                a = u / sum;
-                slog += log(sum);
+        if (BASIS) {
+            // rhohat <= 1 with row maximum 1, so the vector shrinks by at most min(A~) per step: it is renormalised
+            // every 8 steps only (and at the end: phase B relies on rows of T summing to one)
+            if ((s & 7) == 7 || s == sp.L - 1) {
+                const double sum = group_sum<KP>(u);
+                if (live) {
+                    if (!(sum > 0.0)) {
+                        // the start state of this basis run is impossible (its emission value underflowed to exactly
+                        // 0): its response is exactly zero — not 0/0 — and weighs nothing in phase B (log scale -inf)
+                        a = 0.0;
+                        slog = -INFINITY;
+                    } else {
+                        a = u / sum;
+                        slog += log(sum);
+                    }
+                }
+            } else if (live) {
+                a = u;
             }
-            if (!BASIS) {
+        } else {
+            const double sum = group_sum<KP>(u);                   // chat_i
+            if (live && i < sp.n) {
+                a = u / sum;
+                slog += log(sum) + mx;                             // ln c_i
                 if (mine) B.alpha[i * K + kk] = a;
-                if (kk == 0) B.cs[i] = sum;
+                if (kk == 0) { B.chat[i] = sum; B.cs[i] = sum * exp(mx); }
             }
         }
     }
@@ -305,8 +322,9 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
     const double* at = current_at(st, L, hst, H);
     const double* __restrict__ lnrho = B.lnrho;
+    const double* __restrict__ rhohat = B.rhohat;
     const double* __restrict__ alpha = B.alpha;
-    const double* __restrict__ cs = B.cs;
+    const double* __restrict__ cs = B.chat;                  // rho_i / c_i = rhohat_i / chat_i
     const int64_t item = ((int64_t)blockIdx.x * HW + warp) * G + grp;
     const int64_t nitems = BASIS ? (int64_t)(sp.nch - 1) * K : sp.nch;
     const int c = BASIS ? 1 + (int)(item / K) : (int)item;              // basis runs: chunks 1 .. nch-1
@@ -325,18 +343,19 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     if (mine) b = BASIS ? (kk == j0 ? 1.0 : 0.0) : B.vb[(int64_t)c * K + kk];
     double slog = 0.0, gl = 0.0;
     // loads run two steps ahead, exp / reciprocal one step ahead of the dependent chain (which runs through b only)
-    auto LR = [&](int64_t i) { return (mine && i >= i0) ? lnrho[i * K + kk] : -INFINITY; };
+    auto LR = [&](int64_t i) { return (!BASIS && mine && i >= i0) ? lnrho[i * K + kk] : 0.0; };
+    auto RH = [&](int64_t i) { return (mine && i >= i0) ? rhohat[i * K + kk] : 0.0; };
     auto CI = [&](int64_t i) { return (live && i >= i0) ? cs[i] : 1.0; };
     auto AL = [&](int64_t i) { return (!BASIS && mine && i >= 0) ? alpha[i * K + kk] : 0.0; };
-    double lr_c = LR(i1), rho_c = exp(lr_c), inv_c = 1.0 / CI(i1);
-    double lr_n = LR(i1 - 1), ci_n = CI(i1 - 1);
+    double lr_c = LR(i1), rho_c = RH(i1), inv_c = 1.0 / CI(i1);
+    double lr_n = LR(i1 - 1), rho_n = RH(i1 - 1), ci_n = CI(i1 - 1);
     double al_c = AL(i1), al_p = AL(i1 - 1), al_pp = AL(i1 - 2);
     for (int s = 0; s < sp.L; ++s) {
         const int64_t i = i1 - s;
         const bool in = live && i >= i0, on = mine && i >= i0;
         const double lr = lr_c, rho = rho_c, inv = inv_c, al = al_c, aprev = al_p;
-        lr_c = lr_n; rho_c = exp(lr_n); inv_c = 1.0 / ci_n;
-        lr_n = LR(i - 2); ci_n = CI(i - 2);
+        lr_c = lr_n; rho_c = rho_n; inv_c = 1.0 / ci_n;
+        lr_n = LR(i - 2); rho_n = RH(i - 2); ci_n = CI(i - 2);
         al_c = al_p; al_p = al_pp; al_pp = AL(i - 3);
         const double rb = on ? rho * b : 0.0;                          // rho_i[k] beta_i[k]
         if (!BASIS && on) {
@@ -360,11 +379,17 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
             }
         }
         if (BASIS) {
+            // each step is already scaled by 1 / chat_i, so the vector is renormalised every 8 steps only; the result
+            // need not be normalised at the end (phase B' uses U e^{ls}, whatever the split between the two)
             const double nb = dot * inv;
-            const double sum = group_sum<KP>(nb);
-            if (in) {
-                if (sum > 0.0) { b = nb / sum; slog += log(sum); }
-                else { b = 0.0; slog = -INFINITY; }                    // impossible end state: zero response (see forward)
+            if ((s & 7) == 7) {
+                const double sum = group_sum<KP>(nb);
+                if (in) {
+                    if (sum > 0.0) { b = nb / sum; slog += log(sum); }
+                    else { b = 0.0; slog = -INFINITY; }                // impossible end state: zero response (see forward)
+                }
+            } else if (in) {
+                b = nb;
             }
         } else if (in) {
             b = dot * inv;                                             // :1010-1011
@@ -418,7 +443,8 @@ static int64_t scan_ws_doubles(int K, int64_t n) {
     const int64_t nch = (n + L - 1) / L;
     const int64_t KK = (int64_t)K * K;
     // transfer matrices + log scales + boundary vectors + S partials + the two scalar partial arrays
-    return nch * KK + nch * K + nch * K + nch * KK + 2 * nch + 64;
+    // + rhohat [n][K], row max [n], chat [n]
+    return nch * KK + nch * K + nch * K + nch * KK + 2 * nch + 64 + n * K + 2 * n;
 }
 
 template <int KP>
@@ -479,9 +505,6 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
     PassArgs a{x, n, state, workspace, nullptr, lnrho, nullptr, nullptr, force, 0};
     int rc;
     if (mode == BGMM_HMM_FULL) {
-        a.lnrho_only = 1;
-        rc = launch_pass_large_part(a, K, D, BGMM_F64, 1, s);
-        if (rc) return rc;
         ScanPlan sp;
         sp.n = n; sp.K = K; sp.L = hmm_chunk_len(n); sp.nch = (int)((n + sp.L - 1) / sp.L);
         const int64_t KK = (int64_t)K * K, nch = sp.nch;
@@ -489,6 +512,14 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
         B.lnrho = lnrho; B.alpha = alpha; B.gamma = gamma; B.cs = cs; B.beta_out = beta_out;
         B.tf = scan_ws; B.ls = B.tf + nch * KK; B.vb = B.ls + nch * K; B.ps = B.vb + nch * K;
         B.plc = B.ps + nch * KK; B.pgl = B.plc + nch;
+        double* rh = B.pgl + nch;
+        B.rhohat = rh; B.chat = rh + n * K;
+        double* rmx = B.chat + n;
+        B.rowmax = rmx;
+        a.rhohat_out = rh; a.rowmax_out = rmx;
+        a.lnrho_only = 1;
+        rc = launch_pass_large_part(a, K, D, BGMM_F64, 1, s);
+        if (rc) return rc;
         if (K <= 2) rc = launch_scan<2>(sp, state, L, hst, H, force, B, s);
         else if (K <= 4) rc = launch_scan<4>(sp, state, L, hst, H, force, B, s);
         else if (K <= 8) rc = launch_scan<8>(sp, state, L, hst, H, force, B, s);

@@ -202,7 +202,19 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
                         if (k < K) a.lnrho_out[grow * K + k] = lr[kb][e];
                     }
             }
-            if (a.lnrho_only) continue;                     // HMM emission pass: the scan kernels take over from ln rho
+            if (a.lnrho_only) {                             // HMM emission pass: the scan kernels take over from here
+                if (valid && a.rhohat_out != nullptr) {
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int k = 8 * kb + 2 * q + e;
+                            if (k < K) a.rhohat_out[grow * K + k] = exp_nonpos(lr[kb][e] - mx);
+                        }
+                    if (q == 0) a.rowmax_out[grow] = mx;
+                }
+                continue;
+            }
             double sum = 0.0, dot = 0.0;
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
