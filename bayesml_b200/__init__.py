@@ -8,7 +8,7 @@
 The compute path is hand-written CUDA for sm_100a behind a C ABI (include/bgmm.h, libbgmm.so); there is no CPU
 fallback.  Importing the package does not need a GPU; fitting does.
 """
-from . import gaussianmixture, hiddenmarkovnormal  # noqa: F401
+from . import gaussianmixture, hiddenmarkovnormal, multivariate_normal  # noqa: F401
 from ._exceptions import (CriteriaError, DataFormatError, ParameterFormatError,  # noqa: F401
                           ParameterFormatWarning, ResultWarning)
 

@@ -90,3 +90,25 @@ def shape_consistency(val, val_name, correct, correct_name, exception_class):
     if val != correct:
         raise exception_class(f"{val_name} must coincide with {correct_name}: "
                               f"{val_name} = {val}, {correct_name} = {correct}")
+
+
+def pos_float(val, val_name, exception_class):
+    """Positive real scalar; integers are cast to float (reference _check.py:19-26)."""
+    if _is_float(val) and val > 0.0:
+        return val
+    if _is_int(val) and val > 0:
+        return float(val)
+    raise exception_class(val_name + " must be positive (not including 0.0).")
+
+
+def pos_def_sym_mat(val, val_name, exception_class):
+    """One symmetric positive-definite matrix, checked by Cholesky (reference _check.py:121-138)."""
+    ok = type(val) is np.ndarray and val.ndim == 2 and val.shape[0] == val.shape[1]
+    if ok and np.allclose(val, val.T):
+        try:
+            np.linalg.cholesky(val)
+            return val
+        except np.linalg.LinAlgError:
+            raise exception_class(
+                val_name + " must be a positive definite symmetric 2-dimensional numpy.ndarray.") from None
+    raise exception_class(val_name + " must be a symmetric 2-dimensional numpy.ndarray.")
