@@ -34,8 +34,9 @@ struct ScanPlan {
     int K, L, nch;
 };
 
+// Chunk length: <= 4096 chunks (the length of the sequential phase B), at least 32 elements each.
 __host__ __device__ inline int hmm_chunk_len(int64_t n) {
-    int64_t L = (n + 4095) / 4096;          // <= 4096 chunks: the length of the sequential phase B
+    int64_t L = (n + 4095) / 4096;
     if (L < 32) L = 32;
     return (int)((L + 7) & ~int64_t(7));
 }
@@ -96,7 +97,30 @@ __device__ __forceinline__ const double* current_at(const double* st, const Layo
     return hst + H.set[ctrl[BGMM_CTRL_CUR]] + H.s_at;
 }
 
-template <int KP, bool BASIS>
+// Mixing mode.  Two message vectors at Hilbert distance <= Delta are at distance <= tau^(W-1) Delta after W steps of
+// either recursion (Birkhoff contraction, tau = tanh(Delta(A~) / 4); the emission values are diagonal scalings and do not
+// change the metric).  Below 1e-18 the W-step transfer matrix is rank one in fp64, so the boundary vector of a chunk is
+//   forward : the normalised end vector of ONE run over the W elements before the chunk, from any start;
+//   backward: ONE un-normalised run over the W elements after the chunk from the all-ones vector, true scale included:
+//             U w = (U 1)(alpha_end . w) / (alpha_end . 1) = U 1, because alpha_end . w = sum_k gamma_k = 1.
+// hmm_window returns the smallest such W for the current A~ (hmm_trans_kernel stores ln tau and ln Delta), or 0 when the
+// window would cost more than the exact alternative — the K basis runs per chunk (phase A) + the sequential sweep (B).
+// Windows that reach the end of the sequence start from the true vector there (pi~ / ones) and are exact.
+__device__ __forceinline__ int hmm_window(const double* st, const Layout& L, const double* hst, const HmmLayout& H,
+                                          int chunk_len, int K) {
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    const double* misc = hst + H.set[ctrl[BGMM_CTRL_CUR]] + H.s_misc;
+    const double lntau = misc[2], lndelta = misc[3];
+    if (!(lndelta > -INFINITY)) return 8;                     // A~ exactly uniform: rank one after a single step
+    if (!(lntau < 0.0)) return 0;
+    const double w = ceil((-41.5 - lndelta) / lntau) + 1.0;     // tau^(W-1) Delta < 1e-18
+    const double cap = fmin(16384.0, 0.5 * (double)chunk_len * (double)K);
+    if (!(w <= cap)) return 0;
+    return w < 8.0 ? 8 : (int)w;
+}
+
+// MODE 0: phase C (exact recursion from the boundary vector);  1: phase A (K basis runs per chunk; skipped in mixing mode)
+template <int KP, int MODE>
 __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
                                                      const double* __restrict__ hst, const HmmLayout H, const int force,
                                                      const ScanBufs B) {
@@ -105,19 +129,21 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
     constexpr int G = 32 / KP;
     const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
+    constexpr bool BASIS = (MODE != 0);                     // renormalise sparsely, no per-element outputs
+    if (MODE == 1 && hmm_window(st, L, hst, H, sp.L, sp.K) > 0) return;
     const double* at = current_at(st, L, hst, H);
     const double* __restrict__ rhohat = B.rhohat;
     const double* __restrict__ rowmax = B.rowmax;
     const int64_t item = ((int64_t)blockIdx.x * HW + warp) * G + grp;
-    const int64_t nitems = BASIS ? (int64_t)(sp.nch - 1) * K : sp.nch;
-    const int c = BASIS ? (int)(item / K) : (int)item;
-    const int j0 = BASIS ? (int)(item - (int64_t)c * K) : 0;
+    const int64_t nitems = MODE == 1 ? (int64_t)(sp.nch - 1) * K : sp.nch;
+    const int c = MODE == 1 ? (int)(item / K) : (int)item;
+    const int j0 = MODE == 1 ? (int)(item - (int64_t)c * K) : 0;
     const bool live = item < nitems, mine = live && kk < K;
     double acol[KP];
 #pragma unroll
     for (int j = 0; j < KP; ++j) acol[j] = (mine && j < K) ? at[j * K + kk] : 0.0;
     double a = 0.0;
-    if (mine) a = BASIS ? (kk == j0 ? 1.0 : 0.0) : B.vb[(int64_t)c * K + kk];
+    if (mine) a = MODE == 1 ? (kk == j0 ? 1.0 : 0.0) : B.vb[(int64_t)c * K + kk];
     const int64_t i0 = (int64_t)c * sp.L;
     double slog = 0.0;
     // emission values are fetched two steps ahead of the dependent chain (which runs through `a` only)
@@ -163,7 +189,7 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
             }
         }
     }
-    if (BASIS) {
+    if (MODE == 1) {
         if (mine) B.tf[((int64_t)c * K + j0) * K + kk] = a;
         if (live && kk == 0) B.ls[(int64_t)c * K + j0] = slog;
     } else if (live && kk == 0) {
@@ -180,6 +206,10 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
 // The normaliser of the forward sweep is sum_j w_j (the rows of T sum to one), formed redundantly by every lane in a
 // fixed order instead of a shuffle reduction after the matrix-vector product.
 constexpr int SEQ_T = 128;
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
@@ -192,11 +222,13 @@ __host__ __device__ inline int seq_batch(int K) {
 
 template <int KP, bool FWD>
 __global__ void __launch_bounds__(SEQ_T) hmm_seq_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                        const double* __restrict__ hst, const HmmLayout H,
                                                         const int force, const ScanBufs B) {
     extern __shared__ __align__(16) double sq[];
     __shared__ __align__(16) double lines[2][32];
     const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    if (hmm_window(st, L, hst, H, sp.L, sp.K) > 0) return;   // mixing mode: the window kernel wrote the boundary vectors
     const int K = sp.K, KK = K * K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb_chunk = seq_batch(K);
     const int stride = KK + K + 8;                       // per chunk: matrix [K][K] | e [K] | {exp(max), ...}
@@ -225,20 +257,27 @@ __global__ void __launch_bounds__(SEQ_T) hmm_seq_kernel(const ScanPlan sp, const
             const int c = chunk_of(s0 + q);
             const double* src = B.tf + (int64_t)c * KK;
             // asynchronous copies: a whole batch is in flight at once (a load -> store loop would serialise on latency)
-            for (int e = tid - t0; e < KK; e += nt) cp_async8(dst + q * stride + e, src + e);
-            for (int e = tid - t0; e < K; e += nt) cp_async8(dst + q * stride + KK + e, B.ls + (int64_t)c * K + e);
+            if ((K & 1) == 0) {             // K even: every row pair is 16-byte aligned on both sides (stride is even too)
+                for (int e = 2 * (tid - t0); e < KK; e += 2 * nt) cp_async16(dst + q * stride + e, src + e);
+                for (int e = 2 * (tid - t0); e < K; e += 2 * nt) cp_async16(dst + q * stride + KK + e, B.ls + (int64_t)c * K + e);
+            } else {
+                for (int e = tid - t0; e < KK; e += nt) cp_async8(dst + q * stride + e, src + e);
+                for (int e = tid - t0; e < K; e += nt) cp_async8(dst + q * stride + KK + e, B.ls + (int64_t)c * K + e);
+            }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     };
-    auto scale_batch = [&](int b, int t0, int nt) {      // ls -> e = exp(ls - max), exp(max); one thread per chunk
+    auto scale_batch = [&](int b, int t0, int nt) {      // ls -> e = exp(ls - max), exp(max); one warp per chunk, lane = j
         double* dst = sq + (size_t)(b & 1) * nb_chunk * stride;
         const int s0 = b * nb_chunk, cnt = min(nb_chunk, nsteps - s0);
-        for (int q = tid - t0; q < cnt; q += nt) {
+        for (int q = (tid - t0) >> 5; q < cnt; q += nt >> 5) {
             double* e = dst + q * stride + KK;
-            double mx = -INFINITY;
-            for (int j = 0; j < K; ++j) mx = fmax(mx, e[j]);
-            for (int j = 0; j < K; ++j) e[j] = (mx > -INFINITY) ? exp(e[j] - mx) : 0.0;
-            e[K] = (mx > -INFINITY) ? exp(mx) : 0.0;
+            const double v = lane < K ? e[lane] : -INFINITY;
+            double mx = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane < K) e[lane] = (mx > -INFINITY) ? exp(v - mx) : 0.0;
+            if (lane == 0) e[K] = (mx > -INFINITY) ? exp(mx) : 0.0;
         }
     };
     if (nbatch > 0) {
@@ -311,7 +350,8 @@ __global__ void __launch_bounds__(SEQ_T) hmm_seq_kernel(const ScanPlan sp, const
 // BASIS (phase A'): from unit vector j at the chunk's last element to the previous chunk's last element.
 // Otherwise (phase C'): from the boundary vector w[c]; gamma, the xi sum S[j][k] = sum_i alpha_{i-1}[j] rho_i[k]
 // beta_i[k] / c_i (A~ is applied once at the end), sum gamma ln rho, gamma_0, optionally beta.
-template <int KP, bool BASIS>
+// MODE as in hmm_fwd_kernel (0: phase C', 1: phase A')
+template <int KP, int MODE>
 __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
                                                      double* __restrict__ hst, const HmmLayout H, const int force,
                                                      const ScanBufs B) {
@@ -319,6 +359,8 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
     constexpr int G = 32 / KP;
+    constexpr bool BASIS = (MODE != 0);                     // no per-element outputs
+    if (MODE == 1 && hmm_window(st, L, hst, H, sp.L, sp.K) > 0) return;
     const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
     const double* at = current_at(st, L, hst, H);
     const double* __restrict__ lnrho = B.lnrho;
@@ -326,9 +368,9 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     const double* __restrict__ alpha = B.alpha;
     const double* __restrict__ cs = B.chat;                  // rho_i / c_i = rhohat_i / chat_i
     const int64_t item = ((int64_t)blockIdx.x * HW + warp) * G + grp;
-    const int64_t nitems = BASIS ? (int64_t)(sp.nch - 1) * K : sp.nch;
-    const int c = BASIS ? 1 + (int)(item / K) : (int)item;              // basis runs: chunks 1 .. nch-1
-    const int j0 = BASIS ? (int)(item % K) : 0;
+    const int64_t nitems = MODE == 1 ? (int64_t)(sp.nch - 1) * K : sp.nch;
+    const int c = MODE == 1 ? 1 + (int)(item / K) : (int)item;          // basis runs: chunks 1 .. nch-1
+    const int j0 = MODE == 1 ? (int)(item % K) : 0;
     const bool live = item < nitems, mine = live && kk < K;
     double arow[KP], srow[BASIS ? 1 : KP];
 #pragma unroll
@@ -340,7 +382,7 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     const int64_t i0 = (int64_t)c * sp.L;
     const int64_t i1 = (i0 + sp.L < sp.n ? i0 + sp.L : sp.n) - 1;        // last element of the chunk
     double b = 0.0;
-    if (mine) b = BASIS ? (kk == j0 ? 1.0 : 0.0) : B.vb[(int64_t)c * K + kk];
+    if (mine) b = MODE == 1 ? (kk == j0 ? 1.0 : 0.0) : B.vb[(int64_t)c * K + kk];
     double slog = 0.0, gl = 0.0;
     // loads run two steps ahead, exp / reciprocal one step ahead of the dependent chain (which runs through b only)
     auto LR = [&](int64_t i) { return (!BASIS && mine && i >= i0) ? lnrho[i * K + kk] : 0.0; };
@@ -378,7 +420,7 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
                 srow[2 * k2 + 1] = fma(f, vv.y, srow[2 * k2 + 1]);
             }
         }
-        if (BASIS) {
+        if (MODE == 1) {
             // each step is already scaled by 1 / chat_i, so the vector is renormalised every 8 steps only; the result
             // need not be normalised at the end (phase B' uses U e^{ls}, whatever the split between the two)
             const double nb = dot * inv;
@@ -395,7 +437,7 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
             b = dot * inv;                                             // :1010-1011
         }
     }
-    if (BASIS) {
+    if (MODE == 1) {
         if (mine) B.tf[((int64_t)c * K + j0) * K + kk] = b;
         if (live && kk == 0) B.ls[(int64_t)c * K + j0] = slog;
     }
@@ -407,6 +449,80 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
         }
         const double t = group_sum<KP>(gl);
         if (live && kk == 0) B.pgl[c] = t;
+    }
+}
+
+// Mixing mode: the boundary vector of every chunk from a warm-up window of W elements (see hmm_window).
+//   FWD : v[c] = normalised alpha at element cL-1, run over [cL-W, cL-1] from a flat vector (from pi~ when the window
+//         reaches element 0, where the first element has no transition: then it is the exact recursion);
+//   !FWD: w[c] = beta at the last element e of chunk c, un-normalised run from ones over [e+1, e+W] (exact when the
+//         window reaches element N-1, where beta = 1, :939).
+template <int KP, bool FWD>
+__global__ void __launch_bounds__(HT) hmm_window_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                        const double* __restrict__ hst, const HmmLayout H,
+                                                        const int force, const ScanBufs B) {
+    __shared__ __align__(16) double lines[HW][2][32];
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    const int W = hmm_window(st, L, hst, H, sp.L, sp.K);
+    if (W <= 0) return;
+    constexpr int G = 32 / KP;
+    const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
+    const double* at = current_at(st, L, hst, H);
+    const double* __restrict__ rhohat = B.rhohat;
+    const double* __restrict__ chat = B.chat;
+    const int c = (int)(((int64_t)blockIdx.x * HW + warp) * G + grp);
+    const bool live = c < sp.nch, mine = live && kk < K;
+    double av[KP];                                          // FWD: column kk of A~;  !FWD: row kk
+#pragma unroll
+    for (int j = 0; j < KP; ++j) av[j] = (mine && j < K) ? (FWD ? at[j * K + kk] : at[kk * K + j]) : 0.0;
+    if (FWD) {
+        const double* Pc = st + L.params[ctrl[BGMM_CTRL_CUR]];
+        double pmax = -INFINITY;
+        for (int k = 0; k < K; ++k) pmax = fmax(pmax, Pc[L.p_elnpi + k]);
+        const double pt = (kk < K) ? exp(Pc[L.p_elnpi + kk] - pmax) : 0.0;      // pi~ (:849)
+        const int64_t end = (int64_t)c * sp.L - 1;          // last element before chunk c
+        const int64_t first = end - W + 1;                  // first element of the window (may be < 0)
+        double a = mine ? (first <= 0 ? pt : 1.0) : 0.0;
+        auto RH = [&](int64_t i) { return (mine && i >= 0 && i <= end) ? rhohat[i * K + kk] : 0.0; };
+        double rho_c = RH(first), rho_n = RH(first + 1);
+        for (int s = 0; s < W; ++s) {
+            const int64_t i = first + s;
+            const double rho = rho_c;
+            rho_c = rho_n;
+            rho_n = RH(i + 2);
+            double* line = lines[warp][s & 1];
+            publish<KP>(line, lane, a);
+            const double dot = group_dot<KP>(line, grp * KP, av);
+            const double u = rho * (i == 0 ? a : dot);
+            const bool on = live && i >= 0 && i <= end;
+            if ((s & 7) == 7 || s == W - 1) {
+                const double sum = group_sum<KP>(u);
+                if (on) a = u / sum;
+            } else if (on) {
+                a = u;
+            }
+        }
+        if (mine) B.vb[(int64_t)c * K + kk] = (c == 0) ? pt : a;
+    } else {
+        const int64_t e = ((int64_t)(c + 1) * sp.L < sp.n ? (int64_t)(c + 1) * sp.L : sp.n) - 1;   // last element of chunk c
+        const int64_t top = e + W;                          // first element visited (may be > N-1)
+        double b = mine ? 1.0 : 0.0;
+        auto RH = [&](int64_t i) { return (mine && i > e && i < sp.n) ? rhohat[i * K + kk] : 0.0; };
+        auto CI = [&](int64_t i) { return (live && i > e && i < sp.n) ? chat[i] : 1.0; };
+        double rho_c = RH(top), inv_c = 1.0 / CI(top), rho_n = RH(top - 1), ci_n = CI(top - 1);
+        for (int s = 0; s < W; ++s) {
+            const int64_t i = top - s;
+            const double rho = rho_c, inv = inv_c;
+            rho_c = rho_n; inv_c = 1.0 / ci_n;
+            rho_n = RH(i - 2); ci_n = CI(i - 2);
+            const bool on = live && i > e && i < sp.n;
+            double* line = lines[warp][s & 1];
+            publish<KP>(line, lane, on ? rho * b : 0.0);
+            const double dot = group_dot<KP>(line, grp * KP, av);
+            if (on) b = dot * inv;                          // :1010-1011
+        }
+        if (mine) B.vb[(int64_t)c * K + kk] = b;
     }
 }
 
@@ -454,7 +570,6 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
     const int per_cta = HW * G;
     const int64_t nbasis = (int64_t)(sp.nch - 1) * sp.K;
     const unsigned gb = (unsigned)((nbasis + per_cta - 1) / per_cta), gc = (unsigned)((sp.nch + per_cta - 1) / per_cta);
-    if (sp.nch > 1) hmm_fwd_kernel<KP, true><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     const size_t smem_seq = (size_t)2 * seq_batch(sp.K) * (sp.K * sp.K + sp.K + 8) * sizeof(double);
     {   // per launch: the attribute is per device
         cudaError_t e = cudaFuncSetAttribute(hmm_seq_kernel<KP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
@@ -462,11 +577,16 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
             e = cudaFuncSetAttribute(hmm_seq_kernel<KP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(hmm_seq)");
     }
-    hmm_seq_kernel<KP, true><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, force, B);
-    hmm_fwd_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
-    if (sp.nch > 1) hmm_bwd_kernel<KP, true><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
-    hmm_seq_kernel<KP, false><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, force, B);
-    hmm_bwd_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    // boundary vectors: either {basis runs, sequential sweep} or {one warm-up window per chunk}; the device decides
+    // (hmm_window) from the current A~, the kernels of the other branch return at once
+    if (sp.nch > 1) hmm_fwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_seq_kernel<KP, true><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_window_kernel<KP, true><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_fwd_kernel<KP, 0><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    if (sp.nch > 1) hmm_bwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_seq_kernel<KP, false><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_window_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_bwd_kernel<KP, 0><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_reduce_kernel<<<(sp.K * sp.K + 2 + 31) / 32, 256, 0, stream>>>(sp, st, L, hst, H, force, B);
     return check_cuda(cudaGetLastError(), "hmm scan launch");
 }

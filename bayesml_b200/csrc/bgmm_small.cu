@@ -419,7 +419,33 @@ __global__ void __launch_bounds__(256) hmm_trans_kernel(double* __restrict__ st,
     __syncthreads();
     lc = block_sum(lc, red);
     for (int e = tid; e < KK; e += nt) Sn[H.s_at + e] = exp(Sn[H.s_lna + e] - mx);
-    if (tid == 0) { Sn[H.s_misc + 0] = mx; Sn[H.s_misc + 1] = lc; }
+    // Projective (Hilbert-metric) diameter of A~: Delta = max_{j,j'} [max_k d_k - min_k d_k], d_k = ln a~_jk - ln a~_j'k.
+    // Every forward / backward step contracts the Hilbert distance between two message vectors by tau = tanh(Delta / 4)
+    // (Birkhoff), whatever the emission values (diagonal scalings leave the metric unchanged); the scan kernels use
+    // ln tau and ln Delta to decide whether a chunk is long enough to forget its boundary vector (bgmm_hmm.cu).
+    double dl = 0.0;
+    for (int pr = tid; pr < KK; pr += nt) {
+        const int j = pr / K, j2 = pr - j * K;
+        if (j2 <= j) continue;
+        double hi = -INFINITY, lo = INFINITY;
+        for (int k = 0; k < K; ++k) {
+            const double d = Sn[H.s_lna + j * K + k] - Sn[H.s_lna + j2 * K + k];
+            hi = fmax(hi, d);
+            lo = fmin(lo, d);
+        }
+        dl = fmax(dl, hi - lo);
+    }
+    for (int o = 16; o; o >>= 1) dl = fmax(dl, __shfl_xor_sync(0xffffffffu, dl, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = dl;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < (nt >> 5); ++w) dl = fmax(dl, red[w]);
+        Sn[H.s_misc + 0] = mx;
+        Sn[H.s_misc + 1] = lc;
+        Sn[H.s_misc + 2] = log1p(-2.0 / (exp(0.5 * dl) + 1.0));      // ln tanh(Delta / 4)
+        Sn[H.s_misc + 3] = log_ni(dl);                                // ln Delta (-inf when A~ is exactly uniform)
+    }
 }
 
 }  // namespace bgmm
