@@ -20,6 +20,7 @@
 // shared-memory line (one STS + K/2 broadcast LDS.128 per step).  All sums are in a fixed order (deterministic).
 #include "bgmm_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace bgmm {
 
@@ -32,6 +33,7 @@ constexpr int HT = 32 * HW;
 struct ScanPlan {
     int64_t n;
     int K, L, nch;
+    int window_cap;      // longest warm-up window the mixing mode may use (0 disables it); env BGMM_HMM_WINDOW_CAP
 };
 
 // Chunk length: <= 4096 chunks (the length of the sequential phase B), at least 32 elements each.
@@ -107,14 +109,16 @@ __device__ __forceinline__ const double* current_at(const double* st, const Layo
 // window would cost more than the exact alternative — the K basis runs per chunk (phase A) + the sequential sweep (B).
 // Windows that reach the end of the sequence start from the true vector there (pi~ / ones) and are exact.
 __device__ __forceinline__ int hmm_window(const double* st, const Layout& L, const double* hst, const HmmLayout& H,
-                                          int chunk_len, int K) {
+                                          const ScanPlan& sp) {
+    const int chunk_len = sp.L, K = sp.K;
+    if (sp.window_cap <= 0) return 0;
     const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
     const double* misc = hst + H.set[ctrl[BGMM_CTRL_CUR]] + H.s_misc;
     const double lntau = misc[2], lndelta = misc[3];
     if (!(lndelta > -INFINITY)) return 8;                     // A~ exactly uniform: rank one after a single step
     if (!(lntau < 0.0)) return 0;
     const double w = ceil((-41.5 - lndelta) / lntau) + 1.0;     // tau^(W-1) Delta < 1e-18
-    const double cap = fmin(16384.0, 0.5 * (double)chunk_len * (double)K);
+    const double cap = fmin((double)sp.window_cap, 0.5 * (double)chunk_len * (double)K);
     if (!(w <= cap)) return 0;
     return w < 8.0 ? 8 : (int)w;
 }
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
     constexpr int G = 32 / KP;
     const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
     constexpr bool BASIS = (MODE != 0);                     // renormalise sparsely, no per-element outputs
-    if (MODE == 1 && hmm_window(st, L, hst, H, sp.L, sp.K) > 0) return;
+    if (MODE == 1 && hmm_window(st, L, hst, H, sp) > 0) return;
     const double* at = current_at(st, L, hst, H);
     const double* __restrict__ rhohat = B.rhohat;
     const double* __restrict__ rowmax = B.rowmax;
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(SEQ_T) hmm_seq_kernel(const ScanPlan sp, const
     __shared__ __align__(16) double lines[2][32];
     const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
-    if (hmm_window(st, L, hst, H, sp.L, sp.K) > 0) return;   // mixing mode: the window kernel wrote the boundary vectors
+    if (hmm_window(st, L, hst, H, sp) > 0) return;   // mixing mode: the window kernel wrote the boundary vectors
     const int K = sp.K, KK = K * K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb_chunk = seq_batch(K);
     const int stride = KK + K + 8;                       // per chunk: matrix [K][K] | e [K] | {exp(max), ...}
@@ -267,10 +271,20 @@ __global__ void __launch_bounds__(SEQ_T) hmm_seq_kernel(const ScanPlan sp, const
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
     };
-    auto scale_batch = [&](int b, int t0, int nt) {      // ls -> e = exp(ls - max), exp(max); one warp per chunk, lane = j
+    auto scale_batch = [&](int b, int t0, int nt) {      // ls -> e = exp(ls - max), exp(max)
         double* dst = sq + (size_t)(b & 1) * nb_chunk * stride;
         const int s0 = b * nb_chunk, cnt = min(nb_chunk, nsteps - s0);
-        for (int q = (tid - t0) >> 5; q < cnt; q += nt >> 5) {
+        if (K <= 8) {                                    // many small chunks per batch: one thread per chunk
+            for (int q = tid - t0; q < cnt; q += nt) {
+                double* e = dst + q * stride + KK;
+                double mx = -INFINITY;
+                for (int j = 0; j < K; ++j) mx = fmax(mx, e[j]);
+                for (int j = 0; j < K; ++j) e[j] = (mx > -INFINITY) ? exp(e[j] - mx) : 0.0;
+                e[K] = (mx > -INFINITY) ? exp(mx) : 0.0;
+            }
+            return;
+        }
+        for (int q = (tid - t0) >> 5; q < cnt; q += nt >> 5) {      // few large chunks: one warp per chunk, lane = j
             double* e = dst + q * stride + KK;
             const double v = lane < K ? e[lane] : -INFINITY;
             double mx = v;
@@ -360,7 +374,7 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
     constexpr int G = 32 / KP;
     constexpr bool BASIS = (MODE != 0);                     // no per-element outputs
-    if (MODE == 1 && hmm_window(st, L, hst, H, sp.L, sp.K) > 0) return;
+    if (MODE == 1 && hmm_window(st, L, hst, H, sp) > 0) return;
     const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
     const double* at = current_at(st, L, hst, H);
     const double* __restrict__ lnrho = B.lnrho;
@@ -464,7 +478,7 @@ __global__ void __launch_bounds__(HT) hmm_window_kernel(const ScanPlan sp, const
     __shared__ __align__(16) double lines[HW][2][32];
     const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
-    const int W = hmm_window(st, L, hst, H, sp.L, sp.K);
+    const int W = hmm_window(st, L, hst, H, sp);
     if (W <= 0) return;
     constexpr int G = 32 / KP;
     const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
@@ -476,51 +490,72 @@ __global__ void __launch_bounds__(HT) hmm_window_kernel(const ScanPlan sp, const
     double av[KP];                                          // FWD: column kk of A~;  !FWD: row kk
 #pragma unroll
     for (int j = 0; j < KP; ++j) av[j] = (mine && j < K) ? (FWD ? at[j * K + kk] : at[kk * K + j]) : 0.0;
+    // The window is walked in blocks of 8 steps: the 8 emission values (and normalisers) of the NEXT block are in flight
+    // while this block runs, so the global-load latency is spread over 8 steps of the dependent chain.
+    const int WB = (W + 7) >> 3;
     if (FWD) {
         const double* Pc = st + L.params[ctrl[BGMM_CTRL_CUR]];
         double pmax = -INFINITY;
         for (int k = 0; k < K; ++k) pmax = fmax(pmax, Pc[L.p_elnpi + k]);
         const double pt = (kk < K) ? exp(Pc[L.p_elnpi + kk] - pmax) : 0.0;      // pi~ (:849)
         const int64_t end = (int64_t)c * sp.L - 1;          // last element before chunk c
-        const int64_t first = end - W + 1;                  // first element of the window (may be < 0)
+        const int64_t first = end - 8 * (int64_t)WB + 1;    // first element of the window (may be < 0)
         double a = mine ? (first <= 0 ? pt : 1.0) : 0.0;
         auto RH = [&](int64_t i) { return (mine && i >= 0 && i <= end) ? rhohat[i * K + kk] : 0.0; };
-        double rho_c = RH(first), rho_n = RH(first + 1);
-        for (int s = 0; s < W; ++s) {
-            const int64_t i = first + s;
-            const double rho = rho_c;
-            rho_c = rho_n;
-            rho_n = RH(i + 2);
-            double* line = lines[warp][s & 1];
-            publish<KP>(line, lane, a);
-            const double dot = group_dot<KP>(line, grp * KP, av);
-            const double u = rho * (i == 0 ? a : dot);
-            const bool on = live && i >= 0 && i <= end;
-            if ((s & 7) == 7 || s == W - 1) {
-                const double sum = group_sum<KP>(u);
-                if (on) a = u / sum;
-            } else if (on) {
-                a = u;
+        double rc[8], rn[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) rn[t] = RH(first + t);
+        for (int blk = 0; blk < WB; ++blk) {
+            const int64_t ib = first + 8 * (int64_t)blk;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) rc[t] = rn[t];
+            if (blk + 1 < WB) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) rn[t] = RH(ib + 8 + t);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int64_t i = ib + t;
+                double* line = lines[warp][t & 1];
+                publish<KP>(line, lane, a);
+                const double dot = group_dot<KP>(line, grp * KP, av);
+                const double u = rc[t] * (i == 0 ? a : dot);
+                const bool on = live && i >= 0;
+                if (t == 7) {
+                    const double sum = group_sum<KP>(u);
+                    if (on) a = u / sum;
+                } else if (on) {
+                    a = u;
+                }
             }
         }
         if (mine) B.vb[(int64_t)c * K + kk] = (c == 0) ? pt : a;
     } else {
         const int64_t e = ((int64_t)(c + 1) * sp.L < sp.n ? (int64_t)(c + 1) * sp.L : sp.n) - 1;   // last element of chunk c
-        const int64_t top = e + W;                          // first element visited (may be > N-1)
+        const int64_t top = e + 8 * (int64_t)WB;            // first element visited (may be > N-1)
         double b = mine ? 1.0 : 0.0;
         auto RH = [&](int64_t i) { return (mine && i > e && i < sp.n) ? rhohat[i * K + kk] : 0.0; };
         auto CI = [&](int64_t i) { return (live && i > e && i < sp.n) ? chat[i] : 1.0; };
-        double rho_c = RH(top), inv_c = 1.0 / CI(top), rho_n = RH(top - 1), ci_n = CI(top - 1);
-        for (int s = 0; s < W; ++s) {
-            const int64_t i = top - s;
-            const double rho = rho_c, inv = inv_c;
-            rho_c = rho_n; inv_c = 1.0 / ci_n;
-            rho_n = RH(i - 2); ci_n = CI(i - 2);
-            const bool on = live && i > e && i < sp.n;
-            double* line = lines[warp][s & 1];
-            publish<KP>(line, lane, on ? rho * b : 0.0);
-            const double dot = group_dot<KP>(line, grp * KP, av);
-            if (on) b = dot * inv;                          // :1010-1011
+        double rc[8], rn[8], ic[8], cn[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { rn[t] = RH(top - t); cn[t] = CI(top - t); }
+        for (int blk = 0; blk < WB; ++blk) {
+            const int64_t ib = top - 8 * (int64_t)blk;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { rc[t] = rn[t]; ic[t] = 1.0 / cn[t]; }
+            if (blk + 1 < WB) {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) { rn[t] = RH(ib - 8 - t); cn[t] = CI(ib - 8 - t); }
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const int64_t i = ib - t;
+                const bool on = live && i > e && i < sp.n;
+                double* line = lines[warp][t & 1];
+                publish<KP>(line, lane, on ? rc[t] * b : 0.0);
+                const double dot = group_dot<KP>(line, grp * KP, av);
+                if (on) b = dot * ic[t];                    // :1010-1011
+            }
         }
         if (mine) B.vb[(int64_t)c * K + kk] = b;
     }
@@ -627,6 +662,8 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
     if (mode == BGMM_HMM_FULL) {
         ScanPlan sp;
         sp.n = n; sp.K = K; sp.L = hmm_chunk_len(n); sp.nch = (int)((n + sp.L - 1) / sp.L);
+        const char* wc = getenv("BGMM_HMM_WINDOW_CAP");          // tests / experiments: 0 forces the basis + sweep path
+        sp.window_cap = wc != nullptr ? atoi(wc) : 16384;
         const int64_t KK = (int64_t)K * K, nch = sp.nch;
         ScanBufs B;
         B.lnrho = lnrho; B.alpha = alpha; B.gamma = gamma; B.cs = cs; B.beta_out = beta_out;
