@@ -473,12 +473,13 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
 //         window reaches element N-1, where beta = 1, :939).
 template <int KP, bool FWD>
 __global__ void __launch_bounds__(HT) hmm_window_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
-                                                        const double* __restrict__ hst, const HmmLayout H,
+                                                        double* hst, const HmmLayout H,
                                                         const int force, const ScanBufs B) {
     __shared__ __align__(16) double lines[HW][2][32];
     const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
     const int W = hmm_window(st, L, hst, H, sp);
+    if (FWD && blockIdx.x == 0 && threadIdx.x == 0) hst[H.sc + 2] = (double)W;   // diagnostics: the path taken
     if (W <= 0) return;
     constexpr int G = 32 / KP;
     const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;

@@ -510,6 +510,7 @@ class HMMEngine(VBEngine):
                     "ms": h[self.hoff["ms"]:self.hoff["ms"] + K * K].reshape(K, K).copy(),
                     "gamma0": h[self.hoff["g0"]:self.hoff["g0"] + K].copy(),
                     "sc": h[self.hoff["sc"]:self.hoff["sc"] + 2].copy(),
+                    "window": int(h[self.hoff["sc"] + 2]),      # warm-up window of the last E-step (0 = basis + sweep path)
                     "vlx": h[self.hoff["vlx"]:self.hoff["vlx"] + 4].copy()})
         return out
 

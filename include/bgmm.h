@@ -184,7 +184,7 @@ int bgmm_publish(int K, int D, double* state, const void* comm_desc, int force, 
  *   ZETA0 [K][K] prior h0_zeta_vecs | LNCZ0 ln C(zeta0) sum (:828) |
  *   SET0 / SET1 (ping-pong with ctrl.cur): +SET_ZETA [K][K] hn_zeta_vecs, +SET_LNA ln a~ (:852), +SET_AT a~ = exp(ln a~
  *   - max) (:853), +SET_MISC {max ln a~, ln C(zeta) sum (:854)} |
- *   MS [K][K] sum_i xi_i (:839) | G0 [K] gamma_0 | SC {sum_i ln c_i, sum gamma.ln rho} |
+ *   MS [K][K] sum_i xi_i (:839) | G0 [K] gamma_0 | SC {sum_i ln c_i, sum gamma.ln rho, warm-up window of the last pass} |
  *   VLX {E ln p(z) :886, E ln p(A) :892, -E ln q(z) :906-909, -E ln q(A) :915}. */
 enum {
     BGMM_HMM_OFF_ZETA0 = 0, BGMM_HMM_OFF_LNCZ0, BGMM_HMM_OFF_SET0, BGMM_HMM_OFF_SET1, BGMM_HMM_OFF_SET_ZETA,

@@ -167,3 +167,34 @@ def test_unsupported_shape_fails_loudly(lib_built):
     from bayesml_b200.engine import HMMEngine
     with pytest.raises(RuntimeError, match="unsupported shape"):
         HMMEngine(40, 4)
+
+
+def test_window_and_basis_paths_agree(lib_built, monkeypatch):
+    """The two ways of getting the chunk boundary vectors — warm-up windows (when the Birkhoff criterion on A~ holds) and
+    K basis runs + sequential sweep — must give the same fit; the window path must actually have been taken."""
+    from bayesml_b200.engine import HMMEngine
+    n, D, K, iters = 1_500_000, 2, 4, 5          # chunks of 368 elements: a window of ~230 steps pays off
+    rng = np.random.default_rng(5)
+    mu = rng.normal(0.0, 3.0, size=(K, D))
+    jump = rng.random(n) > 0.7
+    jump[0] = True
+    nxt = rng.integers(0, K, size=n)
+    z = nxt[np.maximum.accumulate(np.where(jump, np.arange(n), 0))]
+    x = mu[z] + rng.normal(size=(n, D))
+    eye = np.tile(np.eye(D), (K, 1, 1))
+    out = {}
+    for cap in ("0", "16384"):
+        monkeypatch.setenv("BGMM_HMM_WINDOW_CAP", cap)
+        eng = HMMEngine(K, D)
+        eng.load_data(x)
+        eng.set_hmm_prior(np.full(K, .5), np.full((K, K), .5), np.zeros((K, D)), np.ones(K), np.full(K, float(D)), eye,
+                          np.zeros(K), 0.0, 0.0)
+        eng.set_hmm_params(np.full(K, .5), np.full((K, K), .5), mu + 0.3, np.ones(K), np.full(K, float(D)), eye * D)
+        hist, _ = eng.run(iters, 0.0)
+        out[cap] = (hist, eng.fetch_params(), eng.gamma_buf.cpu().numpy(), eng.cs_buf.cpu().numpy())
+    assert out["0"][1]["window"] == 0 and out["16384"][1]["window"] >= 8
+    assert np.allclose(out["0"][0], out["16384"][0], rtol=1e-11)
+    for key in ("ms", "zeta", "m", "winv", "ns"):
+        assert np.allclose(out["0"][1][key], out["16384"][1][key], rtol=1e-10, atol=1e-12), key
+    assert np.allclose(out["0"][2], out["16384"][2], rtol=1e-9, atol=1e-13)
+    assert np.allclose(out["0"][3], out["16384"][3], rtol=1e-11)
