@@ -22,7 +22,7 @@ MAX_RANKS = 16
 N_CTRL = 16
 HMM_OFF_NAMES = ("zeta0", "lncz0", "set0", "set1", "set_zeta", "set_lna", "set_at", "set_misc", "ms", "g0", "sc", "vlx",
                  "total")
-HMM_FULL, HMM_STATS_FROM_GAMMA = 0, 1
+HMM_FULL, HMM_STATS_FROM_GAMMA, HMM_EMISSION_ONLY = 0, 1, 2
 
 _lib = None
 
@@ -78,6 +78,8 @@ def load():
     lib.bgmm_hmm_scan_workspace_doubles.argtypes = [i32, i64]
     lib.bgmm_hmm_pass.restype = i32
     lib.bgmm_hmm_pass.argtypes = [vp, i64, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.bgmm_hmm_viterbi.restype = i32
+    lib.bgmm_hmm_viterbi.argtypes = [i64, i32, vp, vp, vp, vp, vp, vp, vp]
     lib.bgmm_hmm_small.restype = i32
     lib.bgmm_hmm_small.argtypes = [i32, i32, vp, vp, i32, i32, f64, i32, vp]
     if lib.bgmm_abi_version() != ABI_VERSION:

@@ -627,7 +627,138 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
     return check_cuda(cudaGetLastError(), "hmm scan launch");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Viterbi (_hiddenmarkovnormal.py:1466-1480): omega_0 = ln rho_0 + ln pi~;  omega_i[k] = ln rho_i[k] + max_j (ln a~_jk +
+// omega_{i-1}[j]), phi_i[k] = argmax_j (first maximum, as np.argmax); then the path is traced back from argmax omega_{N-1}.
+// The recursion is sequential in i and is kept in the reference's operation order (same additions, same comparison order),
+// so omega / phi / the path are bit-identical to numpy's for identical ln rho.  One CTA: warps 1..3 stage ln rho tiles
+// into shared memory (cp.async, double buffered), warp 0 runs the recursion (lane k owns state k and column k of ln a~).
+constexpr int VT_TILE = 256;       // steps per staged tile
+template <int KP>
+__global__ void __launch_bounds__(SEQ_T) hmm_viterbi_fwd_kernel(const int64_t n, const int K, const double* __restrict__ lnrho,
+                                                                const double* __restrict__ lnpi,
+                                                                const double* __restrict__ lna, double* __restrict__ omega,
+                                                                int32_t* __restrict__ phi) {
+    extern __shared__ __align__(16) double vt[];            // [2][VT_TILE][K]
+    __shared__ __align__(16) double lines[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool mine = lane < K;
+    const int64_t ntile = (n + VT_TILE - 1) / VT_TILE;
+    auto load_tile = [&](int64_t t, int t0, int nt) {
+        double* dst = vt + (size_t)(t & 1) * VT_TILE * K;
+        const int64_t base = t * VT_TILE * K;
+        const int64_t cnt = (t * VT_TILE + VT_TILE <= n ? (int64_t)VT_TILE : n - t * VT_TILE) * K;
+        for (int64_t e = tid - t0; e < cnt; e += nt) cp_async8(dst + e, lnrho + base + e);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    };
+    double acol[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) acol[j] = (mine && j < K) ? lna[j * K + lane] : -INFINITY;
+    double om = 0.0;
+    load_tile(0, 0, SEQ_T);
+    __syncthreads();
+    for (int64_t t = 0; t < ntile; ++t) {
+        if (warp > 0) {
+            if (t + 1 < ntile) load_tile(t + 1, 32, SEQ_T - 32);
+        } else {
+            const double* src = vt + (size_t)(t & 1) * VT_TILE * K;
+            const int cnt = (int)(t * VT_TILE + VT_TILE <= n ? (int64_t)VT_TILE : n - t * VT_TILE);
+            for (int q = 0; q < cnt; ++q) {
+                const int64_t i = t * VT_TILE + q;
+                const double lr = mine ? src[q * K + lane] : 0.0;
+                int arg = 0;
+                if (i == 0) {
+                    om = mine ? lr + lnpi[lane] : -INFINITY;                 // :1469
+                } else {
+                    double* line = lines[q & 1];
+                    line[lane] = om;
+                    __syncwarp();
+                    double best = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) {
+                        if (j < K) {
+                            const double cand = acol[j] + line[j];           // ln a~[j][k] + omega_{i-1}[j]   (:1471-1472)
+                            if (j == 0 || cand > best) { best = cand; arg = j; }
+                        }
+                    }
+                    om = lr + best;
+                }
+                if (mine) { omega[i * K + lane] = om; phi[i * K + lane] = arg; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// back-tracking (:1474-1479): z_{N-1} = argmax omega_{N-1}; z_i = phi_{i+1}[z_{i+1}].  phi tiles are staged backwards.
+__global__ void __launch_bounds__(SEQ_T) hmm_viterbi_back_kernel(const int64_t n, const int K, const double* __restrict__ omega,
+                                                                 const int32_t* __restrict__ phi, int32_t* __restrict__ path) {
+    extern __shared__ __align__(16) int32_t pt[];           // [TB][K]
+    constexpr int TB = 1024;
+    __shared__ int32_t zs[TB];
+    const int tid = threadIdx.x;
+    __shared__ int cur;
+    if (tid == 0) {
+        int best = 0;
+        double bv = omega[(n - 1) * K];
+        for (int k = 1; k < K; ++k) {
+            const double v = omega[(n - 1) * K + k];
+            if (v > bv) { bv = v; best = k; }
+        }
+        cur = best;
+        path[n - 1] = best;
+    }
+    __syncthreads();
+    // elements n-2 .. 0 in tiles of TB, highest tile first; element i needs phi[i+1]
+    for (int64_t hi = n - 2; hi >= 0; hi -= TB) {
+        const int64_t lo = hi - TB + 1 > 0 ? hi - TB + 1 : 0;
+        const int cnt = (int)(hi - lo + 1);
+        for (int64_t e = tid; e < (int64_t)cnt * K; e += SEQ_T) pt[e] = phi[(lo + 1) * K + e];       // rows lo+1 .. hi+1
+        __syncthreads();
+        if (tid == 0) {
+            int z = cur;
+            for (int q = cnt - 1; q >= 0; --q) {
+                z = pt[q * K + z];
+                zs[q] = z;
+            }
+            cur = z;
+        }
+        __syncthreads();
+        for (int q = tid; q < cnt; q += SEQ_T) path[lo + q] = zs[q];
+        __syncthreads();
+    }
+}
+
 }  // namespace bgmm
+
+extern "C" int bgmm_hmm_viterbi(int64_t n, int K, const double* lnrho, const double* lnpi, const double* lna, double* omega,
+                                int32_t* phi, int32_t* path, void* stream) {
+    using namespace bgmm;
+    if (n <= 0 || K < 1 || K > 32 || lnrho == nullptr || lnpi == nullptr || lna == nullptr || omega == nullptr ||
+        phi == nullptr || path == nullptr) {
+        set_error("bgmm_hmm_viterbi: bad argument (n=%lld K=%d, K <= 32)", (long long)n, K);
+        return BGMM_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem_f = (size_t)2 * VT_TILE * K * sizeof(double);
+    const size_t smem_b = (size_t)1024 * K * sizeof(int32_t);
+    cudaError_t e = cudaFuncSetAttribute(hmm_viterbi_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1024 * 32 * 4));
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(viterbi_back)");
+#define BGMM_VIT(KP)                                                                                                   \
+    do {                                                                                                               \
+        e = cudaFuncSetAttribute(hmm_viterbi_fwd_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);  \
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(viterbi_fwd)");                                \
+        hmm_viterbi_fwd_kernel<KP><<<1, SEQ_T, smem_f, s>>>(n, K, lnrho, lnpi, lna, omega, phi);                         \
+    } while (0)
+    if (K <= 2) BGMM_VIT(2);
+    else if (K <= 4) BGMM_VIT(4);
+    else if (K <= 8) BGMM_VIT(8);
+    else if (K <= 16) BGMM_VIT(16);
+    else BGMM_VIT(32);
+#undef BGMM_VIT
+    hmm_viterbi_back_kernel<<<1, SEQ_T, smem_b, s>>>(n, K, omega, phi, path);
+    return check_cuda(cudaGetLastError(), "viterbi launch");
+}
 
 extern "C" int64_t bgmm_hmm_scan_workspace_doubles(int K, int64_t n) {
     if (K <= 0 || K > 32 || n <= 0) return 0;
@@ -646,10 +777,17 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
         set_error("bgmm_hmm_pass: unsupported shape K=%d D=%d (float64, K <= 32, D <= 128)", K, D);
         return BGMM_ENOSUP;
     }
-    if (x == nullptr || n <= 0 || state == nullptr || hst == nullptr || workspace == nullptr || gamma == nullptr ||
+    if (x == nullptr || n <= 0 || state == nullptr || hst == nullptr || workspace == nullptr ||
+        (mode != BGMM_HMM_EMISSION_ONLY && gamma == nullptr) ||
         (mode == BGMM_HMM_FULL && (scan_ws == nullptr || lnrho == nullptr || alpha == nullptr || cs == nullptr))) {
         set_error("bgmm_hmm_pass: NULL buffer or n <= 0");
         return BGMM_EINVAL;
+    }
+    if (mode == BGMM_HMM_EMISSION_ONLY) {                        // ln rho of x under the current parameter set, nothing else
+        if (lnrho == nullptr) { set_error("bgmm_hmm_pass: lnrho is NULL"); return BGMM_EINVAL; }
+        PassArgs ea{x, n, state, workspace, nullptr, lnrho, nullptr, nullptr, force, 0};
+        ea.lnrho_only = 1;
+        return launch_pass_large_part(ea, K, D, BGMM_F64, 1, (cudaStream_t)stream);
     }
     if (mode != BGMM_HMM_FULL && mode != BGMM_HMM_STATS_FROM_GAMMA) {
         set_error("bgmm_hmm_pass: unknown mode %d", mode);

@@ -514,6 +514,26 @@ class HMMEngine(VBEngine):
                     "vlx": h[self.hoff["vlx"]:self.hoff["vlx"] + 4].copy()})
         return out
 
+    def viterbi(self, ln_pi_tilde, ln_a_tilde):
+        """Most probable state path of the loaded sequence under the current parameter set (:1466-1480): the emission log
+        densities (bgmm_hmm_pass, emission-only mode), then the max-plus recursion and the back-tracking on the device
+        (bgmm_hmm_viterbi).  -> (path [n] int64 numpy, omega [n][K] device tensor, phi [n][K] int32 device tensor)."""
+        n, K = self.n_local, self.K
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bgmm_hmm_pass(self.x.data_ptr(), n, K, self.D, self.state.data_ptr(), self.hst.data_ptr(),
+                                              self.workspace.data_ptr(), 0, self.lnrho_buf.data_ptr(), 0, 0, 0, 0,
+                                              _lib.HMM_EMISSION_ONLY, 1, self._stream()), "bgmm_hmm_pass(emission)")
+            lnpi = torch.as_tensor(np.ascontiguousarray(ln_pi_tilde, dtype=np.float64)).to(self.device)
+            lna = torch.as_tensor(np.ascontiguousarray(ln_a_tilde, dtype=np.float64)).to(self.device)
+            omega = torch.empty((n, K), dtype=torch.float64, device=self.device)
+            phi = torch.empty((n, K), dtype=torch.int32, device=self.device)
+            path = torch.empty(n, dtype=torch.int32, device=self.device)
+            _lib.check(self.lib.bgmm_hmm_viterbi(n, K, self.lnrho_buf.data_ptr(), lnpi.data_ptr(), lna.data_ptr(),
+                                                 omega.data_ptr(), phi.data_ptr(), path.data_ptr(), self._stream()),
+                       "bgmm_hmm_viterbi")
+            self.kernel_launches += 5
+            return path.cpu().numpy().astype(np.int64), omega, phi
+
     def final_pass(self):
         """`_update_q_z` with the current parameters (:1133, :1490) keeping ln rho, alpha, beta, gamma, c on the device."""
         with torch.cuda.device(self.device):

@@ -7,8 +7,8 @@ statistics, the M-steps, the ELBO and the convergence test run in hand-written s
 include/bgmm.h: bgmm_hmm_pass / bgmm_hmm_small) through `bayesml_b200.engine.HMMEngine`; there is no CPU fallback
 for that path (float64, c_num_classes <= 32, c_degree <= 128; anything else raises).  What stays on the host is
 K-sized numpy work outside the iteration loop: argument checks, hyperparameter plumbing, the RNG-consuming
-initialisations (so the random stream is the reference's), restart bookkeeping, the predictive parameters and the
-max-plus (Viterbi) back-tracking over device-computed emission log densities.
+initialisations (so the random stream is the reference's), restart bookkeeping and the predictive parameters.  The
+Viterbi path of `estimate_latent_vars` (max-plus recursion + back-tracking) also runs on the device (bgmm_hmm_viterbi).
 
 The per-element arrays (`_ln_rho`, `_rho`, `alpha_vecs`, `beta_vecs`, `gamma_vecs`, `_cs`, `xi_mats`) stay on the
 GPU until the attribute is read; `xi_mats` (N x K x K) is formed on the host from them on first access.
@@ -121,9 +121,9 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         self.p_lambda_mats = np.empty([K, D, D])
         self.p_lambda_mats_inv = np.empty([K, D, D])
 
-        # Viterbi work arrays (:598-599)
-        self.omega_vecs = None
-        self.phi_vecs = None
+        # Viterbi work arrays (:598-599), device resident until read
+        self._lazy_omega_vecs = _LazyDeviceArray()
+        self._lazy_phi_vecs = _LazyDeviceArray()
 
         self.set_h0_params(h0_eta_vec, h0_zeta_vecs, h0_m_vecs, h0_kappas, h0_nus, h0_w_mats)
 
@@ -133,6 +133,20 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
     beta_vecs = _lazy_property("beta_vecs")
     gamma_vecs = _lazy_property("gamma_vecs")
     _cs = _lazy_property("_cs")
+    omega_vecs = _lazy_property("omega_vecs")
+
+    @property
+    def phi_vecs(self):
+        """arg-max table of the Viterbi recursion (:1472); int64 as in the reference."""
+        v = self._lazy_phi_vecs.get()
+        if v is not None and v.dtype != np.int64:
+            v = v.astype(np.int64)
+            self._lazy_phi_vecs.set_host(v)
+        return v
+
+    @phi_vecs.setter
+    def phi_vecs(self, value):
+        self._lazy_phi_vecs.set_host(value)
 
     @property
     def _rho(self):
@@ -562,8 +576,8 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         """Hidden-state estimates of the sequence x (:1425-1499): the jointly most probable path (`viterbi=True`,
         loss "0-1" only) or the per-element marginals gamma ("squared"/"KL") / their arg-max ("0-1").
 
-        The emission log densities and (for `viterbi=False`) the whole forward-backward pass run on the device; the
-        max-plus recursion and back-tracking of the Viterbi path are an O(N K^2) host loop, as in the reference.
+        Everything runs on the device: the emission log densities, the max-plus recursion and back-tracking of the
+        Viterbi path (in the reference's operation order), or (for `viterbi=False`) the whole forward-backward pass.
         As in the reference, `viterbi=False` also overwrites ns / ms / x_bar_vecs / s_mats with the statistics of x."""
         _check.float_vecs(x, 'x', DataFormatError)
         if x.shape[-1] != self.c_degree:
@@ -583,25 +597,16 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         eng.load_data(x)
         self._push_prior(eng)
         if viterbi:
-            # the statistics side effects of the device pass are not applied: the reference only fills _ln_rho/_rho here
+            # only the emission densities are evaluated (the reference fills _ln_rho / _rho here and nothing else); the
+            # max-plus recursion and the back-tracking run on the device in the reference's operation order
             self._push_hn(eng)
-            eng.final_pass()
-            self._clear_elementwise()
-            ln_rho = eng.lnrho_buf.cpu().numpy()
-            self._lazy_ln_rho.set_host(ln_rho)
+            path, omega, phi = eng.viterbi(self._ln_pi_tilde_vec, self._ln_a_tilde_mat)
+            self._rho_host = None                   # alpha / beta / gamma / xi keep their values, as in the reference
+            self._lazy_ln_rho.set_device(eng.lnrho_buf)
+            self._lazy_omega_vecs.set_device(omega)
+            self._lazy_phi_vecs.set_device(phi)
             z_hat = np.zeros([n, K], dtype=int)
-            self.omega_vecs = np.zeros([n, K])
-            self.phi_vecs = np.zeros([n, K], dtype=int)
-            self.omega_vecs[0] = ln_rho[0] + self._ln_pi_tilde_vec
-            for i in range(1, n):
-                cand = self._ln_a_tilde_mat + self.omega_vecs[i - 1, :, np.newaxis]
-                self.omega_vecs[i] = ln_rho[i] + np.max(cand, axis=0)
-                self.phi_vecs[i] = np.argmax(cand, axis=0)
-            k = np.argmax(self.omega_vecs[-1])
-            z_hat[-1, k] = 1
-            for i in range(n - 2, -1, -1):
-                k = self.phi_vecs[i + 1, k]
-                z_hat[i, k] = 1
+            z_hat[np.arange(n), path] = 1
             return z_hat
         self._final_e_step(eng)
         if loss == "squared" or loss == "KL":

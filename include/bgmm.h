@@ -201,6 +201,7 @@ int64_t bgmm_hmm_scan_workspace_doubles(int K, int64_t n);
 #define BGMM_HMM_FULL 0             /* `_update_q_z` :1020-1026: emission density, forward, backward, gamma, xi, statistics */
 #define BGMM_HMM_STATS_FROM_GAMMA 1 /* `_calc_n_m_x_bar_s` :837-845 of a given gamma (random_responsibility init :944-952);
                                        the caller has written MS, G0 and SC into hst                                      */
+#define BGMM_HMM_EMISSION_ONLY 2    /* `_calc_rho` :988-996 only: lnrho[n][K] (the other per-element buffers may be NULL)    */
 /* One E-step over the whole (centred, float64) sequence x[n][D] with the CURRENT parameter set:
  *   lnrho[n][K] (:988-996), alpha[n][K] and cs[n] (:999-1006), gamma[n][K] (:1014), optionally beta_out[n][K]
  *   (:1008-1011; NULL inside the loop), hst.MS / G0 / SC, and the gamma-weighted raw moments into state.STATS.
@@ -213,6 +214,13 @@ int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* state, double*
  * ELBO terms with A / xi / gamma_0 / c) followed by the mixture's small kernel with ln rho free of E[ln pi] (:989-992)
  * and the 9-term ELBO (:869-932).  Modes as bgmm_small. */
 int bgmm_hmm_small(int K, int D, double* state, double* hst, int mode, int max_itr, double tol, int hist_len, void* stream);
+
+/* Viterbi path (`estimate_latent_vars(viterbi=True)`, :1466-1480) from lnrho[n][K], ln pi~ [K] and ln a~ [K][K] (device
+ * pointers): omega[n][K] (:1469-1471), phi[n][K] (int32, row 0 is not written — the reference leaves it zero, :1472) and
+ * path[n] (int32 state indices, :1474-1479).  The recursion keeps the reference's operation order, so the outputs are
+ * bit-identical to numpy's for identical inputs.  K <= 32. */
+int bgmm_hmm_viterbi(int64_t n, int K, const double* lnrho, const double* lnpi, const double* lna, double* omega,
+                     int32_t* phi, int32_t* path, void* stream);
 
 #ifdef __cplusplus
 }

@@ -112,7 +112,10 @@ def test_update_posterior_end_to_end(name, lib_built):
     if "latent_x" in g.files:
         vit = model.estimate_latent_vars(g["latent_x"], loss="0-1", viterbi=True)
         assert np.array_equal(vit, g["latent_viterbi"])
+        assert vit.dtype == g["latent_viterbi"].dtype
         assert _close(model.omega_vecs, g["latent_omega"], rtol=1e-8)
+        assert model.phi_vecs.shape == model.omega_vecs.shape and np.array_equal(model.phi_vecs[0], np.zeros(K, dtype=int))
+        assert _close(model.make_prediction("squared"), g["pred_squared"], rtol=1e-8)     # gamma of the fit is untouched
         onehot = model.estimate_latent_vars(g["latent_x"], loss="0-1", viterbi=False)
         assert np.array_equal(onehot, g["latent_marginal_onehot"])
         gam = model.estimate_latent_vars(g["latent_x"], loss="squared", viterbi=False)
@@ -198,3 +201,38 @@ def test_window_and_basis_paths_agree(lib_built, monkeypatch):
         assert np.allclose(out["0"][1][key], out["16384"][1][key], rtol=1e-10, atol=1e-12), key
     assert np.allclose(out["0"][2], out["16384"][2], rtol=1e-9, atol=1e-13)
     assert np.allclose(out["0"][3], out["16384"][3], rtol=1e-11)
+
+
+def test_viterbi_long_sequence_is_bit_identical_to_the_numpy_recursion(lib_built):
+    """bgmm_hmm_viterbi on a 300k-element sequence vs the reference's recursion (numpy, same ln rho): omega, phi and the
+    path are bit-identical (same operation order)."""
+    import torch
+    from bayesml_b200 import _lib
+    n, K = 300_000, 7
+    rng = np.random.default_rng(11)
+    ln_rho = rng.normal(size=(n, K)) * 3.0 - 5.0
+    ln_pi = np.log(rng.dirichlet(np.ones(K)))
+    ln_a = np.log(rng.dirichlet(np.ones(K), size=K))
+    omega = np.zeros((n, K))
+    phi = np.zeros((n, K), dtype=np.int64)
+    omega[0] = ln_rho[0] + ln_pi
+    for i in range(1, n):
+        cand = ln_a + omega[i - 1, :, np.newaxis]
+        omega[i] = ln_rho[i] + np.max(cand, axis=0)
+        phi[i] = np.argmax(cand, axis=0)
+    path = np.empty(n, dtype=np.int64)
+    path[-1] = np.argmax(omega[-1])
+    for i in range(n - 2, -1, -1):
+        path[i] = phi[i + 1, path[i + 1]]
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.as_tensor(a).to(dev)  # noqa: E731
+    d_rho, d_pi, d_a = t(ln_rho), t(ln_pi), t(ln_a)
+    d_om = torch.empty((n, K), dtype=torch.float64, device=dev)
+    d_phi = torch.empty((n, K), dtype=torch.int32, device=dev)
+    d_path = torch.empty(n, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().bgmm_hmm_viterbi(n, K, d_rho.data_ptr(), d_pi.data_ptr(), d_a.data_ptr(), d_om.data_ptr(),
+                                            d_phi.data_ptr(), d_path.data_ptr(), torch.cuda.current_stream().cuda_stream),
+               "bgmm_hmm_viterbi")
+    assert np.array_equal(d_om.cpu().numpy(), omega)
+    assert np.array_equal(d_phi.cpu().numpy(), phi)
+    assert np.array_equal(d_path.cpu().numpy(), path)
