@@ -63,14 +63,18 @@ __global__ void __launch_bounds__(LG_THREADS) coef_pack_kernel(const double* __r
 
 constexpr int LG_ETHREADS = 288;   // E kernel: 8 GEMM warps + 1 warp that streams the coefficient chunks by TMA
 
-// (i, j) of every logical feature, packed (i << 8) | j; kinds: 0xFFFF constant 1, 0xFE00 | i linear, 0xFFFE padding (zero).
+// Every logical feature as a product x[a] * x[b] of two columns of the X tile EXTENDED by the constant columns
+// x[D] = 1 and x[D + 1] = 0 (they live in the tile's row padding): quadratic (i, j), linear (D, i), constant (D, D), padding
+// (D + 1, D + 1).  Packed (a << 8) | b.  The fragment generation is then branch-free and still exact (1 * x = x).
 __global__ void __launch_bounds__(256) feat_table_kernel(unsigned short* __restrict__ tab, const int D, const int P,
                                                          const int n) {
     const int p = blockIdx.x * 256 + threadIdx.x;
     if (p >= n) return;
     int kind, i, j;
     feat_decode(p, D, P, kind, i, j);
-    tab[p] = kind == 2 ? (unsigned short)((i << 8) | j) : (kind == 1 ? (unsigned short)(0xFE00 | i) : (kind == 0 ? 0xFFFF : 0xFFFE));
+    const int fa = kind == 2 ? i : (kind == 3 ? D + 1 : D);
+    const int fb = kind == 2 ? j : (kind == 1 ? i : (kind == 0 ? D : D + 1));
+    tab[p] = (unsigned short)((fa << 8) | fb);
 }
 
 // In the E-GEMM every 8-row block of Phi is consumed by exactly one warp, so Phi is never staged in shared memory: each
@@ -129,6 +133,7 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
         const int lrow = 8 * warp + g;
         const int eo0 = (2 * q) ^ fg, eo1 = (8 + 2 * q) ^ fg;
         const double* xr = xs + lrow * XP;                     // this thread's row of the X tile
+        for (int r = tid; r < LG_ETILE; r += 256) { xs[r * XP + D] = 1.0; xs[r * XP + D + 1] = 0.0; }   // constant columns
         double sprod = 1.0;
         int64_t cc = 0;
         int it = 0;
@@ -156,12 +161,7 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
                         const unsigned int code = tb[16 * w + 4 * h];
-                        const int fi = code >> 8, fj = code & 0xFF;
-                        double v;
-                        if (fi < 0xFE) v = xr[fi] * xr[fj];
-                        else if (fi == 0xFE) v = xr[fj];
-                        else v = (fj == 0xFF) ? 1.0 : 0.0;
-                        af[w][h] = v;
+                        af[w][h] = xr[code >> 8] * xr[code & 0xFF];     // columns D, D + 1 of the tile hold 1 and 0
                     }
                 mbar_wait(&cfull[b], (uint32_t)((cc >> 1) & 1));
                 const double* eB = coefS + b * 8 * KB * LG_CW + g * LG_CW;
@@ -291,9 +291,12 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
     const int64_t s_begin = ry * per, s_end = min(nsub, s_begin + per);
 
     // this thread's two features (logical order: B column g of block b is feature 128cx + 8b + g)
+    // as x[a] * x[b] with unconditional loads and selects for the constant factors (no branches in the GEMM loop)
     int kind0, i0, j0, kind1, i1, j1;
     feat_decode(LG_MCW * cx + 8 * (2 * warp) + g, D, P, kind0, i0, j0);
     feat_decode(LG_MCW * cx + 8 * (2 * warp + 1) + g, D, P, kind1, i1, j1);
+    const bool ua0 = kind0 == 1 || kind0 == 2, ub0 = kind0 == 2, ua1 = kind1 == 1 || kind1 == 2, ub1 = kind1 == 2;
+    const double cb0 = kind0 == 3 ? 0.0 : 1.0, cb1 = kind1 == 3 ? 0.0 : 1.0;
     for (int e = tid; e < LG_MSUB * RP; e += LG_THREADS) rS[e] = 0.0;     // padded components stay zero
 
     double macc[2][KB][2];
@@ -349,7 +352,8 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
                 ra[0] = mR[ks * 4 * RP];
             }
             const double* xr = xt + (4 * ks + q) * D;
-            const double b0 = feat_value(kind0, i0, j0, xr), b1 = feat_value(kind1, i1, j1, xr);
+            const double xa0 = xr[i0], xb0 = xr[j0], xa1 = xr[i1], xb1 = xr[j1];
+            const double b0 = (ua0 ? xa0 : 1.0) * (ub0 ? xb0 : cb0), b1 = (ua1 ? xa1 : 1.0) * (ub1 ? xb1 : cb1);
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
                 dmma(macc[0][kb][0], macc[0][kb][1], ra[kb], b0);
