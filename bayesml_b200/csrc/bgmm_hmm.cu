@@ -82,6 +82,7 @@ struct ScanBufs {
     const double* rhohat;  // [n][K] exp(ln rho - row max): what the recursions multiply by (rho_i / c_i = rhohat_i / chat_i)
     const double* rowmax;  // [n]    max_k ln rho
     double* chat;          // [n]    c_i exp(-row max): the normaliser in rhohat units
+    double* ichat;         // [n]    1 / chat_i (hmm_cs_kernel), what the backward kernels multiply by
     double* alpha;         // [n][K]
     double* gamma;         // [n][K]
     double* cs;            // [n]
@@ -137,7 +138,6 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
     if (MODE == 1 && hmm_window(st, L, hst, H, sp) > 0) return;
     const double* at = current_at(st, L, hst, H);
     const double* __restrict__ rhohat = B.rhohat;
-    const double* __restrict__ rowmax = B.rowmax;
     const int64_t item = ((int64_t)blockIdx.x * HW + warp) * G + grp;
     const int64_t nitems = MODE == 1 ? (int64_t)(sp.nch - 1) * K : sp.nch;
     const int c = MODE == 1 ? (int)(item / K) : (int)item;
@@ -152,14 +152,12 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
     double slog = 0.0;
     // emission values are fetched two steps ahead of the dependent chain (which runs through `a` only)
     auto RH = [&](int64_t i, int s) { return (mine && s < sp.L && i < sp.n) ? rhohat[i * K + kk] : 0.0; };
-    auto MX = [&](int64_t i, int s) { return (!BASIS && live && s < sp.L && i < sp.n) ? rowmax[i] : 0.0; };
     double rho_c = RH(i0, 0), rho_n = RH(i0 + 1, 1);
-    double mx_c = MX(i0, 0), mx_n = MX(i0 + 1, 1);
     for (int s = 0; s < sp.L; ++s) {
         const int64_t i = i0 + s;
-        const double rho = rho_c, mx = mx_c;
-        rho_c = rho_n; mx_c = mx_n;
-        rho_n = RH(i + 2, s + 2); mx_n = MX(i + 2, s + 2);
+        const double rho = rho_c;
+        rho_c = rho_n;
+        rho_n = RH(i + 2, s + 2);
         double* line = lines[warp][s & 1];
         publish<KP>(line, lane, a);
         const double dot = group_dot<KP>(line, grp * KP, acol);
@@ -184,21 +182,38 @@ __global__ void __launch_bounds__(HT) hmm_fwd_kernel(const ScanPlan sp, const do
                 a = u;
             }
         } else {
-            const double sum = group_sum<KP>(u);                   // chat_i
+            const double sum = group_sum<KP>(u);                   // chat_i; c_i, 1 / chat_i and sum ln c_i: hmm_cs_kernel
             if (live && i < sp.n) {
                 a = u / sum;
-                slog += log(sum) + mx;                             // ln c_i
                 if (mine) B.alpha[i * K + kk] = a;
-                if (kk == 0) { B.chat[i] = sum; B.cs[i] = sum * exp(mx); }
+                if (kk == 0) B.chat[i] = sum;
             }
         }
     }
     if (MODE == 1) {
         if (mine) B.tf[((int64_t)c * K + j0) * K + kk] = a;
         if (live && kk == 0) B.ls[(int64_t)c * K + j0] = slog;
-    } else if (live && kk == 0) {
-        B.plc[c] = slog;
     }
+}
+
+// c_i = chat_i e^{max_i} (:1001-1004), 1 / chat_i and the chunk's sum of ln c_i (for -E ln q(z), :909): element-wise, kept
+// out of the sequential recursions.  One CTA per chunk, fixed-order block sum.
+__global__ void __launch_bounds__(128) hmm_cs_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                     const int force, const ScanBufs B) {
+    __shared__ double red[40];
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    const int c = blockIdx.x;
+    const int64_t i0 = (int64_t)c * sp.L, i1 = i0 + sp.L < sp.n ? i0 + sp.L : sp.n;
+    double acc = 0.0;
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += 128) {
+        const double ch = B.chat[i], mx = B.rowmax[i];
+        B.cs[i] = ch * exp(mx);
+        B.ichat[i] = 1.0 / ch;
+        acc += log(ch) + mx;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) B.plc[c] = acc;
 }
 
 // Phase B (both directions): the sequential sweep over the chunk transfer matrices, one CTA.
@@ -380,7 +395,7 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     const double* __restrict__ lnrho = B.lnrho;
     const double* __restrict__ rhohat = B.rhohat;
     const double* __restrict__ alpha = B.alpha;
-    const double* __restrict__ cs = B.chat;                  // rho_i / c_i = rhohat_i / chat_i
+    const double* __restrict__ cs = B.ichat;                 // rho_i / c_i = rhohat_i * (1 / chat_i)
     const int64_t item = ((int64_t)blockIdx.x * HW + warp) * G + grp;
     const int64_t nitems = MODE == 1 ? (int64_t)(sp.nch - 1) * K : sp.nch;
     const int c = MODE == 1 ? 1 + (int)(item / K) : (int)item;          // basis runs: chunks 1 .. nch-1
@@ -403,14 +418,14 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     auto RH = [&](int64_t i) { return (mine && i >= i0) ? rhohat[i * K + kk] : 0.0; };
     auto CI = [&](int64_t i) { return (live && i >= i0) ? cs[i] : 1.0; };
     auto AL = [&](int64_t i) { return (!BASIS && mine && i >= 0) ? alpha[i * K + kk] : 0.0; };
-    double lr_c = LR(i1), rho_c = RH(i1), inv_c = 1.0 / CI(i1);
+    double lr_c = LR(i1), rho_c = RH(i1), inv_c = CI(i1);
     double lr_n = LR(i1 - 1), rho_n = RH(i1 - 1), ci_n = CI(i1 - 1);
     double al_c = AL(i1), al_p = AL(i1 - 1), al_pp = AL(i1 - 2);
     for (int s = 0; s < sp.L; ++s) {
         const int64_t i = i1 - s;
         const bool in = live && i >= i0, on = mine && i >= i0;
         const double lr = lr_c, rho = rho_c, inv = inv_c, al = al_c, aprev = al_p;
-        lr_c = lr_n; rho_c = rho_n; inv_c = 1.0 / ci_n;
+        lr_c = lr_n; rho_c = rho_n; inv_c = ci_n;
         lr_n = LR(i - 2); rho_n = RH(i - 2); ci_n = CI(i - 2);
         al_c = al_p; al_p = al_pp; al_pp = AL(i - 3);
         const double rb = on ? rho * b : 0.0;                          // rho_i[k] beta_i[k]
@@ -485,7 +500,7 @@ __global__ void __launch_bounds__(HT) hmm_window_kernel(const ScanPlan sp, const
     const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, kk = lane % KP, grp = lane / KP;
     const double* at = current_at(st, L, hst, H);
     const double* __restrict__ rhohat = B.rhohat;
-    const double* __restrict__ chat = B.chat;
+    const double* __restrict__ chat = B.ichat;             // 1 / chat_i
     const int c = (int)(((int64_t)blockIdx.x * HW + warp) * G + grp);
     const bool live = c < sp.nch, mine = live && kk < K;
     double av[KP];                                          // FWD: column kk of A~;  !FWD: row kk
@@ -543,7 +558,7 @@ __global__ void __launch_bounds__(HT) hmm_window_kernel(const ScanPlan sp, const
         for (int blk = 0; blk < WB; ++blk) {
             const int64_t ib = top - 8 * (int64_t)blk;
 #pragma unroll
-            for (int t = 0; t < 8; ++t) { rc[t] = rn[t]; ic[t] = 1.0 / cn[t]; }
+            for (int t = 0; t < 8; ++t) { rc[t] = rn[t]; ic[t] = cn[t]; }
             if (blk + 1 < WB) {
 #pragma unroll
                 for (int t = 0; t < 8; ++t) { rn[t] = RH(ib - 8 - t); cn[t] = CI(ib - 8 - t); }
@@ -596,7 +611,7 @@ static int64_t scan_ws_doubles(int K, int64_t n) {
     const int64_t KK = (int64_t)K * K;
     // transfer matrices + log scales + boundary vectors + S partials + the two scalar partial arrays
     // + rhohat [n][K], row max [n], chat [n]
-    return nch * KK + nch * K + nch * K + nch * KK + 2 * nch + 64 + n * K + 2 * n;
+    return nch * KK + nch * K + nch * K + nch * KK + 2 * nch + 64 + n * K + 3 * n;
 }
 
 template <int KP>
@@ -619,6 +634,7 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
     hmm_seq_kernel<KP, true><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, B);
     hmm_window_kernel<KP, true><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_fwd_kernel<KP, 0><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    hmm_cs_kernel<<<sp.nch, 128, 0, stream>>>(sp, st, L, force, B);
     if (sp.nch > 1) hmm_bwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_seq_kernel<KP, false><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, B);
     hmm_window_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
@@ -812,6 +828,7 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
         B.rhohat = rh; B.chat = rh + n * K;
         double* rmx = B.chat + n;
         B.rowmax = rmx;
+        B.ichat = rmx + n;
         a.rhohat_out = rh; a.rowmax_out = rmx;
         a.lnrho_only = 1;
         rc = launch_pass_large_part(a, K, D, BGMM_F64, 1, s);

@@ -464,7 +464,7 @@ class HMMEngine(VBEngine):
         # emission (3) + per direction {basis runs (only with > 1 chunk), sweep, window, chunk kernel} + reduction +
         # statistics (2); of the three boundary-vector kernels the device runs one branch, the others return at once
         chunk = (max(32, -(-self.n_local // 4096)) + 7) // 8 * 8
-        self.kernel_launches += (10 + (4 if self.n_local > chunk else 2)) if mode == _lib.HMM_FULL else 2
+        self.kernel_launches += (11 + (4 if self.n_local > chunk else 2)) if mode == _lib.HMM_FULL else 2
 
     def begin(self, max_itr, tol, init=None):
         """Post-init E-step + ELBO (:1092-1101) and the first M-step.  `init` = (gamma [n][K], ms [K][K]) for the
