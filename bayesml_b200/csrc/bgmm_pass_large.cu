@@ -137,13 +137,40 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
         double sprod = 1.0;
         int64_t cc = 0;
         int it = 0;
+        // D <= 32: a 64-row tile is <= 8 elements per thread, so the NEXT tile is fetched into registers before this
+        // tile's GEMM and only stored to shared memory at the top of the next iteration (the global round trip, otherwise
+        // exposed once per tile, hides behind the GEMM; at small D it is most of the kernel's time)
+        const bool reg_prefetch = D <= 32;
+        double pre[8];
+        auto fetch_tile = [&](int64_t tt) {
+            const int64_t r0 = tt * LG_ETILE;
+            const int64_t lim = tt < ntiles ? min((int64_t)LG_ETILE, a.n - r0) * D : 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int e = tid + 256 * j;
+                pre[j] = e < lim ? x[r0 * D + e] : 0.0;
+            }
+        };
+        if (reg_prefetch) fetch_tile(blockIdx.x);
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int64_t row0 = t * LG_ETILE;
             const int rows = (int)min((int64_t)LG_ETILE, a.n - row0);
             asm volatile("bar.sync 1, 256;" ::: "memory");     // every GEMM warp is done with the previous X tile
-            for (int e = tid; e < LG_ETILE * D; e += 256) {
-                const int r = e / D, c = e - r * D;
-                xs[r * XP + c] = (e < rows * D) ? x[row0 * D + e] : 0.0;
+            if (reg_prefetch) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int e = tid + 256 * j;
+                    if (e < LG_ETILE * D) {
+                        const int r = e / D, c = e - r * D;
+                        xs[r * XP + c] = pre[j];
+                    }
+                }
+                fetch_tile(t + gridDim.x);
+            } else {
+                for (int e = tid; e < LG_ETILE * D; e += 256) {
+                    const int r = e / D, c = e - r * D;
+                    xs[r * XP + c] = (e < rows * D) ? x[row0 * D + e] : 0.0;
+                }
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             double acc[2][KB][2];
