@@ -19,6 +19,7 @@
 // of KP = 2^ceil(log2 K) lanes owns one chunk (32 / KP chunks per warp), state vectors are exchanged through a per-warp
 // shared-memory line (one STS + K/2 broadcast LDS.128 per step).  All sums are in a fixed order (deterministic).
 #include "bgmm_common.cuh"
+#include "bgmm_mma.cuh"
 #include <math.h>
 #include <stdlib.h>
 
@@ -644,6 +645,106 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Emission pass for small D (<= 8): `_calc_rho` :988-996 as ln rho[n][k] = coef_k . phi(x'_n), one thread per element.
+// The tiled large-regime kernel is tile-latency bound at these sizes (a 64-row tile is a few KB); here the coefficient
+// rows are broadcast from shared memory, phi(x) (P = 1 + D + D(D+1)/2 <= 45 values) lives in registers and the kernel
+// streams x once and writes ln rho, rhohat = exp(ln rho - row max) and the row max: HBM bound.
+template <int D>
+__global__ void __launch_bounds__(256, 2) hmm_emit_small_kernel(const double* __restrict__ x, const int64_t n, const int K,
+                                                                const double* __restrict__ st, const Layout L,
+                                                                const int force, double* __restrict__ lnrho,
+                                                                double* __restrict__ rhohat, double* __restrict__ rowmax) {
+    constexpr int P = 1 + D + D * (D + 1) / 2;
+    constexpr int PP = (P + 1) & ~1;                        // even pitch: rows of cf stay 16-byte aligned
+    __shared__ __align__(16) double cf[32 * PP];
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    const double* __restrict__ coef = st + L.params[ctrl[BGMM_CTRL_CUR]] + L.p_coef;
+    for (int e = threadIdx.x; e < K * PP; e += 256) {
+        const int k = e / PP, p = e - k * PP;
+        cf[e] = p < P ? coef[(int64_t)k * L.pitch + p] : 0.0;
+    }
+    __syncthreads();
+    // a warp owns 32 consecutive elements: its [32][K] block of ln rho / rhohat is contiguous in memory, so the values are
+    // staged in shared memory (odd pitch) and written out with consecutive lanes on consecutive addresses
+    extern __shared__ __align__(16) double stage_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, KS = K | 1;
+    double* stg = stage_raw + (size_t)warp * (32 * KS + 32);
+    double* mxs = stg + 32 * KS;
+    for (int64_t base = (int64_t)blockIdx.x * 256 + warp * 32; base < n; base += (int64_t)gridDim.x * 256) {
+        const int64_t row = base + lane;
+        const bool valid = row < n;
+        double phi[PP];
+        phi[0] = 1.0;
+        if (PP > P) phi[PP - 1] = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) phi[1 + i] = valid ? x[row * D + i] : 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) phi[1 + D + i * (i + 1) / 2 + j] = phi[1 + i] * phi[1 + j];
+        double mx = -INFINITY;
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {                       // the component loop stays rolled: phi is the register budget
+            const double2* c2 = reinterpret_cast<const double2*>(cf + k * PP);
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int p = 0; p < PP / 2; ++p) {
+                const double2 c = c2[p];
+                a0 = fma(c.x, phi[2 * p], a0);
+                a1 = fma(c.y, phi[2 * p + 1], a1);
+            }
+            const double lr = a0 + a1;
+            stg[lane * KS + k] = lr;
+            mx = fmax(mx, lr);
+        }
+        mxs[lane] = mx;
+        if (rowmax != nullptr && valid) rowmax[row] = mx;
+        __syncwarp();
+        const int64_t lim = (n - base < 32 ? n - base : 32) * K;
+        for (int e = lane; e < lim; e += 32) {
+            const int r = e / K, k = e - r * K;
+            const double lr = stg[r * KS + k];
+            lnrho[base * K + e] = lr;
+            if (rhohat != nullptr) rhohat[base * K + e] = exp_nonpos(lr - mxs[r]);
+        }
+        __syncwarp();
+    }
+}
+
+template <int D>
+static int launch_emit_small_d(const void* x, int64_t n, int K, const double* st, const Layout& L, int force, double* lnrho,
+                               double* rhohat, double* rowmax, cudaStream_t s) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t g = (n + 255) / 256;
+    if (g > (int64_t)sms * 8) g = (int64_t)sms * 8;
+    const size_t smem = (size_t)8 * (32 * (K | 1) + 32) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(hmm_emit_small_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(hmm_emit_small)");
+    hmm_emit_small_kernel<D><<<(unsigned)g, 256, smem, s>>>(static_cast<const double*>(x), n, K, st, L, force, lnrho, rhohat,
+                                                           rowmax);
+    return check_cuda(cudaGetLastError(), "hmm_emit_small launch");
+}
+
+// D <= 8 and K <= 32: the thread-per-element kernel; otherwise -1 (the caller uses the large-regime E kernel)
+static int launch_emit_small(const void* x, int64_t n, int K, int D, const double* st, const Layout& L, int force,
+                             double* lnrho, double* rhohat, double* rowmax, cudaStream_t s) {
+    if (K > 32 || getenv("BGMM_HMM_NO_SMALL_EMIT") != nullptr) return -1;
+    switch (D) {
+        case 1: return launch_emit_small_d<1>(x, n, K, st, L, force, lnrho, rhohat, rowmax, s);
+        case 2: return launch_emit_small_d<2>(x, n, K, st, L, force, lnrho, rhohat, rowmax, s);
+        case 3: return launch_emit_small_d<3>(x, n, K, st, L, force, lnrho, rhohat, rowmax, s);
+        case 4: return launch_emit_small_d<4>(x, n, K, st, L, force, lnrho, rhohat, rowmax, s);
+        case 5: return launch_emit_small_d<5>(x, n, K, st, L, force, lnrho, rhohat, rowmax, s);
+        case 6: return launch_emit_small_d<6>(x, n, K, st, L, force, lnrho, rhohat, rowmax, s);
+        case 7: return launch_emit_small_d<7>(x, n, K, st, L, force, lnrho, rhohat, rowmax, s);
+        case 8: return launch_emit_small_d<8>(x, n, K, st, L, force, lnrho, rhohat, rowmax, s);
+        default: return -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Viterbi (_hiddenmarkovnormal.py:1466-1480): omega_0 = ln rho_0 + ln pi~;  omega_i[k] = ln rho_i[k] + max_j (ln a~_jk +
 // omega_{i-1}[j]), phi_i[k] = argmax_j (first maximum, as np.argmax); then the path is traced back from argmax omega_{N-1}.
 // The recursion is sequential in i and is kept in the reference's operation order (same additions, same comparison order),
@@ -801,6 +902,9 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
     }
     if (mode == BGMM_HMM_EMISSION_ONLY) {                        // ln rho of x under the current parameter set, nothing else
         if (lnrho == nullptr) { set_error("bgmm_hmm_pass: lnrho is NULL"); return BGMM_EINVAL; }
+        const int rs = launch_emit_small(x, n, K, D, state, make_layout(K, D, 1), force, lnrho, nullptr, nullptr,
+                                         (cudaStream_t)stream);
+        if (rs != -1) return rs;
         PassArgs ea{x, n, state, workspace, nullptr, lnrho, nullptr, nullptr, force, 0};
         ea.lnrho_only = 1;
         return launch_pass_large_part(ea, K, D, BGMM_F64, 1, (cudaStream_t)stream);
@@ -830,8 +934,11 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
         B.rowmax = rmx;
         B.ichat = rmx + n;
         a.rhohat_out = rh; a.rowmax_out = rmx;
-        a.lnrho_only = 1;
-        rc = launch_pass_large_part(a, K, D, BGMM_F64, 1, s);
+        rc = launch_emit_small(x, n, K, D, state, L, force, lnrho, rh, rmx, s);
+        if (rc == -1) {
+            a.lnrho_only = 1;
+            rc = launch_pass_large_part(a, K, D, BGMM_F64, 1, s);
+        }
         if (rc) return rc;
         if (K <= 2) rc = launch_scan<2>(sp, state, L, hst, H, force, B, s);
         else if (K <= 4) rc = launch_scan<4>(sp, state, L, hst, H, force, B, s);
