@@ -151,3 +151,21 @@ def test_no_cpu_fallback_without_cuda():
     m = gaussianmixture.LearnModel(3, 2, seed=0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.update_posterior(np.random.default_rng(0).normal(size=(50, 2)))
+
+
+def test_hmm_entry_points_reject_bad_arguments_without_touching_the_gpu(lib_built):
+    """The hidden-Markov C-ABI entry points validate on the host first (no CUDA call is made for these inputs)."""
+    lib = _lib.load()
+    off = (ctypes.c_int64 * len(_lib.HMM_OFF_NAMES))()
+    assert lib.bgmm_hmm_layout(0, off) == -1 and b"bgmm_hmm_layout" in lib.bgmm_last_error()
+    assert lib.bgmm_hmm_layout(5, off) == 0
+    h = dict(zip(_lib.HMM_OFF_NAMES, off))
+    assert h["zeta0"] == 0 and h["set1"] - h["set0"] == 3 * 32 + 8 and h["total"] > h["vlx"] > h["sc"] > h["g0"] > h["ms"]
+    assert lib.bgmm_hmm_supported(32, 128) == 1 and lib.bgmm_hmm_supported(33, 4) == 0 and lib.bgmm_hmm_supported(4, 129) == 0
+    assert lib.bgmm_hmm_scan_workspace_doubles(40, 1000) == 0 and lib.bgmm_hmm_scan_workspace_doubles(8, 100000) > 100000 * 8
+    assert lib.bgmm_hmm_small(3, 2, None, None, 0, 1, 0.0, 2, None) == -1
+    assert lib.bgmm_hmm_pass(None, 10, 40, 2, None, None, None, None, None, None, None, None, None, 0, 0, None) == -3
+    assert b"unsupported shape" in lib.bgmm_last_error()
+    assert lib.bgmm_hmm_pass(None, 10, 4, 2, None, None, None, None, None, None, None, None, None, 0, 0, None) == -1
+    assert lib.bgmm_hmm_viterbi(0, 4, None, None, None, None, None, None, None) == -1
+    assert lib.bgmm_hmm_viterbi(10, 40, None, None, None, None, None, None, None) == -1
