@@ -9,15 +9,15 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libbgmm.so")
 
 # constants mirrored from include/bgmm.h (checked against bgmm_abi_version at load time)
-ABI_VERSION = 2
+ABI_VERSION = 3
 F64, F32 = 0, 1
-PASS_AUTO, PASS_SIMPLE, PASS_DMMA, PASS_F32, PASS_LARGE = 0, 1, 2, 3, 4
+PASS_AUTO, PASS_SIMPLE, PASS_DMMA, PASS_F32, PASS_LARGE, PASS_DIRECT = 0, 1, 2, 3, 4, 5
 SMALL_FEATURES, SMALL_ITERATE, SMALL_STATS = 0, 1, 2
 
 OFF_NAMES = ("center", "alpha0", "kappa0", "nu0", "m0", "w0inv", "lnb0", "lnc0", "params0", "params1", "stats",
-             "ns", "xbar", "smats", "vlk", "vlterms", "vlhist", "ctrl", "total", "stats_len", "params_len", "pitch")
-POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb", "coef")
-CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR, CTRL_SEQ = range(8)
+             "ns", "xbar", "smats", "vlk", "vlterms", "vlhist", "ctrl", "total", "stats_len", "params_len", "pitch", "shift")
+POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb", "coef", "acst")
+CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR, CTRL_SEQ, CTRL_ROBUST = range(9)
 MAX_RANKS = 16
 N_CTRL = 16
 HMM_OFF_NAMES = ("zeta0", "lncz0", "set0", "set1", "set_zeta", "set_lna", "set_at", "set_misc", "ms", "g0", "sc", "vlx",
@@ -42,6 +42,10 @@ def load():
     lib.bgmm_abi_version.argtypes = []
     lib.bgmm_last_error.restype = ctypes.c_char_p
     lib.bgmm_last_error.argtypes = []
+    lib.bgmm_robust_threshold.restype = f64
+    lib.bgmm_robust_threshold.argtypes = []
+    lib.bgmm_set_robust_threshold.restype = f64
+    lib.bgmm_set_robust_threshold.argtypes = [f64]
     lib.bgmm_layout.restype = i32
     lib.bgmm_layout.argtypes = [i32, i32, i32, ctypes.POINTER(i64), ctypes.POINTER(i64)]
     lib.bgmm_workspace_doubles.restype = i64

@@ -1,11 +1,15 @@
 // C-ABI glue of libbgmm: argument checks, error reporting, layout queries, data preparation, dispatch.
 #include "bgmm_common.cuh"
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 
 namespace bgmm {
 
 static thread_local char g_err[512] = "";
+static double g_robust_threshold = 2.0e4;
+
+double robust_threshold() { return g_robust_threshold; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -20,7 +24,7 @@ int check_cuda(cudaError_t e, const char* what) {
     return BGMM_ECUDA;
 }
 
-int launch_pass_simple(const PassArgs& a, int K, int D, int dtype, int, cudaStream_t stream);
+int launch_pass_simple(const PassArgs& a, int K, int D, int dtype, int direct, cudaStream_t stream);
 int simple_grid_cap(int K, int D);
 bool dmma_supported(int K, int D, int dtype);
 int launch_pass_dmma(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream);
@@ -74,6 +78,12 @@ static int64_t colsum_stride(int D) {
 using namespace bgmm;
 
 extern "C" int bgmm_abi_version(void) { return BGMM_ABI_VERSION; }
+extern "C" double bgmm_robust_threshold(void) { return g_robust_threshold; }
+extern "C" double bgmm_set_robust_threshold(double t) {
+    const double old = g_robust_threshold;
+    g_robust_threshold = t;
+    return old;
+}
 extern "C" const char* bgmm_last_error(void) { return g_err; }
 
 extern "C" int bgmm_layout(int K, int D, int hist_len, int64_t* off, int64_t* poff) {
@@ -88,10 +98,11 @@ extern "C" int bgmm_layout(int K, int D, int hist_len, int64_t* off, int64_t* po
     off[BGMM_OFF_STATS] = L.stats; off[BGMM_OFF_NS] = L.ns; off[BGMM_OFF_XBAR] = L.xbar; off[BGMM_OFF_SMATS] = L.smats;
     off[BGMM_OFF_VLK] = L.vlk; off[BGMM_OFF_VLTERMS] = L.vlterms; off[BGMM_OFF_VLHIST] = L.vlhist;
     off[BGMM_OFF_CTRL] = L.ctrl; off[BGMM_OFF_TOTAL] = L.total; off[BGMM_OFF_STATS_LEN] = L.stats_len;
-    off[BGMM_OFF_PARAMS_LEN] = L.params_len; off[BGMM_OFF_PITCH] = L.pitch;
+    off[BGMM_OFF_PARAMS_LEN] = L.params_len; off[BGMM_OFF_PITCH] = L.pitch; off[BGMM_OFF_SHIFT] = L.shift;
     poff[BGMM_P_ALPHA] = L.p_alpha; poff[BGMM_P_KAPPA] = L.p_kappa; poff[BGMM_P_NU] = L.p_nu; poff[BGMM_P_M] = L.p_m;
     poff[BGMM_P_WINV] = L.p_winv; poff[BGMM_P_W] = L.p_w; poff[BGMM_P_ELNPI] = L.p_elnpi;
     poff[BGMM_P_ELNDET] = L.p_elndet; poff[BGMM_P_LNB] = L.p_lnb; poff[BGMM_P_COEF] = L.p_coef;
+    poff[BGMM_P_ACST] = L.p_acst;
     return BGMM_OK;
 }
 
@@ -153,12 +164,12 @@ extern "C" int bgmm_pass_supported(int K, int D, int dtype, int variant) {
     if (variant == BGMM_PASS_DMMA) return dmma_supported(K, D, dtype) ? 1 : 0;
     if (variant == BGMM_PASS_F32) return f32_supported(K, D, dtype) ? 1 : 0;
     if (variant == BGMM_PASS_LARGE) return large_supported(K, D, dtype) ? 1 : 0;
-    return variant == BGMM_PASS_SIMPLE || variant == BGMM_PASS_AUTO;
+    return variant == BGMM_PASS_SIMPLE || variant == BGMM_PASS_AUTO || variant == BGMM_PASS_DIRECT;
 }
 
 extern "C" int bgmm_pass_resolve(int K, int D, int dtype, int variant, int has_r_in) {
+    if (has_r_in) return variant == BGMM_PASS_DIRECT ? BGMM_PASS_DIRECT : BGMM_PASS_SIMPLE;
     if (variant != BGMM_PASS_AUTO) return variant;
-    if (has_r_in) return BGMM_PASS_SIMPLE;
     if (dmma_supported(K, D, dtype)) return BGMM_PASS_DMMA;
     if (large_supported(K, D, dtype)) return BGMM_PASS_LARGE;
     if (f32_supported(K, D, dtype)) return BGMM_PASS_F32;
@@ -176,24 +187,41 @@ extern "C" int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, doub
     PassArgs a{x, n, state, workspace, r_out, lnrho_out, argmax_out, r_in, force, accumulate};
     cudaStream_t s = (cudaStream_t)stream;
     variant = bgmm_pass_resolve(K, D, dtype, variant, r_in != nullptr);
+    if (r_in != nullptr) {                                     // statistics of given responsibilities: no E-step; moments
+        if (variant != BGMM_PASS_SIMPLE && variant != BGMM_PASS_DIRECT) {   // about the centre (SIMPLE) or state.SHIFT (DIRECT)
+            set_error("bgmm_pass: variant %d does not take r_in", variant);
+            return BGMM_ENOSUP;
+        }
+        a.ignore_robust = 1;
+        return launch_pass_simple(a, K, D, dtype, variant == BGMM_PASS_DIRECT ? 1 : 0, s);
+    }
+    if (variant == BGMM_PASS_DIRECT) {                         // forced: whatever ctrl.robust says
+        a.ignore_robust = 1;
+        return launch_pass_simple(a, K, D, dtype, 1, s);
+    }
+    int rc;
     if (variant == BGMM_PASS_LARGE) {
-        if (r_in != nullptr) { set_error("bgmm_pass: LARGE variant does not take r_in"); return BGMM_ENOSUP; }
-        return launch_pass_large(a, K, D, dtype, s);
-    }
-    if (variant == BGMM_PASS_F32) {
-        if (r_in != nullptr || !f32_supported(K, D, dtype)) {
-            set_error("bgmm_pass: F32 variant does not support K=%d D=%d dtype=%d r_in=%p", K, D, dtype, (const void*)r_in);
+        rc = launch_pass_large(a, K, D, dtype, s);
+    } else if (variant == BGMM_PASS_F32) {
+        if (!f32_supported(K, D, dtype)) {
+            set_error("bgmm_pass: F32 variant does not support K=%d D=%d dtype=%d", K, D, dtype);
             return BGMM_ENOSUP;
         }
-        return launch_pass_f32(a, K, D, dtype, s);
-    }
-    if (variant == BGMM_PASS_DMMA) {
-        if (r_in != nullptr || !dmma_supported(K, D, dtype)) {
-            set_error("bgmm_pass: DMMA variant does not support K=%d D=%d dtype=%d r_in=%p", K, D, dtype, (const void*)r_in);
+        rc = launch_pass_f32(a, K, D, dtype, s);
+    } else if (variant == BGMM_PASS_DMMA) {
+        if (!dmma_supported(K, D, dtype)) {
+            set_error("bgmm_pass: DMMA variant does not support K=%d D=%d dtype=%d", K, D, dtype);
             return BGMM_ENOSUP;
         }
-        return launch_pass_dmma(a, K, D, dtype, s);
+        rc = launch_pass_dmma(a, K, D, dtype, s);
+    } else if (variant == BGMM_PASS_SIMPLE) {
+        rc = launch_pass_simple(a, K, D, dtype, 0, s);
+    } else {
+        set_error("bgmm_pass: unknown variant %d", variant);
+        return BGMM_EINVAL;
     }
-    if (variant != BGMM_PASS_SIMPLE) { set_error("bgmm_pass: unknown variant %d", variant); return BGMM_EINVAL; }
-    return launch_pass_simple(a, K, D, dtype, 0, s);
+    if (rc) return rc;
+    // conditioning guard: the kernels above returned at once if ctrl.robust is set; this one returns at once if it is not
+    if (g_robust_threshold < INFINITY) rc = launch_pass_simple(a, K, D, dtype, 1, s);
+    return rc;
 }

@@ -13,9 +13,9 @@ __host__ __device__ inline int feat_pitch(int D) { return (feat_count(D) + 7) & 
 struct Layout {
     int K, D, P, pitch, hist_len;
     int64_t center, alpha0, kappa0, nu0, m0, w0inv, lnb0, lnc0, params[2], stats, ns, xbar, smats, vlk, vlterms,
-        vlhist, ctrl, total, stats_len, params_len;
+        vlhist, ctrl, total, stats_len, params_len, shift;
     // offsets inside one parameter set
-    int64_t p_alpha, p_kappa, p_nu, p_m, p_winv, p_w, p_elnpi, p_elndet, p_lnb, p_coef;
+    int64_t p_alpha, p_kappa, p_nu, p_m, p_winv, p_w, p_elnpi, p_elndet, p_lnb, p_coef, p_acst;
 };
 
 __host__ __device__ inline int64_t align8(int64_t v) { return (v + 7) & ~int64_t(7); }
@@ -35,6 +35,7 @@ __host__ __device__ inline Layout make_layout(int K, int D, int hist_len) {
     L.p_elndet = o; o += align8(K);
     L.p_lnb = o;    o += align8(K);
     L.p_coef = o;   o += (int64_t)K * L.pitch;
+    L.p_acst = o;   o += align8(K);
     L.params_len = o;
     o = 0;
     L.center = o;  o += align8(D);
@@ -55,6 +56,7 @@ __host__ __device__ inline Layout make_layout(int K, int D, int hist_len) {
     L.vlk = o;     o += (int64_t)K * 8;
     L.vlterms = o; o += 8;
     L.ctrl = o;    o += BGMM_N_CTRL / 2;  // int32[16]
+    L.shift = o;   o += align8(KD);
     L.vlhist = o;  o += align8(hist_len); // variable length: keep it LAST so no other offset depends on hist_len
     L.total = o;
     return L;
@@ -114,6 +116,9 @@ struct PassArgs {
     int32_t* argmax_out;
     const double* r_in;
     int force, accumulate;
+    // conditioning guard (ctrl.ROBUST): 0 = feature-map kernel, returns at once when the flag is set (the DIRECT kernel
+    // launched behind it does the pass); 1 = ignore the flag (given responsibilities, hidden-Markov path, forced variant)
+    int ignore_robust = 0;
     int lnrho_only = 0;   // large-regime E kernel: write ln rho only (no softmax / r / entropy): the HMM emission pass
     double* rhohat_out = nullptr;   // with lnrho_only: exp(ln rho - row max) [n][K] and the row max [n] (scan inputs)
     double* rowmax_out = nullptr;
@@ -143,6 +148,15 @@ __host__ __device__ inline HmmLayout make_hmm_layout(int K) {
     H.total = o;
     return H;
 }
+
+// Entry test of every pass kernel: queued launches after convergence are no-ops (ctrl.done), and the feature-map kernels
+// stand down when bgmm_small has flagged the current parameter set as ill-conditioned (ctrl.robust): the DIRECT kernel
+// launched behind them does that pass.
+__device__ __forceinline__ bool pass_skip(const volatile int* ctrl, int force, int ignore_robust) {
+    return (!force && ctrl[BGMM_CTRL_DONE]) || (!ignore_robust && ctrl[BGMM_CTRL_ROBUST]);
+}
+
+double robust_threshold();
 
 // sum of `nparts` per-CTA partial statistics buffers (workspace) into state.STATS, fixed order (bgmm_pass_dmma.cu)
 void launch_reduce_partials(const PassArgs& a, const Layout& L, int nparts, cudaStream_t stream);

@@ -906,6 +906,7 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
                                          (cudaStream_t)stream);
         if (rs != -1) return rs;
         PassArgs ea{x, n, state, workspace, nullptr, lnrho, nullptr, nullptr, force, 0};
+        ea.ignore_robust = 1;                                    // the hidden-Markov path has no DIRECT kernel
         ea.lnrho_only = 1;
         return launch_pass_large_part(ea, K, D, BGMM_F64, 1, (cudaStream_t)stream);
     }
@@ -917,6 +918,7 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
     const Layout L = make_layout(K, D, 1);
     const HmmLayout H = make_hmm_layout(K);
     PassArgs a{x, n, state, workspace, nullptr, lnrho, nullptr, nullptr, force, 0};
+    a.ignore_robust = 1;
     int rc;
     if (mode == BGMM_HMM_FULL) {
         ScanPlan sp;

@@ -49,7 +49,7 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     const int wg = warp >> 2, wq = warp & 3;                  // warpgroup (0,1 consumers; 2 producer), warp in group
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
-    if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
+    if (pass_skip(ctrl, a.force, a.ignore_robust)) return;
     const double* __restrict__ coef_g = a.state + L.params[ctrl[BGMM_CTRL_CUR]] + L.p_coef;
     const double* __restrict__ x = static_cast<const double*>(a.x);
 
@@ -392,8 +392,8 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
                                                               const int64_t len, double* __restrict__ out,
                                                               const int64_t rows_slot, const double rows,
                                                               const int accumulate, const int* __restrict__ ctrl,
-                                                              const int force) {
-    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+                                                              const int force, const int ignore_robust) {
+    if (pass_skip(ctrl, force, ignore_robust)) return;
     __shared__ double slice[8][32];
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int64_t o = (int64_t)blockIdx.x * 32 + lane;
@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc += slice[i][lane];
     if (o == rows_slot) acc = rows;
+    if (o == rows_slot + 1) { out[o] = 0.0; return; }     // format marker: moments about the centre (feature-map kernels)
     out[o] = accumulate ? out[o] + acc : acc;
 }
 
@@ -424,7 +425,7 @@ void launch_reduce_partials(const PassArgs& a, const Layout& L, int nparts, cuda
     const int64_t len = L.stats_len;
     reduce_partials_kernel<<<(int)((len + 31) / 32), 256, 0, stream>>>(
         a.workspace, nparts, len, a.state + L.stats, (int64_t)L.K * L.pitch + 1, (double)a.n, a.accumulate,
-        reinterpret_cast<const int*>(a.state + L.ctrl), a.force);
+        reinterpret_cast<const int*>(a.state + L.ctrl), a.force, a.ignore_robust);
 }
 
 struct DmmaPlan {

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
     __shared__ int is_last;
     const int K = L.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
-    if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
+    if (pass_skip(ctrl, a.force, a.ignore_robust)) return;
     const double* Pc = a.state + L.params[ctrl[BGMM_CTRL_CUR]];
     const float* __restrict__ x = static_cast<const float*>(a.x);
 
@@ -262,6 +262,7 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
         double s0 = 0.0;
         for (int b = 0; b < (int)gridDim.x; ++b) s0 += __ldcg(&ws[(int64_t)b * len + o]);
         if (o == (int64_t)K * L.pitch + 1) s0 = (double)a.n;
+        if (o == (int64_t)K * L.pitch + 2) { out[o] = 0.0; continue; }      // format marker: moments about the centre
         out[o] = a.accumulate ? out[o] + s0 : s0;
     }
     if (tid == 0) ctrl[BGMM_CTRL_PASS_TICKET] = 0;

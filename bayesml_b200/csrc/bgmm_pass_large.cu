@@ -46,9 +46,10 @@ __device__ __forceinline__ double feat_value(int kind, int i, int j, const doubl
 // -1e300 padding applied) stored contiguously, so that the E kernel fetches a chunk with ONE TMA bulk copy.
 template <int KB>
 __global__ void __launch_bounds__(LG_THREADS) coef_pack_kernel(const double* __restrict__ st, const Layout L,
-                                                               double* __restrict__ packed, const int force) {
+                                                               double* __restrict__ packed, const int force,
+                                                               const int ignore_robust) {
     const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
-    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    if (pass_skip(ctrl, force, ignore_robust)) return;
     const double* __restrict__ coef_g = st + L.params[ctrl[BGMM_CTRL_CUR]] + L.p_coef;
     const int c = blockIdx.x;
     double* out = packed + (int64_t)c * 8 * KB * LG_CW;
@@ -89,7 +90,7 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
     const int K = L.K, D = L.D, P = L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
-    if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
+    if (pass_skip(ctrl, a.force, a.ignore_robust)) return;
     const double* __restrict__ x = static_cast<const double*>(a.x);
 
     const int nchunk = (P + LG_CW - 1) / LG_CW;
@@ -299,7 +300,7 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
     const int K = L.K, D = L.D, P = L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
-    if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
+    if (pass_skip(ctrl, a.force, a.ignore_robust)) return;
     const double* __restrict__ x = static_cast<const double*>(a.x);
     const double* __restrict__ rws = a.r_out;
 
@@ -463,7 +464,7 @@ static int launch_large_t(const PassArgs& a, const Layout& L, int which, cudaStr
                               4 * sizeof(uint64_t) + sizeof(unsigned short) * (size_t)nchunk_e * LG_CW + 128;
         cudaError_t e = cudaFuncSetAttribute(e_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(e_large)");
-        coef_pack_kernel<KB><<<nchunk_e, LG_THREADS, 0, stream>>>(a.state, L, packed, a.force);
+        coef_pack_kernel<KB><<<nchunk_e, LG_THREADS, 0, stream>>>(a.state, L, packed, a.force, a.ignore_robust);
         feat_table_kernel<<<(nchunk_e * LG_CW + 255) / 256, 256, 0, stream>>>(ftab, L.D, L.P, nchunk_e * LG_CW);
         e_large_kernel<KB><<<grid_e, LG_ETHREADS, smem_e, stream>>>(a, L, ews, packed, ftab);
     }

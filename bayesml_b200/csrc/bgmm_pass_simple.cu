@@ -6,6 +6,13 @@
 // Replaces `_update_q_z` :772-784, `_calc_n_x_bar_s` :725-732 and the `xlogy` term :704 of
 // /root/reference/bayesml/gaussianmixture/_gaussianmixture.py.  This is the correctness baseline on the GPU
 // and the path for shapes the tensor-pipe kernel does not cover; the fast path is bgmm_pass_dmma.cu.
+//
+// DIRECT instantiation (BGMM_PASS_DIRECT): the conditioning-safe form of the same sweep.  ln rho_nk is evaluated from the
+// explicit differences d = x' - m'_k  (a_k + sum_{i>=j} coefq_ij d_i d_j: the reference's (x - m_k)^T Lambda_k (x - m_k),
+// :775-781) and the statistics are the moments of (x' - shift_k) with shift_k ~ the component's own mean (state.SHIFT), i.e.
+// the reference's two-pass centred form (:730-732) up to a shift that bgmm_small removes.  No term grows with the distance
+// of a component from the global centre, at twice the arithmetic of the feature-map form.  It runs in place of the
+// requested variant whenever bgmm_small has raised ctrl.ROBUST for the current parameter set.
 #include "bgmm_common.cuh"
 #include <math.h>
 
@@ -14,13 +21,18 @@ namespace bgmm {
 constexpr int SIMPLE_THREADS = 128;
 
 
-template <typename T>
+template <typename T, bool DIRECT>
 __global__ void __launch_bounds__(SIMPLE_THREADS) pass_simple_kernel(const PassArgs a, const Layout L, const int tile) {
     extern __shared__ double sm[];
     const int K = L.K, D = L.D, P = L.P, tid = threadIdx.x;
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
     if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
-    const double* __restrict__ coef = a.state + L.params[ctrl[BGMM_CTRL_CUR]] + L.p_coef;
+    if (!a.ignore_robust && (ctrl[BGMM_CTRL_ROBUST] != 0) != DIRECT) return;   // the other form does this pass
+    const double* __restrict__ Pc = a.state + L.params[ctrl[BGMM_CTRL_CUR]];
+    const double* __restrict__ coef = Pc + L.p_coef;
+    const double* __restrict__ mvec = Pc + L.p_m;              // [K][D] (DIRECT)
+    const double* __restrict__ acst = Pc + L.p_acst;           // [K]    (DIRECT)
+    const double* __restrict__ shift = a.state + L.shift;      // [K][D] (DIRECT)
     const T* __restrict__ x = static_cast<const T*>(a.x);
 
     const int xp = D + 1;                 // padded row pitch: conflict-free per-thread rows
@@ -59,15 +71,27 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) pass_simple_kernel(const PassA
             double mx = -INFINITY;
             for (int k = 0; k < K; ++k) {
                 const double* c = coef + (int64_t)k * L.pitch;
-                double acc = c[0];
-                for (int i = 0; i < D; ++i) acc = fma(c[1 + i], xr[i], acc);
+                double acc;
                 int q = 1 + D;
-                for (int i = 0; i < D; ++i) {
-                    const double xi = xr[i];
-                    double row = 0.0;
-                    for (int j = 0; j <= i; ++j) row = fma(c[q + j], xr[j], row);
-                    acc = fma(row, xi, acc);
-                    q += i + 1;
+                if constexpr (DIRECT) {
+                    const double* mk = mvec + (int64_t)k * D;
+                    acc = acst[k];
+                    for (int i = 0; i < D; ++i) {
+                        double row = 0.0;
+                        for (int j = 0; j <= i; ++j) row = fma(c[q + j], xr[j] - mk[j], row);
+                        acc = fma(row, xr[i] - mk[i], acc);
+                        q += i + 1;
+                    }
+                } else {
+                    acc = c[0];
+                    for (int i = 0; i < D; ++i) acc = fma(c[1 + i], xr[i], acc);
+                    for (int i = 0; i < D; ++i) {
+                        const double xi = xr[i];
+                        double row = 0.0;
+                        for (int j = 0; j <= i; ++j) row = fma(c[q + j], xr[j], row);
+                        acc = fma(row, xi, acc);
+                        q += i + 1;
+                    }
                 }
                 rr[k] = acc;
                 mx = fmax(mx, acc);
@@ -100,19 +124,22 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) pass_simple_kernel(const PassA
         for (int o = tid; o < K * P; o += SIMPLE_THREADS) {
             const int k = o / P, p = o - k * P;
             double acc = 0.0;
+            const double* sk = shift + (int64_t)k * D;
             if (p == 0) {
                 for (int s = 0; s < rows; ++s) acc += rs[(size_t)s * K + k];
             } else if (p <= D) {
                 const int i = p - 1;
-                for (int s = 0; s < rows; ++s) acc = fma(rs[(size_t)s * K + k], xs[s * xp + i], acc);
+                const double si = DIRECT ? sk[i] : 0.0;
+                for (int s = 0; s < rows; ++s) acc = fma(rs[(size_t)s * K + k], xs[s * xp + i] - si, acc);
             } else {
                 const int q = p - 1 - D;
                 int i = (int)((sqrt(8.0 * q + 1.0) - 1.0) * 0.5);
                 while (i * (i + 1) / 2 > q) --i;
                 while ((i + 1) * (i + 2) / 2 <= q) ++i;
                 const int j = q - i * (i + 1) / 2;
+                const double si = DIRECT ? sk[i] : 0.0, sj = DIRECT ? sk[j] : 0.0;
                 for (int s = 0; s < rows; ++s)
-                    acc = fma(rs[(size_t)s * K + k], xs[s * xp + i] * xs[s * xp + j], acc);
+                    acc = fma(rs[(size_t)s * K + k], (xs[s * xp + i] - si) * (xs[s * xp + j] - sj), acc);
             }
             part[(int64_t)k * L.pitch + p] += acc;
         }
@@ -121,6 +148,7 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) pass_simple_kernel(const PassA
     if (tid == 0) {
         part[(int64_t)K * L.pitch] = ent;
         part[(int64_t)K * L.pitch + 1] = 0.0;
+        part[(int64_t)K * L.pitch + 2] = 0.0;
     }
 
     // ---- last CTA reduces the per-CTA partials in CTA order (deterministic) ----
@@ -140,7 +168,8 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) pass_simple_kernel(const PassA
         double acc = 0.0;
         for (int b = 0; b < (int)gridDim.x; ++b) acc += ws[(int64_t)b * len + o];
         if (o == (int64_t)K * L.pitch + 1) acc = (double)a.n;
-        out[o] = a.accumulate ? out[o] + acc : acc;
+        if (o == (int64_t)K * L.pitch + 2) acc = DIRECT ? 1.0 : 0.0;        // format marker: moments about state.SHIFT
+        out[o] = (a.accumulate && o != (int64_t)K * L.pitch + 2) ? out[o] + acc : acc;
     }
     if (tid == 0) ctrl[BGMM_CTRL_PASS_TICKET] = 0;
 }
@@ -162,8 +191,7 @@ int simple_grid_cap(int K, int D) {
     return (int)cap;
 }
 
-int launch_pass_simple(const PassArgs& a, int K, int D, int dtype, int hist_len_unused, cudaStream_t stream) {
-    (void)hist_len_unused;
+int launch_pass_simple(const PassArgs& a, int K, int D, int dtype, int direct, cudaStream_t stream) {
     const Layout L = make_layout(K, D, 1);  // offsets used by the pass do not depend on hist_len
     const int tile = simple_tile(K, D);
     if (tile < 1) {
@@ -175,17 +203,14 @@ int launch_pass_simple(const PassArgs& a, int K, int D, int dtype, int hist_len_
     int64_t grid64 = ntiles < 1 ? 1 : ntiles;
     if (grid64 > simple_grid_cap(K, D)) grid64 = simple_grid_cap(K, D);
     const int grid = (int)grid64;
-    cudaError_t e;
-    if (dtype == BGMM_F64) {
-        e = cudaFuncSetAttribute(pass_simple_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_simple<double>)");
-        pass_simple_kernel<double><<<grid, SIMPLE_THREADS, smem, stream>>>(a, L, tile);
-    } else {
-        e = cudaFuncSetAttribute(pass_simple_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_simple<float>)");
-        pass_simple_kernel<float><<<grid, SIMPLE_THREADS, smem, stream>>>(a, L, tile);
-    }
-    return check_cuda(cudaGetLastError(), "pass_simple_kernel launch");
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_simple)");
+        kern<<<grid, SIMPLE_THREADS, smem, stream>>>(a, L, tile);
+        return check_cuda(cudaGetLastError(), "pass_simple_kernel launch");
+    };
+    if (dtype == BGMM_F64) return direct ? go(pass_simple_kernel<double, true>) : go(pass_simple_kernel<double, false>);
+    return direct ? go(pass_simple_kernel<float, true>) : go(pass_simple_kernel<float, false>);
 }
 
 }  // namespace bgmm

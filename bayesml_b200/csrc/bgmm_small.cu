@@ -46,7 +46,7 @@ __device__ __forceinline__ double ld_peer(const double* p) {     // peer / excha
 __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, const Layout L, const int mode,
                                                     const int max_itr, const double tol,
                                                     const CommDesc* __restrict__ cd,
-                                                    const double* __restrict__ hmm_vlx) {
+                                                    const double* __restrict__ hmm_vlx, const double robust_thresh) {
     extern __shared__ double sm[];
     const int K = L.K, D = L.D, DD = D * D, k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
@@ -104,18 +104,34 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
         __syncthreads();
     }
 
+    double crit_n = 1.0;                 // weight of this component in the conditioning criterion: min(N_k, 1)
     if (iterate || stats_only) {
-        // ---- statistics of component k from the raw moments (about the centre) ----
+        // ---- statistics of component k from the moments about the centre (feature-map kernels) or about
+        //      shift_k (DIRECT kernel; tail[2] > 0):  x_bar = shift + d_bar,  S = M2 / N - d_bar d_bar^T ----
         const double* raw = st + L.stats + (int64_t)k * L.pitch;
         const double N = raw[0];
+        crit_n = fmin(N, 1.0);
+        double fmt;
+        if (fused) {                                            // CTA 0 owns the tail: sum the format marker from the peers
+            fmt = 0.0;
+            for (int r = 0; r < world; ++r) fmt += ld_peer(xb[r] + (int64_t)K * L.pitch + 2);
+        } else {
+            fmt = st[L.stats + (int64_t)K * L.pitch + 2];
+        }
+        const bool shifted = fmt > 0.5;
+        const double* sh = st + L.shift + (int64_t)k * D;
         double* S = st + L.smats + (int64_t)k * DD;
         if (N > 0.0) {
             const double invN = 1.0 / N;
-            for (int i = tid; i < D; i += nt) xbar[i] = raw[1 + i] * invN;
+            for (int i = tid; i < D; i += nt) {
+                const double db = raw[1 + i] * invN;
+                lin[i] = db;
+                xbar[i] = shifted ? sh[i] + db : db;
+            }
             __syncthreads();
             for (int e = tid; e < DD; e += nt) {
                 const int i = e / D, j = e - i * D, hi = max(i, j), lo = min(i, j);
-                S[e] = raw[1 + D + hi * (hi + 1) / 2 + lo] * invN - xbar[i] * xbar[j];
+                S[e] = raw[1 + D + hi * (hi + 1) / 2 + lo] * invN - lin[i] * lin[j];
             }
         } else {
             // reference :729 — x_bar_vecs[k] keeps the un-normalised sum (0 in the original frame), s_mats[k] stale
@@ -124,7 +140,13 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
         __syncthreads();
         for (int i = tid; i < D; i += nt) st[L.xbar + (int64_t)k * D + i] = xbar[i];
         if (tid == 0) st[L.ns + k] = N;
-        if (stats_only) return;
+        if (stats_only) {
+            // x_bar_k becomes the shift of a following centred-statistics sweep (engine.refine_smats: the reference's
+            // two-pass s_mats, :730-732, from the materialised responsibilities)
+            if (N > 0.0)
+                for (int i = tid; i < D; i += nt) st[L.shift + (int64_t)k * D + i] = xbar[i];
+            return;
+        }
 
         // ---- ELBO terms of component k under the CURRENT parameters (those the pass used) ----
         const double kappa = Pc[L.p_kappa + k], nu = Pc[L.p_nu + k], alpha = Pc[L.p_alpha + k];
@@ -284,7 +306,22 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     mq = block_sum(mq, scratch);
     double* coef = Pn + L.p_coef + (int64_t)k * L.pitch;
     // hidden-Markov emission density (_hiddenmarkovnormal.py:988-992): no E[ln pi] term in ln rho
-    if (tid == 0) coef[0] = (hmm_vlx != nullptr ? 0.0 : elnpi_n) + (elndet_n - D * LN2PI - D / kn) / 2.0 - 0.5 * mq;
+    if (tid == 0) {
+        const double acst = (hmm_vlx != nullptr ? 0.0 : elnpi_n) + (elndet_n - D * LN2PI - D / kn) / 2.0;
+        coef[0] = acst - 0.5 * mq;
+        Pn[L.p_acst + k] = acst;                                // ln rho constant of the DIRECT form (no m^T Lambda m term)
+        // conditioning of the feature-map form for this component: the terms of coef . phi(x') are of size
+        // mq = m'^T Lambda m' for the samples the component is responsible for, the result is O(D)
+        // (K = 1: r == 1 exactly whatever ln rho is, and the moments about the global centre ARE the centred ones)
+        st[L.vlk + (int64_t)k * 8 + 7] = (K == 1) ? 0.0 : crit_n * mq;
+    }
+    // the point the DIRECT kernel takes the next moments about: this pass's x_bar_k (the next one will be close), or the
+    // new m_k while the component has no statistics yet
+    if (!stats_only) {
+        double* sh = st + L.shift + (int64_t)k * D;
+        const bool have_xbar = iterate && crit_n > 0.0;
+        for (int i = tid; i < D; i += nt) sh[i] = have_xbar ? xbar[i] : mnew[i];
+    }
     for (int i = tid; i < D; i += nt) coef[1 + i] = lin[i];
     const int nq = D * (D + 1) / 2;
     for (int q = tid; q < nq; q += nt) {
@@ -296,9 +333,7 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     }
     for (int q = L.P + tid; q < L.pitch; q += nt) coef[q] = 0.0;
 
-    if (!iterate) return;
-
-    // ---- last CTA: sum the ELBO, convergence test (:869), flip the parameter sets ----
+    // ---- last CTA: conditioning flag of the new parameter set; sum the ELBO, convergence test (:869), flip the sets ----
     __shared__ int is_last;
     __threadfence();
     __syncthreads();
@@ -310,6 +345,14 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     if (!is_last || tid != 0) return;
     __threadfence();
     volatile const double* vk = st + L.vlk;
+    double crit = 0.0;
+    for (int j = 0; j < K; ++j) crit = fmax(crit, vk[j * 8 + 7]);
+    const int robust = crit > robust_thresh ? 1 : 0;
+    if (!iterate) {
+        ctrl[BGMM_CTRL_ROBUST] = robust;
+        ctrl[BGMM_CTRL_TICKET] = 0;
+        return;
+    }
     double px = 0, pz = 0, ppi = 0, pml = 0, qpi = 0, qml = 0, asum = 0;
     for (int j = 0; j < K; ++j) {
         px += vk[j * 8 + 0]; pz += vk[j * 8 + 1]; ppi += vk[j * 8 + 2]; pml += vk[j * 8 + 3];
@@ -337,7 +380,7 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     }
     if (conv) { ctrl[BGMM_CTRL_CONVERGED] = 1; ctrl[BGMM_CTRL_DONE] = 1; }
     else if (iter >= max_itr) { ctrl[BGMM_CTRL_DONE] = 1; }
-    else { ctrl[BGMM_CTRL_CUR] = cur ^ 1; }
+    else { ctrl[BGMM_CTRL_CUR] = cur ^ 1; ctrl[BGMM_CTRL_ROBUST] = robust; }
     ctrl[BGMM_CTRL_ITER] = iter + 1;
     ctrl[BGMM_CTRL_TICKET] = 0;
 }
@@ -486,7 +529,8 @@ extern "C" int bgmm_hmm_small(int K, int D, double* state, double* hst, int mode
     }
     if (mode != BGMM_SMALL_STATS) hmm_trans_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, L, hst, H, mode);
     const int nt = D <= 16 ? 32 : (D <= 32 ? 64 : (D <= 64 ? 128 : 256));
-    small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol, nullptr, hst + H.vlx);
+    small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol, nullptr, hst + H.vlx,
+                                                        robust_threshold());
     return check_cuda(cudaGetLastError(), "hmm small launch");
 }
 
@@ -515,6 +559,7 @@ extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, do
     // latency-bound kernel full of block barriers: one warp per component while the D x D work is tiny
     const int nt = D <= 16 ? 32 : (D <= 32 ? 64 : (D <= 64 ? 128 : 256));
     small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol,
-                                                        static_cast<const CommDesc*>(comm_desc), nullptr);
+                                                        static_cast<const CommDesc*>(comm_desc), nullptr,
+                                                        robust_threshold());
     return check_cuda(cudaGetLastError(), "small_kernel launch");
 }

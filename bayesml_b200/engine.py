@@ -58,7 +58,7 @@ class VBEngine:
         self.group = group
         env = os.environ.get("BAYESML_B200_PASS_VARIANT", "").lower()     # debugging / tests: force a kernel variant
         if env:
-            variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "f32": _lib.PASS_F32, "large": _lib.PASS_LARGE}[env]
+            variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "f32": _lib.PASS_F32, "large": _lib.PASS_LARGE, "direct": _lib.PASS_DIRECT}[env]
         self.variant = variant
         self.hist_len = 0
         self.state = None
@@ -146,11 +146,10 @@ class VBEngine:
         self.hist_len = int(hist_len)
         self.off, self.poff = _lib.layout(self.K, self.D, self.hist_len)
         self.state = torch.zeros(self.off["total"], dtype=torch.float64, device=self.device)
-        if old is not None:  # keep centre + prior + parameter sets (everything before the statistics) + control words
-            n_keep = old[1]["stats"]
+        if old is not None:  # keep everything in front of the (variable-length, last) ELBO history: no offset there depends on it
+            n_keep = old[1]["vlhist"]
+            assert n_keep == self.off["vlhist"]
             self.state[:n_keep].copy_(old[0][:n_keep])
-            oc = old[1]["ctrl"]
-            self.state[self.off["ctrl"]:self.off["ctrl"] + _lib.N_CTRL // 2].copy_(old[0][oc:oc + _lib.N_CTRL // 2])
         self._host_ctrl = torch.empty(_lib.N_CTRL, dtype=torch.int32).pin_memory()
         self._host_hist = torch.empty(self.hist_len, dtype=torch.float64).pin_memory()
 
@@ -267,11 +266,11 @@ class VBEngine:
         self.small_launches += 1
         self.kernel_launches += 1
 
-    def _pass(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0):
-        self.pass_only(r_out, lnrho_out, argmax_out, r_in, force)
+    def _pass(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0, r_in_variant=_lib.PASS_SIMPLE):
+        self.pass_only(r_out, lnrho_out, argmax_out, r_in, force, r_in_variant)
         self.exchange(force)
 
-    def pass_only(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0):
+    def pass_only(self, r_out=None, lnrho_out=None, argmax_out=None, r_in=None, force=0, r_in_variant=_lib.PASS_SIMPLE):
         """One bgmm_pass launch (E-step + local statistics) without the cross-rank exchange."""
         ptr = lambda t: 0 if t is None else t.data_ptr()  # noqa: E731
         if r_out is None and r_in is None and self.lib.bgmm_pass_resolve(
@@ -282,11 +281,13 @@ class VBEngine:
             r_out = self._r_scratch
         _lib.check(self.lib.bgmm_pass(ptr(self.x), self.n_local, self.K, self.D, self.x_code, self.state.data_ptr(),
                                       self.workspace.data_ptr(), ptr(r_out), ptr(lnrho_out), ptr(argmax_out),
-                                      ptr(r_in), self.variant if r_in is None else _lib.PASS_SIMPLE, force, 0,
+                                      ptr(r_in), self.variant if r_in is None else r_in_variant, force, 0,
                                       self._stream()), "bgmm_pass")
         self.passes += 1
-        self.kernel_launches += {_lib.PASS_DMMA: 2, _lib.PASS_LARGE: 4}.get(
-            self.lib.bgmm_pass_resolve(self.K, self.D, self.x_code, self.variant, int(r_in is not None)), 1)
+        resolved = self.lib.bgmm_pass_resolve(self.K, self.D, self.x_code, self.variant, int(r_in is not None))
+        self.kernel_launches += {_lib.PASS_DMMA: 2, _lib.PASS_LARGE: 5}.get(resolved, 1)
+        if r_in is None and resolved != _lib.PASS_DIRECT and self.lib.bgmm_robust_threshold() < float("inf"):
+            self.kernel_launches += 1           # the conditioning guard: DIRECT kernel behind the feature-map kernel(s)
 
     def exchange(self, force=0):
         """The per-iteration exchange of the statistics between row shards: publish to peer memory (the reduction is
@@ -403,7 +404,23 @@ class VBEngine:
             self._pass(r_out=self.r_dev, lnrho_out=self.lnrho_dev, argmax_out=self.argmax_dev, force=1)
             self._small(_lib.SMALL_STATS, 0, 0.0)
             host = self.state.cpu().numpy()
-        return self._stats_from_host(host)
+        out = self._stats_from_host(host)
+        # False: moments about the global centre (feature-map kernels), s_mats carries an absolute error of
+        # ~ eps * |x_bar_k - c|^2 (far below what the E-step's own rounding does to r, measured in tests/cond_sweep.py);
+        # refine_smats() recomputes it in the two-pass centred form from the materialised r if that is ever wanted
+        out["centred"] = bool(host[self.off["stats"] + self.K * self.off["pitch"] + 2] > 0.5)
+        return out
+
+    def refine_smats(self):
+        """s_mats of the last final_pass in the reference's two-pass centred form (:730-732): one more sweep over X with
+        the materialised responsibilities, moments about x_bar_k (bgmm_pass DIRECT with r_in).  -> s_mats [K][D][D]."""
+        if self.r_dev is None or self.x is None:
+            raise RuntimeError("refine_smats needs the responsibilities of a preceding final_pass on the resident X")
+        with torch.cuda.device(self.device):
+            self._pass(r_in=self.r_dev, force=1, r_in_variant=_lib.PASS_DIRECT)
+            self._small(_lib.SMALL_STATS, 0, 0.0)
+            o = self.off["smats"]
+            return self.state[o:o + self.K * self.D * self.D].cpu().numpy().reshape(self.K, self.D, self.D)
 
 
 class HMMEngine(VBEngine):

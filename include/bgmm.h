@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BGMM_ABI_VERSION 2
+#define BGMM_ABI_VERSION 3
 
 /* dtype of X */
 #define BGMM_F64 0
@@ -52,6 +52,12 @@ extern "C" {
 #define BGMM_PASS_F32 3    /* fp32-mode streaming kernel: X float32, D <= 3, K <= 8 (fp64 accumulation of partials) */
 #define BGMM_PASS_LARGE 4  /* fp64 large K*P regime (D <= 128, K <= 64): E kernel (r -> HBM) + output-stationary M kernel;
                               needs r_out != NULL */
+#define BGMM_PASS_DIRECT 5 /* conditioning-safe form, any K, D: ln rho from the explicit differences (x - m_k) and
+                              statistics about a per-component shift (state.SHIFT) instead of the global centre.
+                              Every other variant is a feature-map kernel whose cancellation error grows like
+                              eps * (m_k - c)^T Lambda_k (m_k - c); bgmm_small evaluates that quantity for every new
+                              parameter set and raises ctrl.ROBUST when it exceeds bgmm_robust_threshold(); bgmm_pass then
+                              runs THIS kernel instead of the requested one (decided on the device, no host sync). */
 
 /* bgmm_small `mode` */
 #define BGMM_SMALL_FEATURES 0 /* features + coef of params[cur] from (alpha, m, kappa, nu, W^-1); no statistics used */
@@ -71,7 +77,8 @@ enum {
     BGMM_OFF_LNC0,           /* _ln_c_h0_alpha[1] (+pad)                                                     */
     BGMM_OFF_PARAMS0,        /* parameter set 0 (see BGMM_P_* below)                                         */
     BGMM_OFF_PARAMS1,        /* parameter set 1 (ping-pong)                                                  */
-    BGMM_OFF_STATS,          /* raw[K][PITCH] then tail[8]: tail[0] = sum_n sum_k r ln r, tail[1] = rows     */
+    BGMM_OFF_STATS,          /* raw[K][PITCH] then tail[8]: tail[0] = sum_n sum_k r ln r, tail[1] = rows,
+                                tail[2] > 0: the moments are taken about state.SHIFT (DIRECT kernel), else about 0  */
     BGMM_OFF_NS,             /* ns[K]                                                                        */
     BGMM_OFF_XBAR,           /* x_bar_vecs[K][D] (centred)                                                   */
     BGMM_OFF_SMATS,          /* s_mats[K][D][D]                                                              */
@@ -83,6 +90,8 @@ enum {
     BGMM_OFF_STATS_LEN,      /* K*PITCH + 8: length (doubles) of the all-reduced statistics buffer           */
     BGMM_OFF_PARAMS_LEN,     /* length of one parameter set                                                  */
     BGMM_OFF_PITCH,          /* PITCH                                                                        */
+    BGMM_OFF_SHIFT,          /* shift[K][D] (centred frame): the point the DIRECT kernel takes its moments about
+                                (previous x_bar_k, or m_k before the first pass); maintained by bgmm_small        */
     BGMM_N_OFFSETS
 };
 
@@ -98,6 +107,7 @@ enum {
     BGMM_P_ELNDET,     /* _e_ln_lambda_dets[K]   */
     BGMM_P_LNB,        /* _ln_b_hn_w_nus[K]      */
     BGMM_P_COEF,       /* coef[K][PITCH]  E-step coefficient rows */
+    BGMM_P_ACST,       /* a_k[K] = E[ln pi_k] + (E[ln|Lambda_k|] - D ln 2pi - D/kappa_k)/2: ln rho constant of the DIRECT form */
     BGMM_N_PARAM_OFFSETS
 };
 
@@ -111,6 +121,8 @@ enum {
     BGMM_CTRL_PASS_TICKET,/* internal: last-CTA election for bgmm_pass                              */
     BGMM_CTRL_ERROR,      /* 1 -> a W^-1 was not positive definite (Cholesky failed)                */
     BGMM_CTRL_SEQ,        /* number of peer-memory exchanges published so far (bgmm_publish)        */
+    BGMM_CTRL_ROBUST,     /* 1 -> the current parameter set is ill-conditioned for the feature-map kernels:
+                             bgmm_pass runs the DIRECT kernel (set by bgmm_small for every new parameter set)  */
     BGMM_N_CTRL = 16
 };
 
@@ -137,13 +149,22 @@ int bgmm_center(const void* x_raw, int dtype_in, void* x_out, int dtype_out, int
  *   r_out / lnrho_out ([n][K] float64) and argmax_out ([n] int32, first index on ties — np.argmax, :1191) are
  *   optional (NULL inside the VB loop: r never touches HBM).
  *   r_in (optional, [n][K] float64): statistics of GIVEN responsibilities instead of the E-step
- *   (`_init_random_responsibility` :734-736).  No-op when ctrl.done != 0 unless `force`.
+ *   (`_init_random_responsibility` :734-736); variant SIMPLE/AUTO: moments about the centre, DIRECT: about state.SHIFT
+ *   (the reference's two-pass centred `s_mats`, :730-732, when SHIFT holds x_bar).  No-op when ctrl.done != 0 unless `force`.
  *   accumulate != 0: add to state.STATS instead of overwriting (row-chunked uploads). */
 int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, double* state, double* workspace,
               double* r_out, double* lnrho_out, int32_t* argmax_out, const double* r_in,
               int variant, int force, int accumulate, void* stream);
 
-/* 1 when `variant` (BGMM_PASS_SIMPLE / _DMMA / _F32 / _LARGE) can run this shape, else 0 */
+/* Conditioning guard of the feature-map kernels.  bgmm_small computes, for every new parameter set,
+ *   crit = max_k min(N_k, 1) * (m_k - c)^T (nu_k W_k) (m_k - c)     (N_k = 1 before the first statistics exist)
+ * and sets ctrl.ROBUST = (crit > threshold).  Default 2e4 (calibrated on the B200, tests/cond_sweep.py: below it every hyperparameter stays within 1e-9 of its own
+ * value or 1e-13 of its array's scale, whichever is larger);
+ * +inf disables the guard, 0 forces the DIRECT kernel.  Process-wide; returns the previous value. */
+double bgmm_set_robust_threshold(double threshold);
+double bgmm_robust_threshold(void);
+
+/* 1 when `variant` (BGMM_PASS_SIMPLE / _DMMA / _F32 / _LARGE / _DIRECT) can run this shape, else 0 */
 int bgmm_pass_supported(int K, int D, int dtype, int variant);
 /* the concrete variant BGMM_PASS_AUTO resolves to (has_r_in: statistics of given responsibilities) */
 int bgmm_pass_resolve(int K, int D, int dtype, int variant, int has_r_in);

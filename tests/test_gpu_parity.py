@@ -34,6 +34,14 @@ def _close(a, b, rtol=RTOL, atol=0.0, what=""):
     assert worst <= rtol or np.allclose(a, b, rtol=rtol, atol=atol), f"{what}: max rel err {worst:.3e}"
 
 
+def _w_rtol(g, state_idx=None):
+    """Bar for hn_w_mats = inv(hn_w_mats_inv): 1e-9, except where hn_w_mats_inv itself is so ill-conditioned (default
+    prior mean far from a tight cluster: rank-one term ~ sep^2) that the reference's LAPACK inverse is only defined to
+    cond * eps — then 16 * cond * eps."""
+    winv = g["final_hn_w_mats_inv"] if state_idx is None else g["traj_hn_w_mats_inv"][state_idx]
+    return max(RTOL, 16 * np.finfo(float).eps * float(np.max(np.linalg.cond(winv))))
+
+
 def _prior_arrays(g):
     from oracle.gmm_vb_oracle import OracleGMM
     prior = {f: g[f] for f in ("h0_alpha_vec", "h0_m_vecs", "h0_kappas", "h0_nus", "h0_w_mats")}
@@ -50,10 +58,13 @@ def _engine_for(g, variant=0, precision="float64"):
     return eng, o
 
 
-TRAJ_CASES = ["traj_d3k4", "traj_d16k8", "traj_offset_d4k3", "traj_prior_d3k2", "traj_k1_d5", "traj_rr_d2k3"]
+TRAJ_CASES = ["traj_d3k4", "traj_d16k8", "traj_offset_d4k3", "traj_prior_d3k2", "traj_k1_d5", "traj_rr_d2k3",
+              # conditioning cases (clusters 1e4 .. 1e5 of their own width apart, a far outlier cluster): the feature-map
+              # kernels hand over to the DIRECT kernel on the device (ctrl.robust), whatever variant was requested
+              "cond_sep1e4_d3k3", "cond_sep1e5_d2k3", "cond_outlier_d4k4", "cond_sep3e4_d16k6", "cond_sub_sep1e4_d3k3"]
 
 
-@pytest.mark.parametrize("variant", ["simple", "dmma", "large"])
+@pytest.mark.parametrize("variant", ["simple", "dmma", "large", "direct"])
 @pytest.mark.parametrize("name", TRAJ_CASES)
 def test_trajectory_from_identical_initial_state(name, variant):
     """Per restart: start the device loop from the reference's recorded initial state, compare every ELBO value of
@@ -61,7 +72,7 @@ def test_trajectory_from_identical_initial_state(name, variant):
     from bayesml_b200 import _lib
     g = load_golden(name)
     kw = _fit_kwargs(g)
-    code = {"simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "large": _lib.PASS_LARGE}[variant]
+    code = {"simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "large": _lib.PASS_LARGE, "direct": _lib.PASS_DIRECT}[variant]
     if not _lib.load().bgmm_pass_supported(int(g["K"]), int(g["D"]), _lib.F64, code):
         pytest.skip(f"{variant} kernel does not cover K={int(g['K'])} D={int(g['D'])}")
     eng, o = _engine_for(g, variant=code)
@@ -75,6 +86,10 @@ def test_trajectory_from_identical_initial_state(name, variant):
             eng.set_params(o.h0_alpha_vec, g["init_hn_m_vecs"][r], o.h0_kappas, o.h0_nus, g["init_hn_w_mats_inv"][r])
             hist, conv = eng.run(kw["max_itr"], kw["tolerance"])
         assert not conv and len(hist) == len(idx) == kw["max_itr"] + 1
+        if name.startswith("cond_") and variant != "direct":
+            assert int(eng.ctrl.cpu()[_lib.CTRL_ROBUST]) == 1, "the conditioning guard did not fire"
+        elif variant != "direct" and name != "traj_offset_d4k3":
+            assert int(eng.ctrl.cpu()[_lib.CTRL_ROBUST]) == 0, "the conditioning guard fired on a well-conditioned case"
         _close(hist, g["traj_vl_terms"][idx, 0], what=f"{name} restart {r} VL history")
         p = eng.fetch_params()
         last = idx[-1]
@@ -82,7 +97,8 @@ def test_trajectory_from_identical_initial_state(name, variant):
                           ("w", "hn_w_mats"), ("winv", "hn_w_mats_inv"), ("e_ln_pi", "_e_ln_pi_vec"),
                           ("e_ln_lambda_dets", "_e_ln_lambda_dets"), ("ln_b", "_ln_b_hn_w_nus"), ("ns", "ns"),
                           ("x_bar", "x_bar_vecs"), ("s_mats", "s_mats")]:
-            _close(p[mine], g["traj_" + ref][last], what=f"{name} restart {r} {ref}")
+            _close(p[mine], g["traj_" + ref][last], rtol=_w_rtol(g, last) if mine == "w" else RTOL,
+                   what=f"{name} restart {r} {ref}")
         # vl_terms order in the fixture: vl, p_x, p_z, p_pi, p_mu_lambda, q_z, q_pi, q_mu_lambda
         _close(p["vl_terms"][:7], g["traj_vl_terms"][last, 1:], what=f"{name} restart {r} ELBO terms")
         _close(p["vl_terms"][7], g["traj_vl_terms"][last, 0], what=f"{name} restart {r} vl")
@@ -100,7 +116,7 @@ def _parse_progress(text):
 
 
 E2E_CASES = ["c1_readme", "traj_d3k4", "traj_d16k8", "traj_rr_d2k3", "traj_offset_d4k3", "traj_prior_d3k2",
-             "traj_k1_d5", "conv_d2k4"]
+             "traj_k1_d5", "conv_d2k4", "cond_sub_sep1e4_d3k3"]
 
 
 @pytest.mark.parametrize("name", E2E_CASES)
@@ -127,18 +143,19 @@ def test_learnmodel_end_to_end_matches_reference(name):
         _close(v1, v2, what=f"{name} restart {r} printed VL")
     for f in ("hn_alpha_vec", "hn_m_vecs", "hn_kappas", "hn_nus", "hn_w_mats", "hn_w_mats_inv", "ns", "x_bar_vecs",
               "s_mats", "_e_ln_pi_vec", "_e_ln_lambda_dets", "_ln_b_hn_w_nus"):
-        _close(getattr(model, f), g["final_" + f], what=f"{name} final {f}")
+        _close(getattr(model, f), g["final_" + f], rtol=_w_rtol(g) if f == "hn_w_mats" else RTOL,
+               what=f"{name} final {f}")
     _close(model.vl, g["final_vl_attr"], what="vl attribute (last restart's)")
     r = model.r_vecs
     assert r.shape == g["final_r_vecs"].shape and r.dtype == np.float64
     assert np.allclose(r, g["final_r_vecs"], rtol=RTOL, atol=1e-300), np.abs(r / g["final_r_vecs"] - 1).max()
-    assert np.allclose(model._ln_rho, g["final_ln_rho"], rtol=RTOL, atol=1e-9)
+    assert np.allclose(model._ln_rho, g["final_ln_rho"], rtol=_w_rtol(g), atol=1e-9)   # far components: ln rho ~ d^T (nu W) d
     assert np.array_equal(np.argmax(r, axis=1), np.argmax(g["final_r_vecs"], axis=1))       # bit-exact assignments
     for f in ("p_pi_vec", "p_mu_vecs", "p_nus", "p_lambda_mats"):                            # stale, prior-based
         _close(getattr(model, f), g["stale_" + f], what="stale " + f)
     model.calc_pred_dist()
     for f in ("p_pi_vec", "p_mu_vecs", "p_nus", "p_lambda_mats"):
-        _close(getattr(model, f), g["pred_" + f], what="pred " + f)
+        _close(getattr(model, f), g["pred_" + f], rtol=_w_rtol(g) if f == "p_lambda_mats" else RTOL, what="pred " + f)
     if "latent_x" in g:
         onehot = model.estimate_latent_vars(g["latent_x"], loss="0-1")
         assert onehot.dtype == g["latent_onehot"].dtype and np.array_equal(onehot, g["latent_onehot"])
@@ -191,7 +208,7 @@ def test_sequential_update_wrappers():
 
 
 @pytest.mark.parametrize("variant", ["simple", "auto", "large"])
-@pytest.mark.parametrize("shape", [(20000, 16, 32), (50000, 2, 8), (5000, 32, 16), (3000, 7, 5), (4099, 16, 13), (6000, 40, 12)])
+@pytest.mark.parametrize("shape", [(20000, 16, 32), (50000, 2, 8), (5000, 32, 16), (3000, 7, 5), (4099, 16, 13), (20000, 40, 12)])
 def test_larger_shapes_against_oracle_and_elbo_monotone(shape, variant, monkeypatch):
     """Seeded synthetic mixtures at sizes the oracle finishes in seconds: trajectory parity from identical init, and
     the reference's own stated test criterion — the ELBO never decreases (doc/devdoc/vb_method.md:184-194)."""
@@ -217,10 +234,12 @@ def test_larger_shapes_against_oracle_and_elbo_monotone(shape, variant, monkeypa
     assert all(b >= a - 1e-9 * abs(a) for a, b in zip(vals[1:], vals[2:])), "ELBO decreased"
     for f in ("hn_alpha_vec", "hn_m_vecs", "hn_kappas", "hn_nus", "hn_w_mats_inv", "ns", "x_bar_vecs"):
         _close(getattr(m, f), getattr(o, f), what=f)
-    # covariance matrices: 1e-9 relative to each matrix's largest entry (the single-pass raw-moment form carries an absolute
-    # error ~ eps * |x_bar_k - c|^2; small off-diagonal entries are not meaningful to 1e-9 of themselves)
-    for k_ in range(k):
-        assert np.max(np.abs(m.s_mats[k_] - o.s_mats[k_])) <= RTOL * np.max(np.abs(o.s_mats[k_])), f"s_mats[{k_}]"
+    # entry by entry, same bar as everything else.  (D = 40 runs with N = 20000: at 500 samples per 40-dimensional
+    # component the fit is so weakly determined that ANY two correct implementations differ by ~5e-10 in the small
+    # entries after 6 iterations — measured with every pass on the DIRECT kernel, scratch notes in DESIGN.md §2.)
+    _close(m.s_mats, o.s_mats, what="s_mats")
+    if variant == "auto":
+        _close(m._engine().refine_smats(), o.s_mats, what="two-pass centred s_mats (bgmm_pass DIRECT with r_in)")
     assert np.allclose(m.r_vecs, o.r_vecs, rtol=RTOL, atol=1e-300)
     assert np.array_equal(np.argmax(m.r_vecs, axis=1), np.argmax(o.r_vecs, axis=1))
     assert np.allclose(m.r_vecs.sum(axis=1), 1.0, rtol=0, atol=1e-12)

@@ -7,7 +7,10 @@ from conftest import load_golden
 from oracle.gmm_vb_oracle import OracleGMM, fit
 
 CASES = ["c1_readme", "traj_d3k4", "traj_d16k8", "traj_rr_d2k3", "traj_offset_d4k3", "traj_prior_d3k2", "traj_k1_d5",
-         "conv_d2k4"]
+         "conv_d2k4", "cond_sep1e4_d3k3", "cond_sep1e5_d2k3", "cond_outlier_d4k4", "cond_sep3e4_d16k6",
+         "cond_sub_sep1e4_d3k3"]
+# fixtures recorded with the reference's `_init_subsampling` replaced by a given initial state (make_golden.py: init_override)
+GIVEN_INIT = {"cond_sep1e4_d3k3", "cond_sep1e5_d2k3", "cond_outlier_d4k4", "cond_sep3e4_d16k6"}
 FIELD_MAP = {"ns": "ns", "x_bar_vecs": "x_bar_vecs", "s_mats": "s_mats", "hn_alpha_vec": "hn_alpha_vec",
              "hn_m_vecs": "hn_m_vecs", "hn_kappas": "hn_kappas", "hn_nus": "hn_nus", "hn_w_mats": "hn_w_mats",
              "hn_w_mats_inv": "hn_w_mats_inv", "_e_ln_pi_vec": "e_ln_pi_vec", "_e_ln_lambda_dets": "e_ln_lambda_dets",
@@ -33,6 +36,16 @@ def test_oracle_reproduces_reference_trajectory(name):
     prior = {f: g[f] for f in ("h0_alpha_vec", "h0_m_vecs", "h0_kappas", "h0_nus", "h0_w_mats")}
     model = OracleGMM(K, D, seed=int(g["seed"]), **prior)
     states = []
+    if name in GIVEN_INIT:
+        restart = [0]
+
+        def given_init(x_):
+            model.hn_m_vecs[:] = g["init_hn_m_vecs"][restart[0]]
+            model.hn_w_mats_inv[:] = g["init_hn_w_mats_inv"][restart[0]]
+            model.hn_w_mats[:] = g["init_hn_w_mats"][restart[0]]
+            model.q_lambda_features()
+            restart[0] += 1
+        model.init_subsampling = given_init
 
     def record(i, t, m):
         rec = {ref: np.array(getattr(m, mine)) for ref, mine in FIELD_MAP.items()}
