@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     double ld = 0.0;
     for (int i = tid; i < D; i += nt) ld += log_ni(ldiag[i]);
     const double logdet = 2.0 * block_sum(ld, scratch);  // ln|W^-1|
-    if (!spd && tid == 0) ctrl[BGMM_CTRL_ERROR] = 1;
+    if (!spd && tid == 0) ctrl[BGMM_CTRL_ERROR] = 1;       // the finaliser below stops the loop
 
     // ---- L <- L^-1 in place (column sweep from the last column; lower triangular; 1/L_jj from rdiag) ----
     for (int j = D - 1; j >= 0; --j) {
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
         conv = fabs((vl - vb) / vb) < tol;
     }
     if (conv) { ctrl[BGMM_CTRL_CONVERGED] = 1; ctrl[BGMM_CTRL_DONE] = 1; }
-    else if (iter >= max_itr) { ctrl[BGMM_CTRL_DONE] = 1; }
+    else if (iter >= max_itr || ctrl[BGMM_CTRL_ERROR]) { ctrl[BGMM_CTRL_DONE] = 1; }   // error: queued launches become no-ops
     else { ctrl[BGMM_CTRL_CUR] = cur ^ 1; ctrl[BGMM_CTRL_ROBUST] = robust; }
     ctrl[BGMM_CTRL_ITER] = iter + 1;
     ctrl[BGMM_CTRL_TICKET] = 0;

@@ -70,6 +70,7 @@ class VBEngine:
         self.passes = 0                       # bgmm_pass calls
         self.kernel_launches = 0              # kernels launched by this engine (pass + reduction + publish + small ...)
         self._pending = None
+        self.failed = False
         self.small_launches = 0
         with torch.cuda.device(self.device):
             self.workspace = torch.empty(int(self.lib.bgmm_workspace_doubles(self.K, self.D)), dtype=torch.float64,
@@ -337,8 +338,7 @@ class VBEngine:
             self._host_hist.copy_(self.state[o:o + self.hist_len], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
         hc = self._host_ctrl
-        if int(hc[_lib.CTRL_ERROR]):
-            raise RuntimeError("bgmm_small: a W^-1 matrix was not positive definite (Cholesky failed)")
+        self.failed = bool(int(hc[_lib.CTRL_ERROR]))     # a W^-1 lost positive definiteness: the loop stopped there
         n_eval = int(hc[_lib.CTRL_ITER])
         return self._host_hist[:n_eval].numpy().copy(), bool(hc[_lib.CTRL_CONVERGED])
 

@@ -25,6 +25,8 @@ from ._exceptions import CriteriaError, DataFormatError, ParameterFormatError, R
 
 __all__ = ["LearnModel"]
 
+MAX_DEGREE = 160            # limit of the device path: bgmm_small keeps a D x D matrix in shared memory
+
 _HN_NAMES = ("hn_alpha_vec", "hn_m_vecs", "hn_kappas", "hn_nus", "hn_w_mats", "hn_w_mats_inv")
 _VL_NAMES = ("_vl_p_x", "_vl_p_z", "_vl_p_pi", "_vl_p_mu_lambda", "_vl_q_z", "_vl_q_pi", "_vl_q_mu_lambda", "vl")
 
@@ -69,6 +71,11 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         self.c_num_classes = _check.pos_int(c_num_classes, 'c_num_classes', ParameterFormatError)
         self.rng = np.random.default_rng(seed)
         K, D = self.c_num_classes, self.c_degree
+        if D > MAX_DEGREE:
+            # the reference accepts any size; the per-component kernel factorises W^-1 in shared memory
+            # (D*D + 6*D + 48 doubles <= 227 KiB): say so here, not inside update_posterior
+            raise ParameterFormatError(
+                f"bayesml_b200.gaussianmixture supports c_degree <= {MAX_DEGREE} (got {D}); there is no CPU fallback")
         self._device, self._precision, self._group = device, precision, process_group
         self._restart_group = restart_group
         self._engine_obj = None
@@ -347,32 +354,48 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
 
         best_vl = 0.0
         best = {name: np.array(getattr(self, name)) for name in _HN_NAMES}      # :838-844
+
+        def draw_init(i, keep_r=True):
+            """Initial state of restart i (:848-859).  Must be called for i = 0, 1, ... in order: nothing but the
+            initialisations consumes self.rng inside the restart loop, so the random stream equals the reference's."""
+            self.reset_hn_params()
+            r_init = None
+            if init_type == 'subsampling':
+                self._init_subsampling(x, offset, n_total)
+            elif init_type == 'random_responsibility':
+                r_init = self._init_random_responsibility(x.shape[0], offset, n_total)
+                r_init = r_init.copy() if keep_r else None    # copy: do not keep the (n_total, K) draw alive through a view
+            else:
+                raise ValueError(
+                    f'init_type={init_type} is unsupported. '
+                    + 'This function supports only '
+                    + '"subsampling" and "random_responsibility"')
+            return {"alpha": self.hn_alpha_vec.copy(), "m": self.hn_m_vecs.copy(),
+                    "kappa": self.hn_kappas.copy(), "nu": self.hn_nus.copy(),
+                    "winv": self.hn_w_mats_inv.copy(), "r_init": r_init}
+
         with eng.phase("host_init(+upload)"):
-            inits = []
-            for i in range(num_init):
-                self.reset_hn_params()
-                r_init = None
-                if init_type == 'subsampling':
-                    self._init_subsampling(x, offset, n_total)
-                elif init_type == 'random_responsibility':
-                    r_init = self._init_random_responsibility(x.shape[0], offset, n_total)
-                else:
-                    raise ValueError(
-                        f'init_type={init_type} is unsupported. '
-                        + 'This function supports only '
-                        + '"subsampling" and "random_responsibility"')
-                inits.append({"alpha": self.hn_alpha_vec.copy(), "m": self.hn_m_vecs.copy(),
-                              "kappa": self.hn_kappas.copy(), "nu": self.hn_nus.copy(),
-                              "winv": self.hn_w_mats_inv.copy(), "r_init": r_init})
+            first = draw_init(0) if num_init > 0 else None      # overlaps the asynchronous upload
         with eng.phase("centre"):
             eng.load_data_finish()
             self._push_prior(eng)
         with eng.phase("vb_loop"):
-            results = self._run_restarts(eng, inits, max_itr, tolerance)
+            results = self._run_restarts(eng, first, draw_init, num_init, max_itr, tolerance, n_total)
 
         never_converged = True
+        n_failed = sum(1 for res in results if res.get("failed"))
+        if results and n_failed == len(results):
+            raise RuntimeError("bgmm_small: a W^-1 matrix was not positive definite (Cholesky failed) in every restart")
+        first_ok = True
         for i, res in enumerate(results):
             hist = res["hist"]
+            if res.get("failed"):
+                # the reference inverts with LU and never raises here; a restart whose W^-1 lost positive definiteness is
+                # dropped from the selection instead of aborting the other restarts
+                warnings.warn(f"restart {i}: W^-1 lost positive definiteness (Cholesky failed); restart skipped",
+                              ResultWarning)
+                print(f'\r{i}. VL: nan (failed)')
+                continue
             # same progress text as :861, :868, :871
             print(f'\r{i}. VL: {hist[0]}', end='')
             for t in range(len(hist) - 1):
@@ -381,7 +404,8 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
                 never_converged = False
                 print('(converged)', end='')
             self._apply_state(res["state"])
-            if i == 0 or self.vl > best_vl:                                      # :873 (strict: ties keep the earlier)
+            if first_ok or self.vl > best_vl:                                    # :873 (strict: ties keep the earlier)
+                first_ok = False
                 print('*')
                 best_vl = self.vl
                 for name in _HN_NAMES:
@@ -403,28 +427,41 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
     _STATE_KEYS = ("alpha", "m", "kappa", "nu", "w", "winv", "e_ln_pi", "e_ln_lambda_dets", "ln_b", "vl_terms", "ns",
                    "x_bar", "s_mats")
 
-    def _restart_streams(self, eng, n_restarts):
-        """How many restarts to keep in flight on this GPU: one restart of >= one wave of tiles already fills it."""
-        tiles = max(1, -(-eng.n_local // 64))
+    def _restart_streams(self, n_restarts, n_total):
+        """How many restarts to keep in flight on this GPU: one restart of >= one wave of tiles already fills it.
+        Derived from quantities every rank of a row-sharding process group agrees on (the GLOBAL row count and the
+        group size): the restarts of all ranks must issue their collectives in the same order."""
+        shard_world = 1
+        if self._group is not None:
+            import torch.distributed as dist
+            shard_world = dist.get_world_size(self._group)
+        tiles = max(1, -(-(-(-n_total // shard_world)) // 64))
         return int(max(1, min(n_restarts, 148 // tiles, 16)))
 
-    def _run_restarts(self, eng, inits, max_itr, tolerance):
-        """Run every restart of `inits` (this rank's share when `restart_group` is set); -> per-restart results in order."""
+    def _run_restarts(self, eng, first, draw_init, num_init, max_itr, tolerance, n_total):
+        """Run every restart (this rank's share when `restart_group` is set); -> per-restart results in order.
+        Initial states are drawn in restart order; with one restart in flight they are drawn one at a time, right before
+        the restart runs (the reference holds one (N, K) responsibility array at a time, and so does this)."""
         import torch
         rank, world = 0, 1
         if self._restart_group is not None:
             import torch.distributed as dist
             rank, world = dist.get_rank(self._restart_group), dist.get_world_size(self._restart_group)
-        mine = [i for i in range(len(inits)) if i % world == rank]
+        mine = [i for i in range(num_init) if i % world == rank]
         results = {}
-        n_streams = self._restart_streams(eng, len(mine)) if mine else 0
+        n_streams = self._restart_streams(len(mine), n_total) if mine else 0
         if n_streams <= 1:
-            for i in mine:
-                ini = inits[i]
+            for i in range(num_init):
+                is_mine = i % world == rank
+                ini = first if i == 0 else draw_init(i, keep_r=is_mine)   # every rank draws every state: same stream
+                if not is_mine:
+                    continue
                 eng.set_params(ini["alpha"], ini["m"], ini["kappa"], ini["nu"], ini["winv"])
                 hist, conv = eng.run(max_itr, tolerance, r_init=ini["r_init"])
-                results[i] = {"hist": hist, "converged": conv, "state": self._state_of(eng)}
+                ini["r_init"] = None
+                results[i] = {"hist": hist, "converged": conv, "state": self._state_of(eng), "failed": eng.failed}
         else:
+            inits = [first] + [draw_init(i, keep_r=(i % world == rank)) for i in range(1, num_init)]
             from .engine import VBEngine
             while len(self._extra_engines) < n_streams - 1:
                 self._extra_engines.append(VBEngine(self.c_num_classes, self.c_degree, device=eng.device,
@@ -460,13 +497,14 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
                     if e.finished():
                         with torch.cuda.stream(st):
                             hist, conv = e.finish()
-                            results[running[slot]] = {"hist": hist, "converged": conv, "state": self._state_of(e)}
+                            results[running[slot]] = {"hist": hist, "converged": conv, "state": self._state_of(e),
+                                                      "failed": e.failed}
                         del running[slot]
                         if todo:
                             start(slot)
         if world > 1:
-            results = self._gather_restarts(results, len(inits), max_itr, rank, world)
-        return [results[i] for i in range(len(inits))]
+            results = self._gather_restarts(results, num_init, max_itr, rank, world)
+        return [results[i] for i in range(num_init)]
 
     def _state_of(self, eng):
         p = eng.fetch_params()
@@ -485,7 +523,8 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         for slot, i in enumerate(i for i in range(n_restarts) if i % world == rank):
             res = results[i]
             h = res["hist"]
-            rec = [np.array([1.0, float(res["converged"]), float(len(h))]), np.pad(h, (0, max_itr + 1 - len(h)))]
+            rec = [np.array([2.0 if res.get("failed") else 1.0, float(res["converged"]), float(len(h))]),
+                   np.pad(h, (0, max_itr + 1 - len(h)))]
             rec += [res["state"][k].ravel() for k in self._STATE_KEYS]
             buf[slot] = np.concatenate(rec)
         t = torch.as_tensor(buf)
@@ -501,14 +540,14 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         full = {}
         for i in range(n_restarts):
             rec = out[i % world][i // world]
-            assert rec[0] == 1.0, "restart record missing"
+            assert rec[0] in (1.0, 2.0), "restart record missing"
             n_h = int(rec[2])
             pos = 3 + max_itr + 1
             state = {}
             for k in self._STATE_KEYS:
                 state[k] = rec[pos:pos + sizes[k]].reshape(shapes[k]).copy()
                 pos += sizes[k]
-            full[i] = {"hist": rec[3:3 + n_h].copy(), "converged": bool(rec[1]), "state": state}
+            full[i] = {"hist": rec[3:3 + n_h].copy(), "converged": bool(rec[1]), "state": state, "failed": rec[0] == 2.0}
         return full
 
     def _final_e_step(self, eng):

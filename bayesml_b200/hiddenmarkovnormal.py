@@ -27,6 +27,8 @@ from . import _check, base
 from ._exceptions import CriteriaError, DataFormatError, ParameterFormatError, ResultWarning
 from .gaussianmixture import _LazyDeviceArray
 
+MAX_NUM_CLASSES, MAX_DEGREE = 32, 128        # limits of the device path (bgmm_hmm_supported)
+
 __all__ = ["LearnModel"]
 
 _HN_NAMES = ("hn_eta_vec", "hn_zeta_vecs", "hn_m_vecs", "hn_kappas", "hn_nus", "hn_w_mats", "hn_w_mats_inv")
@@ -65,6 +67,12 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         self.c_num_classes = _check.pos_int(c_num_classes, 'c_num_classes', ParameterFormatError)
         self.rng = np.random.default_rng(seed)
         K, D = self.c_num_classes, self.c_degree
+        if K > MAX_NUM_CLASSES or D > MAX_DEGREE:
+            # the reference accepts any size; the device scans keep one state vector per lane group (K <= 32) and the
+            # per-component kernel factorises W^-1 in shared memory (D <= 128): say so here, not inside update_posterior
+            raise ParameterFormatError(
+                f"bayesml_b200.hiddenmarkovnormal supports c_num_classes <= {MAX_NUM_CLASSES} and c_degree <= {MAX_DEGREE} "
+                f"(got {K}, {D}); there is no CPU fallback")
         self._device = device
         self._engine_obj = None
 
@@ -402,6 +410,8 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
             eng.set_hmm_params(hn["hn_eta_vec"], hn["hn_zeta_vecs"], hn["hn_m_vecs"], hn["hn_kappas"], hn["hn_nus"],
                                hn["hn_w_mats_inv"])
             hist, converged = eng.run(max_itr, tolerance, init=init)
+            if eng.failed:
+                raise RuntimeError("bgmm_small: a W^-1 matrix was not positive definite (Cholesky failed)")
             print(f'\r{i}. VL: {hist[0]}', end='')                               # :1102, :1110, :1113
             for t in range(len(hist) - 1):
                 print(f'\r{i}. VL: {hist[t + 1]} t={t} ', end='')

@@ -43,6 +43,8 @@ def _worker(rank, world, port, x_full, bounds, out_dir):
         m = gaussianmixture.LearnModel(k, d, seed=11, process_group=dist.group.WORLD)
         offset, n_total = m._shard_layout(x.shape[0])
         assert (offset, n_total) == (bounds[rank], x_full.shape[0])
+        # the number of restarts kept in flight must not depend on the size of the LOCAL shard (uneven shards)
+        assert m._restart_streams(5, 5001) == 3 and m._restart_streams(5, 100) == 5 and m._restart_streams(2, 10 ** 7) == 1
         m.reset_hn_params()
         m._init_subsampling(x, offset, n_total)
         r_init = m._init_random_responsibility(x.shape[0], offset, n_total)

@@ -36,6 +36,18 @@ for init in ("subsampling", "random_responsibility"):
     out[init] = {"alpha": m.hn_alpha_vec.tolist(), "m": m.hn_m_vecs.tolist(), "winv": m.hn_w_mats_inv.tolist(),
                  "vl": float(m.vl), "ns": m.ns.tolist(), "r_rows": int(m.r_vecs.shape[0]),
                  "r_head": m.r_vecs[:5].tolist(), "stdout": buf.getvalue()}
+# deliberately uneven shards + several restarts in flight (CUDA streams): every rank must pick the same number of
+# concurrent restarts, or the statistics all-reduces of different restarts get paired up (ADVICE r1)
+nu_ = 5001
+ub = np.array([0, 2000] + [nu_] * (world - 1))[:world + 1] if world == 2 else np.linspace(0, nu_, world + 1).astype(int)
+m = gaussianmixture.LearnModel(k, d, seed=7, device=f"cuda:{rank}", process_group=dist.group.WORLD)
+buf = io.StringIO()
+with contextlib.redirect_stdout(buf), warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    m.update_posterior(x[ub[rank]:ub[rank + 1]], max_itr=8, num_init=5, tolerance=0.0)
+out["uneven"] = {"alpha": m.hn_alpha_vec.tolist(), "m": m.hn_m_vecs.tolist(), "winv": m.hn_w_mats_inv.tolist(),
+                 "vl": float(m.vl), "ns": m.ns.tolist(), "stdout": buf.getvalue(),
+                 "streams": m._restart_streams(5, nu_)}
 # restarts spread over the ranks (x replicated), BASELINE config C5's mode
 m = gaussianmixture.LearnModel(k, d, seed=6, device=f"cuda:{rank}", restart_group=dist.group.WORLD)
 buf = io.StringIO()
@@ -88,6 +100,16 @@ def test_two_gpu_sharded_fit_matches_single_gpu_and_oracle(tmp_path):
             assert np.isclose(a["vl"], float(ref.vl), rtol=1e-9)
             assert np.allclose(a["ns"], ref.ns, rtol=1e-9)
         assert np.allclose(a["r_head"], o.r_vecs[:5], rtol=1e-9, atol=1e-300)
+
+    a, b = ranks[0]["uneven"], ranks[1]["uneven"]
+    assert a == b and a["streams"] > 1
+    single = gaussianmixture.LearnModel(k, d, seed=7)
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        single.update_posterior(x[:5001], max_itr=8, num_init=5, tolerance=0.0)
+    assert np.allclose(a["alpha"], single.hn_alpha_vec, rtol=1e-9)
+    assert np.allclose(a["winv"], single.hn_w_mats_inv, rtol=1e-9, atol=1e-12)
+    assert np.isclose(a["vl"], float(single.vl), rtol=1e-9)
 
     # restarts distributed over the ranks: every rank ends in the state of the single-GPU run, bit for bit
     a, b = ranks[0]["restarts"], ranks[1]["restarts"]
