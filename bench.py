@@ -12,8 +12,9 @@ timed iteration streams it from HBM.
 
 Printed JSON keys follow the driver contract; `value` is whole-job throughput with X resident in HBM, `e2e` is
 the same metric through the public API (`LearnModel.update_posterior`) with a HOST array, uploads/downloads
-inside the timed region.  `--impl reference` times the reference's algorithm (the numpy oracle port — the
-reference is pure Python and cannot travel to the GPU box) on the host cores.
+inside the timed region.  `--impl reference` times the UNMODIFIED reference class (`bayesml.gaussianmixture.LearnModel`
+from the oracle/_ref archive that oracle/build_ref.py packs from /root/reference; the numpy oracle port only if that
+archive is missing) on the host cores, on a bounded sample of the same workload.
 """
 import argparse
 import contextlib
@@ -42,7 +43,17 @@ CONFIGS = {
     "c4": (2_000_000, 128, 64, "float64", 3),
     "c5": (4_000_000, 32, 16, "float64", 4),
 }
-FP64_PEAK_TFLOPS = 37.0   # measured on this pool's B200 (profiles/r01_peaks_b200.json: DMMA 37.0, DFMA 36.7, cuBLAS DGEMM 35.4)
+PEAKS_FILE = os.path.join(ROOT, "profiles", "peaks_b200.json")   # tracked: tools/peaks microbenchmarks on this pool's B200
+
+
+def load_peaks():
+    """FP64 / FP32 pipe peaks from the tracked measurement (MEASURED_PEAKS.json, driver-written, has HBM and bf16 only)."""
+    with open(PEAKS_FILE) as f:
+        p = json.load(f)
+    return {"fp64_tflops": float(p["dmma_tflops"]), "fp32_tflops": float(p["ffma2_tflops"]),
+            "source": "profiles/peaks_b200.json (tools/peaks on this pool's B200: DMMA %.1f, DFMA %.1f, cuBLAS DGEMM %.1f, "
+                      "FFMA2 %.1f TFLOP/s); MEASURED_PEAKS.json has no FP64 / FP32 entry"
+                      % (p["dmma_tflops"], p["dfma_tflops"], p["dgemm_cublas_tflops"], p["ffma2_tflops"])}
 
 
 def alg_flops_per_iter(n, d, k):
@@ -141,16 +152,32 @@ class ClockSampler:
         return out
 
 
-def oracle_iteration_time(x, k, d, t_lo=1, t_hi=3):
-    """Per-iteration wall time of the numpy oracle port: (T(max_itr=t_hi) - T(max_itr=t_lo)) / (t_hi - t_lo)."""
+def cpu_fit_time(x, k, d, max_itr):
+    """(wall seconds, kind) of ONE CPU fit with exactly max_itr VB iterations (tolerance=0.0, num_init=1): the unmodified
+    reference class `bayesml.gaussianmixture.LearnModel.update_posterior` when the oracle/_ref archive (or /root/reference)
+    is there, else the numpy oracle port."""
+    from oracle import ref_loader
+    if ref_loader.reference_available():
+        gm = ref_loader.load_reference_gaussianmixture()
+        m = gm.LearnModel(k, d, seed=0)
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t0 = time.perf_counter()
+            m.update_posterior(x, max_itr=max_itr, num_init=1, tolerance=0.0)
+            return time.perf_counter() - t0, "reference"
     from oracle.gmm_vb_oracle import OracleGMM, fit
-    times = {}
-    for t in (t_lo, t_hi):
-        m = OracleGMM(k, d, seed=0)
-        t0 = time.perf_counter()
-        fit(m, x, max_itr=t, num_init=1, tolerance=0.0)
-        times[t] = time.perf_counter() - t0
-    return (times[t_hi] - times[t_lo]) / (t_hi - t_lo)
+    m = OracleGMM(k, d, seed=0)
+    t0 = time.perf_counter()
+    fit(m, x, max_itr=max_itr, num_init=1, tolerance=0.0)
+    return time.perf_counter() - t0, "port"
+
+
+def cpu_iteration_time(x, k, d, t_lo, t_hi):
+    """Per-iteration wall time (T(max_itr=t_hi) - T(max_itr=t_lo)) / (t_hi - t_lo): initialisation, the post-init pass and
+    the final E-step (:895) cancel."""
+    a, kind = cpu_fit_time(x, k, d, t_lo)
+    b, _ = cpu_fit_time(x, k, d, t_hi)
+    return (b - a) / (t_hi - t_lo), kind
 
 
 def blas_threads():
@@ -165,46 +192,132 @@ def cpu_baseline(cfg, budget_rows=200_000):
     n_total, d, k, _, idx = CONFIGS[cfg]
     n = min(n_total, budget_rows)
     x = synth_host(n, d, k, 1234 + idx)
-    per_iter = oracle_iteration_time(x, k, d)
+    per_iter, kind = cpu_iteration_time(x, k, d, 1, 3)
+    what = ("the reference class bayesml.gaussianmixture.LearnModel.update_posterior (oracle/_ref archive)" if kind == "reference"
+            else "numpy oracle port (oracle/gmm_vb_oracle.py)")
     return {"value": n * k / per_iter, "unit": UNIT, "cores": blas_threads(), "host_cpus": os.cpu_count(),
-            "kind": "port", "s_per_iter_at_sample": per_iter,
-            "sample": f"numpy oracle port (oracle/gmm_vb_oracle.py), N={n} rows of the {cfg} workload (D={d}, K={k}), "
+            "kind": kind, "s_per_iter_at_sample": per_iter,
+            "sample": f"{what}, N={n} rows of the {cfg} workload (D={d}, K={k}), "
                       f"(T(max_itr=3)-T(max_itr=1))/2, tolerance=0.0, num_init=1; linear in N"}
 
 
 def run_reference_arm(args):
-    """The reference's algorithm on the host cores (oracle port; the reference itself is Python and is not on the box)."""
+    """The UNMODIFIED reference class on the host cores, through its own public API: two calls of
+    `LearnModel.update_posterior(x, max_itr=T, num_init=1, tolerance=0.0)` with T = warmup and T = warmup + steps; the
+    difference is exactly `steps` VB iterations (:863-869) — initialisation, post-init pass and final E-step cancel.
+    Each step is a bounded sample of the workload (N rows of the same synthetic mixture), sized from a short calibration
+    so that the whole run stays within a few minutes; the per-row cost of the reference is linear in N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.gmm_vb_oracle import OracleGMM, fit  # noqa: F401
     n_total, d, k, _, idx = CONFIGS[args.config]
-    total_iters = args.steps + args.warmup
-    n = int(min(n_total, max(20_000, 200_000 * min(1.0, 30.0 / max(total_iters, 1)))))
+    t_lo, t_hi = max(args.warmup, 1), max(args.warmup, 1) + args.steps
+    # calibration: one short fit on 50k rows -> rows * iterations per second of this host
+    n_cal = min(n_total, 50_000)
+    x = synth_host(n_cal, d, k, 1234 + idx)
+    t_cal, kind = cpu_fit_time(x, k, d, 2)
+    rate = n_cal * 4.0 / max(t_cal, 1e-3)                        # 2 iterations + post-init pass + final E-step
+    budget_s = float(os.environ.get("BAYESML_B200_REF_BUDGET_S", "200"))
+    n = int(min(n_total, max(20_000, budget_s * rate / (t_lo + t_hi + 4))))
+    n = int(min(n, 1_000_000)) if n > 1_000_000 else n
     x = synth_host(n, d, k, 1234 + idx)
-    from oracle.gmm_vb_oracle import OracleGMM as O
-    m = O(k, d, seed=0)
-    m.alloc(n)
-    m.reset_hn(); m.init_rho_r(); m.init_subsampling(x); m.e_step(x); m.calc_vl()
-    for _ in range(args.warmup):
-        m.iterate(x)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        m.iterate(x)
-    dt = time.perf_counter() - t0
-    value = n * k * args.steps / dt
+    per_iter, kind = cpu_iteration_time(x, k, d, t_lo, t_hi)
+    value = n * k / per_iter
+    what = ("reference class bayesml.gaussianmixture.LearnModel.update_posterior (unmodified, oracle/_ref archive)"
+            if kind == "reference" else "numpy oracle port (oracle/gmm_vb_oracle.py; oracle/_ref archive missing)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
+        "warmup": args.warmup, "ms_per_step": 1e3 * per_iter, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.config}: GMM VB N={n_total} D={d} K={k} (timed on a bounded sample of N={n} rows)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": blas_threads(), "host_cpus": os.cpu_count(),
-                         "kind": "port",
-                         "sample": f"numpy oracle port, N={n} rows, {args.steps} VB iterations after {args.warmup} warm-up"},
+                         "kind": kind,
+                         "sample": f"{what}, N={n} rows, (T(max_itr={t_hi}) - T(max_itr={t_lo})) / {args.steps}, "
+                                   f"tolerance=0.0, num_init=1"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def _rel(a, b):
+    """max element-wise relative error, entries below 1e-4 of the array's largest magnitude held to that floor."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = float(np.max(np.abs(b))) if b.size else 0.0
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), max(scale * 1e-4, 1e-300)))) if b.size else 0.0
+
+
+def parity_multi(world, rank, device, group):
+    """Driver-visible multi-GPU parity (world > 1): a small fit with the rows sharded over all ranks — both
+    initialisations, deliberately uneven shards — against the same fit on rank 0 alone and against the CPU oracle, plus
+    one fit with the restarts spread over the ranks (`restart_group`) against the single-GPU restart loop.
+    The oracle is the checker here, exactly as in tests/ (it never feeds the timed path)."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from bayesml_b200 import gaussianmixture
+    n, d, k = 40_001, 16, 8
+    rng = np.random.default_rng(17)
+    x = rng.normal(size=(n, d)) + 4.0 * rng.integers(0, k, size=(n, 1)) * rng.normal(size=(1, d))
+    cuts = np.linspace(0, n, world + 1).astype(int)
+    cuts[1:-1] += (np.arange(1, world) % 2) * 357                # uneven shards
+    fields = ("hn_alpha_vec", "hn_m_vecs", "hn_kappas", "hn_nus", "hn_w_mats_inv", "ns", "x_bar_vecs")
+    out = {"max_rel": 0.0, "max_rel_vs_single_gpu": 0.0, "ranks_bit_identical": True, "cases": []}
+
+    def quiet_fit(model, data, **kw):
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model.update_posterior(data, **kw)
+        return model
+
+    def digest(model):
+        h = hashlib.sha256()
+        for f in fields + ("hn_w_mats",):
+            h.update(np.ascontiguousarray(getattr(model, f)).tobytes())
+        h.update(np.float64(model.vl).tobytes())
+        return torch.tensor(list(h.digest()[:8]), dtype=torch.int64, device=device)
+
+    def same_on_all_ranks(model):
+        dg = digest(model)
+        lo, hi = dg.clone(), dg.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        return bool(torch.equal(lo, hi))
+
+    for init in ("subsampling", "random_responsibility"):
+        kw = dict(max_itr=8, num_init=2, tolerance=0.0, init_type=init)
+        sharded = quiet_fit(gaussianmixture.LearnModel(k, d, seed=5, device=device, process_group=group),
+                            x[cuts[rank]:cuts[rank + 1]], **kw)
+        identical = same_on_all_ranks(sharded)
+        rec = {"case": f"rows sharded over {world} ranks, init_type={init}", "ranks_bit_identical": identical}
+        if rank == 0:
+            from oracle.gmm_vb_oracle import OracleGMM, fit
+            single = quiet_fit(gaussianmixture.LearnModel(k, d, seed=5, device=device), x, **kw)
+            o = OracleGMM(k, d, seed=5)
+            fit(o, x, **kw)
+            rec["max_rel_vs_oracle"] = max([_rel(getattr(sharded, f), getattr(o, f)) for f in fields] + [_rel(sharded.vl, o.vl)])
+            rec["max_rel_vs_single_gpu"] = max([_rel(getattr(sharded, f), getattr(single, f)) for f in fields]
+                                               + [_rel(sharded.vl, single.vl)])
+            rec["r_rows_vs_oracle"] = _rel(sharded.r_vecs[:256], o.r_vecs[:256])
+            out["max_rel"] = max(out["max_rel"], rec["max_rel_vs_oracle"], rec["r_rows_vs_oracle"])
+            out["max_rel_vs_single_gpu"] = max(out["max_rel_vs_single_gpu"], rec["max_rel_vs_single_gpu"])
+        out["ranks_bit_identical"] = out["ranks_bit_identical"] and identical
+        out["cases"].append(rec)
+        dist.barrier(group=group)
+    # restarts spread over the ranks (x replicated): the selection must equal the sequential rule (:873-883)
+    kw = dict(max_itr=25, num_init=2 * world + 1)
+    spread = quiet_fit(gaussianmixture.LearnModel(k, d, seed=6, device=device, restart_group=group), x[:6001], **kw)
+    identical = same_on_all_ranks(spread)
+    rec = {"case": f"{kw['num_init']} restarts spread over {world} ranks (restart_group)", "ranks_bit_identical": identical}
+    if rank == 0:
+        single = quiet_fit(gaussianmixture.LearnModel(k, d, seed=6, device=device), x[:6001], **kw)
+        rec["equal_to_sequential_restart_loop"] = bool(all(np.array_equal(getattr(spread, f), getattr(single, f)) for f in fields)
+                                                       and float(spread.vl) == float(single.vl))
+        out["restart_group_equals_sequential"] = rec["equal_to_sequential_restart_loop"]
+    out["ranks_bit_identical"] = out["ranks_bit_identical"] and identical
+    out["cases"].append(rec)
+    dist.barrier(group=group)
+    return out
 
 
 def main():
@@ -217,6 +330,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity block (world > 1)")
     ap.add_argument("--variant", default="auto", choices=["auto", "simple", "dmma", "f32", "large"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -339,6 +453,8 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tracked = load_peaks()
+    fp64_peak = tracked["fp64_tflops"]
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -349,13 +465,12 @@ def main():
              _lib.PASS_LARGE: "bgmm::e_large_kernel + bgmm::m_large_kernel", _lib.PASS_SIMPLE: "bgmm::pass_simple_kernel"}[
         eng.lib.bgmm_pass_resolve(k, d, eng.x_code, eng.variant, 0)]
     roofline = {
-        "bound": "tensor", "achieved": ach_tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-        "frac": ach_tflops / FP64_PEAK_TFLOPS, "traffic": traffic,
+        "bound": "tensor", "achieved": ach_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": ach_tflops / fp64_peak, "traffic": traffic,
         "kernel": kname,
         "kernel_ms": pass_ms, "kernel_share_of_step": pass_ms / ms_per_step,
         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": x_bytes,
-        "peak_source": "FP64 tensor pipe (DMMA.8x8x4) measured by tools/peaks on this pool's B200 "
-                       "(MEASURED_PEAKS.json has no FP64 entry); 'of measured'",
+        "peak_source": "FP64 tensor pipe (DMMA.8x8x4), " + tracked["source"],
         "hbm": {"achieved_gbs": x_bytes / (pass_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": x_bytes / (pass_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
@@ -366,8 +481,8 @@ def main():
         # so the HBM fraction is the headline roofline and the FP32 FMA-pipe fraction is reported beside it
         roofline.update({"bound": "hbm", "achieved": roofline["hbm"]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
                          "frac": roofline["hbm"]["frac"], "peak_source": roofline["hbm"]["peak_source"],
-                         "fp32": {"achieved_tflops": ach_tflops, "peak_tflops": 73.3, "frac": ach_tflops / 73.3,
-                                  "peak_source": "FFMA2 73.3 / FFMA 70.5 TFLOP/s measured by tools/peaks (profiles/r01_peaks_b200.json)"}})
+                         "fp32": {"achieved_tflops": ach_tflops, "peak_tflops": tracked["fp32_tflops"],
+                                  "frac": ach_tflops / tracked["fp32_tflops"], "peak_source": tracked["source"]}})
 
     # ---- e2e: the public API with a HOST array (pinned), upload + init + steps iterations + final E-step + readback ----
     e2e = None
@@ -396,8 +511,31 @@ def main():
         state_bytes = int(lm._engine().state.numel() * 8)
         e2e = {"value": n_total * k * args.steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(x_host.nbytes / args.steps), "d2h_bytes_per_step": int(2 * state_bytes / args.steps),
-               "seconds": dt, "api": "bayesml_b200.gaussianmixture.LearnModel.update_posterior(x_host, max_itr=steps, "
-                                     "num_init=1, tolerance=0.0): upload + centring + host init + steps iterations + final E-step"}
+               "seconds": dt, "host_buffer": "pinned",
+               "api": "bayesml_b200.gaussianmixture.LearnModel.update_posterior(x_host, max_itr=steps, "
+                      "num_init=1, tolerance=0.0): upload + centring + host init + steps iterations + final E-step"}
+        # the same call on an ordinary (pageable) numpy array, as a user of the reference would pass it
+        x_page = np.array(x_host)
+        del x_host, x_host_t
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            barrier()
+            t0 = time.perf_counter()
+            lm.update_posterior(x_page, max_itr=args.steps, num_init=1, tolerance=0.0)
+            _ = float(lm.vl); _ = lm.hn_alpha_vec.sum()
+            torch.cuda.synchronize(device)
+            dtp = time.perf_counter() - t0
+        dtp_t = torch.tensor([dtp], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dtp_t, op=dist.ReduceOp.MAX)
+        dtp = float(dtp_t.item())
+        e2e["pageable"] = {"value": n_total * k * args.steps / dtp, "unit": UNIT, "seconds": dtp,
+                           "host_buffer": "pageable numpy array (cudaMemcpy from unpinned memory)"}
+        del x_page
+
+    pm = None
+    if world > 1 and not args.no_parity:
+        pm = parity_multi(world, rank, device, group)
 
     if rank == 0:
         line = {
@@ -413,6 +551,10 @@ def main():
             "iters_per_s": 1e3 / ms_per_step, "elbo_finite_and_monotone": ok,
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
+        if e2e is not None:
+            line["e2e_pageable"] = e2e.pop("pageable")
+        if pm is not None:
+            line["parity_multi"] = pm
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.config)
         print(json.dumps(line), flush=True)
