@@ -19,6 +19,7 @@ OFF_NAMES = ("center", "alpha0", "kappa0", "nu0", "m0", "w0inv", "lnb0", "lnc0",
 POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb", "coef", "acst")
 CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR, CTRL_SEQ, CTRL_ROBUST = range(9)
 MAX_RANKS = 16
+MAX_BATCH = 8
 N_CTRL = 16
 HMM_OFF_NAMES = ("zeta0", "lncz0", "set0", "set1", "set_zeta", "set_lna", "set_at", "set_misc", "ms", "g0", "sc", "vlx",
                  "total")
@@ -56,6 +57,10 @@ def load():
     lib.bgmm_center.argtypes = [vp, i32, vp, i32, i64, i32, vp, vp]
     lib.bgmm_pass.restype = i32
     lib.bgmm_pass.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.bgmm_pass_batched.restype = i32
+    lib.bgmm_pass_batched.argtypes = [vp, i64, i32, i32, i32, ctypes.POINTER(vp), vp, vp, vp, vp]
+    lib.bgmm_batch_capacity.restype = i32
+    lib.bgmm_batch_capacity.argtypes = [i32, i32]
     lib.bgmm_pass_supported.restype = i32
     lib.bgmm_pass_supported.argtypes = [i32, i32, i32, i32]
     lib.bgmm_pass_resolve.restype = i32

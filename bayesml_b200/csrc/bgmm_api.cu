@@ -35,6 +35,8 @@ int64_t f32_workspace_doubles(int K, int D);
 bool large_supported(int K, int D, int dtype);
 int launch_pass_large(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream);
 int64_t large_workspace_doubles(int K, int D);
+int launch_pass_batched(const void* x, int64_t n, int K, int D, const BatchDesc& bd, double* sup, double* workspace,
+                        double* r_scratch, cudaStream_t stream);
 
 // ---- data preparation ----
 constexpr int PREP_THREADS = 256;
@@ -157,6 +159,43 @@ extern "C" int bgmm_center(const void* x, int dtype_in, void* y, int dtype_out, 
         center_kernel<float, double><<<grid, PREP_THREADS, 0, s>>>((const float*)x, (double*)y, total, D, c);
     else { set_error("bgmm_center: bad dtype"); return BGMM_EINVAL; }
     return check_cuda(cudaGetLastError(), "bgmm_center launch");
+}
+
+extern "C" int bgmm_batch_capacity(int K, int D) {
+    if (K <= 0 || D <= 0 || !large_supported(K, D, BGMM_F64)) return 1;
+    const int Kp = (K + 7) & ~7;
+    int r = 64 / Kp;
+    if (r > BGMM_MAX_BATCH) r = BGMM_MAX_BATCH;
+    return r < 1 ? 1 : r;
+}
+
+extern "C" int bgmm_pass_batched(const void* x, int64_t n, int K, int D, int R, double* const* states, double* sup,
+                                 double* workspace, double* r_scratch, void* stream) {
+    if (K <= 0 || D <= 0 || n < 0 || R < 2 || R > BGMM_MAX_BATCH || states == nullptr || sup == nullptr ||
+        workspace == nullptr || r_scratch == nullptr || (x == nullptr && n > 0)) {
+        set_error("bgmm_pass_batched: bad argument (n=%lld K=%d D=%d R=%d)", (long long)n, K, D, R);
+        return BGMM_EINVAL;
+    }
+    if (R > bgmm_batch_capacity(K, D)) {
+        set_error("bgmm_pass_batched: R=%d exceeds the capacity %d of K=%d D=%d", R, bgmm_batch_capacity(K, D), K, D);
+        return BGMM_ENOSUP;
+    }
+    BatchDesc bd;
+    bd.R = R;
+    for (int i = 0; i < BGMM_MAX_BATCH; ++i) bd.st[i] = i < R ? states[i] : nullptr;
+    for (int i = 0; i < R; ++i)
+        if (bd.st[i] == nullptr) { set_error("bgmm_pass_batched: member state %d is NULL", i); return BGMM_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = launch_pass_batched(x, n, K, D, bd, sup, workspace, r_scratch, s);
+    if (rc) return rc;
+    if (g_robust_threshold < INFINITY) {
+        // conditioning guard, per member: returns at once unless that member's ctrl.robust is set
+        for (int i = 0; i < R && rc == 0; ++i) {
+            PassArgs a{x, n, bd.st[i], workspace, nullptr, nullptr, nullptr, nullptr, 0, 0};
+            rc = launch_pass_simple(a, K, D, BGMM_F64, 1, s);
+        }
+    }
+    return rc;
 }
 
 extern "C" int bgmm_pass_supported(int K, int D, int dtype, int variant) {

@@ -105,6 +105,12 @@ __device__ __forceinline__ void block_sum4(double& a, double& b, double& c, doub
     a = ta; b = tb; c = tc; d = td;
 }
 
+// Member states of a batched pass (bgmm_pass_batched): device pointers of R state blocks that share X.
+struct BatchDesc {
+    double* st[BGMM_MAX_BATCH];
+    int R;
+};
+
 // Arguments of one pass launch (see bgmm_pass in include/bgmm.h).
 struct PassArgs {
     const void* x;

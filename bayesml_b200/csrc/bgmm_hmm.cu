@@ -25,7 +25,7 @@
 
 namespace bgmm {
 
-int launch_pass_large_part(const PassArgs& a, int K, int D, int dtype, int which, cudaStream_t stream);
+int launch_pass_large_part(const PassArgs& a, int K, int D, int dtype, int which, cudaStream_t stream, int group_blocks = 0);
 bool large_supported(int K, int D, int dtype);
 
 constexpr int HW = 4;            // warps per CTA in the scan kernels

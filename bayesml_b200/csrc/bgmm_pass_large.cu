@@ -82,10 +82,14 @@ __global__ void __launch_bounds__(256) feat_table_kernel(unsigned short* __restr
 // thread builds its A fragments (row g of its block, the features of its quad lane q) from the X tile in registers, one
 // in-stream DMUL per fragment.  (A separate producer starves: its DMULs queue behind the GEMM warps' DMMAs on the in-order
 // FP64 pipe, ~250 cycles each — measured, profiles/.)  The X tile has a padded row pitch (conflict-free column reads).
-template <int KB>
+// GB = 8-component blocks per softmax GROUP.  GB == KB: one mixture (the usual case).  GB < KB: the K components are
+// NG = KB / GB independent mixtures of 8*GB components each that share X (batched restarts, bgmm_pass_batched): one X read
+// and one Phi fragment generation serve all of them; the softmax, the entropy term and r are per group.
+template <int KB, int GB>
 __global__ void __launch_bounds__(LG_ETHREADS, 1)
 e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const double* __restrict__ packed,
                const unsigned short* __restrict__ ftab) {
+    constexpr int NG = KB / GB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int K = L.K, D = L.D, P = L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
@@ -111,7 +115,9 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
 
     const int64_t ntiles = (a.n + LG_ETILE - 1) / LG_ETILE;
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    double ent = 0.0;
+    double ent[NG];
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) ent[gi] = 0.0;
 
     if (warp == 8) {
         // =========================== TMA WARP: coefficient chunks, two stages ===========================
@@ -135,7 +141,9 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
         const int eo0 = (2 * q) ^ fg, eo1 = (8 + 2 * q) ^ fg;
         const double* xr = xs + lrow * XP;                     // this thread's row of the X tile
         for (int r = tid; r < LG_ETILE; r += 256) { xs[r * XP + D] = 1.0; xs[r * XP + D + 1] = 0.0; }   // constant columns
-        double sprod = 1.0;
+        double sprod[NG];
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) sprod[gi] = 1.0;
         int64_t cc = 0;
         int it = 0;
         // D <= 32: a 64-row tile is <= 8 elements per thread, so the NEXT tile is fetched into registers before this
@@ -216,6 +224,43 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
             // ---- softmax over k for row lrow; this thread holds components 8kb + 2q + {0,1} ----
             const int64_t grow = row0 + lrow;
             const bool valid = lrow < rows;
+            if constexpr (NG > 1) {
+                // batched mixtures: one softmax per group of GB blocks; r -> HBM, entropy per group; nothing else is produced
+#pragma unroll
+                for (int gi = 0; gi < NG; ++gi) {
+                    double gmx = -INFINITY;
+#pragma unroll
+                    for (int kb = gi * GB; kb < (gi + 1) * GB; ++kb) gmx = fmax(gmx, fmax(lr[kb][0], lr[kb][1]));
+                    gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, 1));
+                    gmx = fmax(gmx, __shfl_xor_sync(0xffffffffu, gmx, 2));
+                    double gsum = 0.0, gdot = 0.0;
+#pragma unroll
+                    for (int kb = gi * GB; kb < (gi + 1) * GB; ++kb)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double z = lr[kb][e] - gmx;
+                            const double ex = exp_nonpos(z);
+                            lr[kb][e] = ex;
+                            gsum += ex;
+                            gdot = fma(ex, z, gdot);
+                        }
+                    gsum += __shfl_xor_sync(0xffffffffu, gsum, 1);
+                    gsum += __shfl_xor_sync(0xffffffffu, gsum, 2);
+                    gdot += __shfl_xor_sync(0xffffffffu, gdot, 1);
+                    gdot += __shfl_xor_sync(0xffffffffu, gdot, 2);
+                    const double ginv = valid ? 1.0 / gsum : 0.0;
+                    if (valid && q == 0) { ent[gi] = fma(gdot, ginv, ent[gi]); sprod[gi] *= gsum; }
+                    if ((it & 7) == 7) { ent[gi] -= log(sprod[gi]); sprod[gi] = 1.0; }
+#pragma unroll
+                    for (int kb = gi * GB; kb < (gi + 1) * GB; ++kb)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int k = 8 * kb + 2 * q + e;
+                            if (valid && k < K) a.r_out[grow * K + k] = lr[kb][e] * ginv;
+                        }
+                }
+                continue;
+            }
             double mx = -INFINITY;
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) mx = fmax(mx, fmax(lr[kb][0], lr[kb][1]));
@@ -259,8 +304,8 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
             dot += __shfl_xor_sync(0xffffffffu, dot, 1);
             dot += __shfl_xor_sync(0xffffffffu, dot, 2);
             const double inv = valid ? 1.0 / sum : 0.0;
-            if (valid && q == 0) { ent = fma(dot, inv, ent); sprod *= sum; }
-            if ((it & 7) == 7) { ent -= log(sprod); sprod = 1.0; }
+            if (valid && q == 0) { ent[0] = fma(dot, inv, ent[0]); sprod[0] *= sum; }
+            if ((it & 7) == 7) { ent[0] -= log(sprod[0]); sprod[0] = 1.0; }
             int best = 0x7fffffff;
             double bestv = -1.0;
 #pragma unroll
@@ -282,10 +327,14 @@ e_large_kernel(const PassArgs a, const Layout L, double* __restrict__ ews, const
                 if (valid && q == 0) a.argmax_out[grow] = best;
             }
         }
-        ent -= log(sprod);
+#pragma unroll
+        for (int gi = 0; gi < NG; ++gi) ent[gi] -= log(sprod[gi]);
     }
-    ent = block_sum(ent, red);
-    if (tid == 0) ews[blockIdx.x] = ent;
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+        const double v = block_sum(ent[gi], red);
+        if (tid == 0) ews[(int64_t)blockIdx.x * 8 + gi] = v;          // per CTA: 8 slots, one per group
+    }
 }
 
 // Output-stationary statistics GEMM.  A CTA owns the 128-feature chunk cx for the rows of split ry; warp w owns the
@@ -409,7 +458,8 @@ m_large_kernel(const PassArgs a, const Layout L, const double* __restrict__ ews,
     if (cx == 0 && tid < 8) {
         double v = 0.0;
         if (tid == 0 && ry == 0)
-            for (int i = 0; i < n_ews; ++i) v += ews[i];                // fixed order: deterministic
+            for (int i = 0; i < n_ews; ++i) v += ews[(int64_t)i * 8];   // fixed order: deterministic (group 0; the other
+                                                                        // groups of a batched pass are summed by batch_scatter)
         part[(int64_t)K * L.pitch + tid] = v;
     }
 }
@@ -444,29 +494,30 @@ static void large_plan(int K, int D, int64_t n, int& grid_e, int& n_chunks, int&
 int64_t large_workspace_doubles(int K, int D) {
     if (K > 64 || D > 128) return 0;
     const int64_t nchunk = (feat_count(D) + LG_CW - 1) / LG_CW;
-    // <= 64 row splits + E-kernel entropy partials + the packed coefficient image (nchunk x [8*KB][64]) + the (i, j) table
-    return (int64_t)large_max_split(D) * ((int64_t)K * feat_pitch(D) + 8) + 256 + nchunk * 64 * LG_CW +
+    // <= 64 row splits + E-kernel entropy partials (8 group slots per CTA) + the packed coefficient image
+    // (nchunk x [8*KB][64]) + the (i, j) table
+    return (int64_t)large_max_split(D) * ((int64_t)K * feat_pitch(D) + 8) + 8 * 160 + nchunk * 64 * LG_CW +
            (nchunk * LG_CW + 3) / 4 + 8;
 }
 
 // which = 1: E kernel (+ coefficient image / feature table), 2: M kernel (+ reduction over the row splits), 3: both
-template <int KB>
+template <int KB, int GB>
 static int launch_large_t(const PassArgs& a, const Layout& L, int which, cudaStream_t stream) {
     int grid_e, n_chunks, nsplit;
     large_plan(L.K, L.D, a.n, grid_e, n_chunks, nsplit);
     const int64_t len = L.stats_len;
     double* ews = a.workspace + (int64_t)large_max_split(L.D) * len;
-    double* packed = ews + 256;
+    double* packed = ews + 8 * 160;
     const int nchunk_e = (L.P + LG_CW - 1) / LG_CW;
     unsigned short* ftab = reinterpret_cast<unsigned short*>(packed + (int64_t)nchunk_e * 8 * KB * LG_CW);
     if (which & 1) {
         const size_t smem_e = sizeof(double) * ((size_t)2 * 8 * KB * LG_CW + (size_t)LG_ETILE * (L.D + 2) + 40) +
                               4 * sizeof(uint64_t) + sizeof(unsigned short) * (size_t)nchunk_e * LG_CW + 128;
-        cudaError_t e = cudaFuncSetAttribute(e_large_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
+        cudaError_t e = cudaFuncSetAttribute(e_large_kernel<KB, GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(e_large)");
         coef_pack_kernel<KB><<<nchunk_e, LG_THREADS, 0, stream>>>(a.state, L, packed, a.force, a.ignore_robust);
         feat_table_kernel<<<(nchunk_e * LG_CW + 255) / 256, 256, 0, stream>>>(ftab, L.D, L.P, nchunk_e * LG_CW);
-        e_large_kernel<KB><<<grid_e, LG_ETHREADS, smem_e, stream>>>(a, L, ews, packed, ftab);
+        e_large_kernel<KB, GB><<<grid_e, LG_ETHREADS, smem_e, stream>>>(a, L, ews, packed, ftab);
     }
     if (which & 2) {
         constexpr int RP = (8 * KB < 16) ? 16 : 8 * KB;
@@ -480,7 +531,7 @@ static int launch_large_t(const PassArgs& a, const Layout& L, int which, cudaStr
     return check_cuda(cudaGetLastError(), "pass_large launch");
 }
 
-int launch_pass_large_part(const PassArgs& a, int K, int D, int dtype, int which, cudaStream_t stream) {
+int launch_pass_large_part(const PassArgs& a, int K, int D, int dtype, int which, cudaStream_t stream, int group_blocks) {
     if (!large_supported(K, D, dtype)) {
         set_error("bgmm_pass(large): unsupported shape K=%d D=%d dtype=%d", K, D, dtype);
         return BGMM_ENOSUP;
@@ -490,16 +541,86 @@ int launch_pass_large_part(const PassArgs& a, int K, int D, int dtype, int which
         return BGMM_EINVAL;
     }
     const Layout L = make_layout(K, D, 1);
-    switch (large_kb(K)) {
-        case 1: return launch_large_t<1>(a, L, which, stream);
-        case 2: return launch_large_t<2>(a, L, which, stream);
-        case 4: return launch_large_t<4>(a, L, which, stream);
-        default: return launch_large_t<8>(a, L, which, stream);
-    }
+    const int kb = large_kb(K), gb = group_blocks > 0 ? group_blocks : kb;      // gb < kb: batched mixtures (softmax groups)
+#define BGMM_LG_CASE(KBv, GBv) if (kb == KBv && gb == GBv) return launch_large_t<KBv, GBv>(a, L, which, stream);
+    BGMM_LG_CASE(1, 1)
+    BGMM_LG_CASE(2, 2) BGMM_LG_CASE(2, 1)
+    BGMM_LG_CASE(4, 4) BGMM_LG_CASE(4, 2) BGMM_LG_CASE(4, 1)
+    BGMM_LG_CASE(8, 8) BGMM_LG_CASE(8, 4) BGMM_LG_CASE(8, 2) BGMM_LG_CASE(8, 1)
+#undef BGMM_LG_CASE
+    set_error("bgmm_pass(large): no instantiation for %d component blocks in groups of %d", kb, gb);
+    return BGMM_ENOSUP;
 }
 
 int launch_pass_large(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream) {
-    return launch_pass_large_part(a, K, D, dtype, 3, stream);
+    return launch_pass_large_part(a, K, D, dtype, 3, stream, 0);
+}
+
+// ---- batched mixtures (bgmm_pass_batched): R member states share one sweep over X through a "super" state block ----
+// gather: coefficient rows of every member's current parameter set -> rows [r * Kp, r * Kp + K) of the super state's set 0
+// (rows K..Kp-1 of each group: ln rho = -1e300, i.e. r == 0 exactly); super ctrl.done = every member is done.
+__global__ void __launch_bounds__(128) batch_gather_kernel(const BatchDesc bd, double* __restrict__ sup, const Layout Ls,
+                                                           const Layout Lm, const int Kp) {
+    const int ke = blockIdx.x, r = ke / Kp, k = ke - r * Kp;
+    const double* st = bd.st[r];
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + Lm.ctrl);
+    double* dst = sup + Ls.params[0] + Ls.p_coef + (int64_t)ke * Ls.pitch;
+    if (k < Lm.K) {
+        const double* src = st + Lm.params[ctrl[BGMM_CTRL_CUR]] + Lm.p_coef + (int64_t)k * Lm.pitch;
+        for (int p = threadIdx.x; p < Ls.pitch; p += 128) dst[p] = src[p];
+    } else {
+        for (int p = threadIdx.x; p < Ls.pitch; p += 128) dst[p] = p == 0 ? -1.0e300 : 0.0;
+    }
+    if (ke == 0 && threadIdx.x == 0) {
+        int all_done = 1;
+        for (int i = 0; i < bd.R; ++i)
+            all_done &= reinterpret_cast<const volatile int*>(bd.st[i] + Lm.ctrl)[BGMM_CTRL_DONE] != 0;
+        volatile int* sc = reinterpret_cast<volatile int*>(sup + Ls.ctrl);
+        sc[BGMM_CTRL_CUR] = 0; sc[BGMM_CTRL_DONE] = all_done; sc[BGMM_CTRL_ROBUST] = 0;
+    }
+}
+
+// scatter: statistics rows of group r -> member r's STATS (+ tail: the group's entropy term summed over the E kernel's
+// CTAs in a fixed order, the row count, format 0).  Members that are done keep their last statistics.
+__global__ void __launch_bounds__(128) batch_scatter_kernel(const BatchDesc bd, const double* __restrict__ sup, const Layout Ls,
+                                                            const Layout Lm, const int Kp, const double* __restrict__ ews,
+                                                            const int n_ews, const double rows) {
+    const volatile int* sc = reinterpret_cast<const volatile int*>(sup + Ls.ctrl);
+    if (sc[BGMM_CTRL_DONE]) return;
+    const int r = blockIdx.x / (Lm.K + 1), k = blockIdx.x - r * (Lm.K + 1);
+    double* st = bd.st[r];
+    if (reinterpret_cast<const volatile int*>(st + Lm.ctrl)[BGMM_CTRL_DONE]) return;
+    if (k < Lm.K) {
+        const double* src = sup + Ls.stats + (int64_t)(r * Kp + k) * Ls.pitch;
+        double* dst = st + Lm.stats + (int64_t)k * Lm.pitch;
+        for (int p = threadIdx.x; p < Lm.pitch; p += 128) dst[p] = src[p];
+    } else if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int i = 0; i < n_ews; ++i) v += ews[(int64_t)i * 8 + r];
+        double* tail = st + Lm.stats + (int64_t)Lm.K * Lm.pitch;
+        tail[0] = v; tail[1] = rows; tail[2] = 0.0;
+        for (int o = 3; o < 8; ++o) tail[o] = 0.0;
+    }
+}
+
+int launch_pass_batched(const void* x, int64_t n, int K, int D, const BatchDesc& bd, double* sup, double* workspace,
+                        double* r_scratch, cudaStream_t stream) {
+    const int Kp = (K + 7) & ~7, Ke = bd.R * Kp;
+    if (!large_supported(Ke, D, BGMM_F64) || bd.R < 2 || bd.R > BGMM_MAX_BATCH) {
+        set_error("bgmm_pass_batched: unsupported batch (K=%d -> %d per group, R=%d, D=%d; R * Kp <= 64)", K, Kp, bd.R, D);
+        return BGMM_ENOSUP;
+    }
+    const Layout Ls = make_layout(Ke, D, 1), Lm = make_layout(K, D, 1);
+    batch_gather_kernel<<<Ke, 128, 0, stream>>>(bd, sup, Ls, Lm, Kp);
+    PassArgs a{x, n, sup, workspace, r_scratch, nullptr, nullptr, nullptr, 0, 0};
+    a.ignore_robust = 1;                                        // a flagged member is redone by its own DIRECT pass (caller)
+    const int rc = launch_pass_large_part(a, Ke, D, BGMM_F64, 3, stream, Kp / 8);
+    if (rc) return rc;
+    int grid_e, n_chunks, nsplit;
+    large_plan(Ke, D, n, grid_e, n_chunks, nsplit);
+    const double* ews = workspace + (int64_t)large_max_split(D) * Ls.stats_len;
+    batch_scatter_kernel<<<bd.R * (K + 1), 128, 0, stream>>>(bd, sup, Ls, Lm, Kp, ews, grid_e, (double)n);
+    return check_cuda(cudaGetLastError(), "pass_batched launch");
 }
 
 }  // namespace bgmm

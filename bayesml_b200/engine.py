@@ -423,6 +423,48 @@ class VBEngine:
             return self.state[o:o + self.K * self.D * self.D].cpu().numpy().reshape(self.K, self.D, self.D)
 
 
+class RestartBatch:
+    """Several restarts of the same fit advanced by ONE sweep over X per VB iteration (north_star (4); the restart loop
+    `update_posterior` :847-883 run concurrently instead of one after another).
+
+    Members are VBEngines that share the resident X (`share_data_from`); bgmm_pass_batched stacks their coefficient rows
+    into one E-GEMM / M-GEMM of R * Kp components with one softmax per member, then every member runs its own bgmm_small
+    (ELBO, convergence flag, M-step).  Members that are done are carried along as no-ops until the caller swaps them out."""
+
+    def __init__(self, lead, capacity):
+        self.lead, self.lib = lead, lead.lib
+        K, D = lead.K, lead.D
+        self.Kp = (K + 7) // 8 * 8
+        self.capacity = int(capacity)
+        ke = self.capacity * self.Kp
+        with torch.cuda.device(lead.device):
+            off, _ = _lib.layout(ke, D, 1)
+            self.super_state = torch.zeros(off["total"], dtype=torch.float64, device=lead.device)
+            self.workspace = torch.empty(int(self.lib.bgmm_workspace_doubles(ke, D)), dtype=torch.float64, device=lead.device)
+            self.r_scratch = torch.empty((lead.n_local, ke), dtype=torch.float64, device=lead.device)
+
+    def pass_only(self, members):
+        """The shared E-step / statistics sweep of every engine in `members` (2 <= len <= capacity)."""
+        lead = self.lead
+        R = len(members)
+        ptrs = (ctypes.c_void_p * R)(*[m.state.data_ptr() for m in members])
+        with torch.cuda.device(lead.device):
+            _lib.check(self.lib.bgmm_pass_batched(lead.x.data_ptr(), lead.n_local, lead.K, lead.D, R, ptrs,
+                                                  self.super_state.data_ptr(), self.workspace.data_ptr(),
+                                                  self.r_scratch.data_ptr(), lead._stream()), "bgmm_pass_batched")
+        lead.passes += 1
+        # gather + coefficient image + feature table + E + M + reduction + scatter (+ one guard launch per member)
+        lead.kernel_launches += 7 + (R if self.lib.bgmm_robust_threshold() < float("inf") else 0)
+
+    def step(self, members, max_itr=None, tol=None):
+        """One VB iteration (:863-869) of every engine in `members`."""
+        self.pass_only(members)
+        with torch.cuda.device(self.lead.device):
+            for m in members:
+                m._small(_lib.SMALL_ITERATE, m._max_itr if max_itr is None else max_itr, m._tol if tol is None else tol)
+                m._launched += 1
+
+
 class HMMEngine(VBEngine):
     """Device engine of the VB hidden-Markov (Gaussian emission) fit: the mixture engine's state block (alpha plays eta)
     plus the transition-matrix block `hst` and the per-element buffers of the forward-backward scan.

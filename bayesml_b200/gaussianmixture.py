@@ -450,7 +450,10 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         mine = [i for i in range(num_init) if i % world == rank]
         results = {}
         n_streams = self._restart_streams(len(mine), n_total) if mine else 0
-        if n_streams <= 1:
+        batch = self._restart_batch_size(eng, len(mine)) if n_streams <= 1 else 1
+        if batch >= 2:
+            self._run_restarts_batched(eng, first, draw_init, num_init, mine, batch, max_itr, tolerance, results)
+        elif n_streams <= 1:
             for i in range(num_init):
                 is_mine = i % world == rank
                 ini = first if i == 0 else draw_init(i, keep_r=is_mine)   # every rank draws every state: same stream
@@ -505,6 +508,84 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         if world > 1:
             results = self._gather_restarts(results, num_init, max_itr, rank, world)
         return [results[i] for i in range(num_init)]
+
+    def _restart_batch_size(self, eng, n_restarts):
+        """Restarts advanced together by one sweep over X (bgmm_pass_batched): available in the large K*P regime on a
+        single device when several restarts of K (rounded up to 8) components fit one 64-component GEMM."""
+        import os
+        from . import _lib
+        if self._group is not None or n_restarts < 2 or eng.precision != "float64" or os.environ.get("BAYESML_B200_NO_BATCH"):
+            return 1
+        if eng.lib.bgmm_pass_resolve(eng.K, eng.D, eng.x_code, eng.variant, 0) != _lib.PASS_LARGE:
+            return 1
+        return int(min(n_restarts, eng.lib.bgmm_batch_capacity(eng.K, eng.D)))
+
+    def _run_restarts_batched(self, eng, first, draw_init, num_init, mine, batch, max_itr, tolerance, results):
+        """`batch` restarts in flight on one stream, one sweep over X per VB iteration for all of them; a finished
+        restart is swapped for the next one at the next host check.  Initial states are drawn in restart order."""
+        import torch
+        from .engine import RestartBatch, VBEngine
+        world = 1
+        rank = 0
+        if self._restart_group is not None:
+            import torch.distributed as dist
+            rank, world = dist.get_rank(self._restart_group), dist.get_world_size(self._restart_group)
+        while len(self._extra_engines) < batch - 1:
+            self._extra_engines.append(VBEngine(self.c_num_classes, self.c_degree, device=eng.device,
+                                                precision=self._precision, fused_comm=False))
+        slots = [eng] + self._extra_engines[:batch - 1]
+        for extra in slots[1:]:
+            extra.share_data_from(eng)
+            self._push_prior(extra)
+        runner = RestartBatch(eng, batch)
+        next_i = [0]
+
+        def next_init():
+            """-> (restart index, init) of this rank's next restart, drawing (and dropping) the other ranks' states."""
+            while next_i[0] < num_init:
+                i = next_i[0]
+                next_i[0] += 1
+                is_mine = i % world == rank
+                ini = first if i == 0 else draw_init(i, keep_r=is_mine)
+                if is_mine:
+                    return i, ini
+            return None
+
+        running = {}
+
+        def start(slot):
+            nxt = next_init()
+            if nxt is None:
+                return
+            i, ini = nxt
+            e = slots[slot]
+            e.set_params(ini["alpha"], ini["m"], ini["kappa"], ini["nu"], ini["winv"])
+            e.begin(max_itr, tolerance, r_init=ini["r_init"])
+            ini["r_init"] = None
+            running[slot] = i
+
+        for slot in range(batch):
+            start(slot)
+        chunk = 4
+        while running:
+            active = [slots[s] for s in sorted(running)]
+            budget = min(chunk, max(e._max_itr - e._launched for e in active))
+            if len(active) >= 2:
+                for _ in range(max(budget, 0)):
+                    runner.step(active)
+                for e in active:
+                    e._host_ctrl.copy_(e.ctrl, non_blocking=True)
+            else:
+                active[0].enqueue(chunk)
+            torch.cuda.current_stream(eng.device).synchronize()
+            for s in sorted(running):
+                e = slots[s]
+                if e.finished():
+                    hist, conv = e.finish()
+                    results[running[s]] = {"hist": hist, "converged": conv, "state": self._state_of(e), "failed": e.failed}
+                    del running[s]
+                    start(s)
+            chunk = min(16, chunk * 2)
 
     def _state_of(self, eng):
         p = eng.fetch_params()

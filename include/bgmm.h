@@ -164,6 +164,21 @@ int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, double* state, 
 double bgmm_set_robust_threshold(double threshold);
 double bgmm_robust_threshold(void);
 
+/* ---- batched restarts (north_star (4); the restart loop `update_posterior` :847-883) ----
+ * One sweep over X for R independent mixtures of K components each (R restarts of the same fit, each with its own state
+ * block): their coefficient rows are stacked into ONE E-GEMM / M-GEMM of R * Kp components (Kp = K rounded up to 8;
+ * R * Kp <= 64) with one softmax per group, so X is read once and the feature fragments are generated once for all R.
+ * `states_host`: HOST array of R device pointers (member state blocks, bgmm_layout(K, D, .)); `super_state`: a zeroed
+ * block of bgmm_layout(R * Kp, D, 1) doubles owned by the caller; `workspace`: bgmm_workspace_doubles(R * Kp, D);
+ * `r_scratch`: [n][R * Kp] float64.  Per member the effect equals bgmm_pass(variant LARGE): STATS of every member that is
+ * not done is overwritten; members whose ctrl.robust is set are redone by their own DIRECT pass; a no-op when every member
+ * is done.  fp64 only. */
+#define BGMM_MAX_BATCH 8
+int bgmm_pass_batched(const void* x, int64_t n, int K, int D, int R, double* const* states_host, double* super_state,
+                      double* workspace, double* r_scratch, void* stream);
+/* largest R (>= 1) that bgmm_pass_batched accepts for this shape (1: batching not available) */
+int bgmm_batch_capacity(int K, int D);
+
 /* 1 when `variant` (BGMM_PASS_SIMPLE / _DMMA / _F32 / _LARGE / _DIRECT) can run this shape, else 0 */
 int bgmm_pass_supported(int K, int D, int dtype, int variant);
 /* the concrete variant BGMM_PASS_AUTO resolves to (has_r_in: statistics of given responsibilities) */
