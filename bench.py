@@ -320,6 +320,187 @@ def parity_multi(world, rank, device, group):
     return out
 
 
+def selection_follows_reference_rule(text):
+    """The '*' marks of the progress text against the reference's rule (:873-883): restart i is kept iff it is the first
+    one or its final VL is STRICTLY larger than the best so far.  -> (ok, index of the kept restart, number of restarts)."""
+    import re
+    best, kept, ok, n = None, -1, True, 0
+    for line in text.split("\n"):
+        vals = re.findall(r"VL: (-?[0-9.eE+-]+|nan|inf|-inf)", line)
+        if not vals:
+            continue
+        vl = float(vals[-1])
+        should = best is None or vl > best
+        if should:
+            best, kept = vl, n
+        ok = ok and (line.rstrip().endswith("*") == should)
+        n += 1
+    return ok, kept, n
+
+
+def bench_restarts(args, world, rank, local_rank, device, group):
+    """`--restarts R` (BASELINE configs[4], C5): R restarts of the same fit, X replicated on every GPU, the restarts spread
+    over the ranks and advanced `bgmm_batch_capacity` at a time by one shared sweep over X (bgmm_pass_batched).
+    One step = one VB iteration (:863-869) of EVERY restart; value = R * N * K / step time.  No data-path collective:
+    the only exchange is the all-gather of the finished restarts' records in `update_posterior` (e2e leg)."""
+    import torch
+    import torch.distributed as dist
+    from bayesml_b200 import _lib, gaussianmixture
+    from bayesml_b200.engine import RestartBatch, VBEngine
+    n_total, d, k, precision, idx = CONFIGS[args.config]
+    assert precision == "float64"
+    warmup = max(args.warmup, 3)
+    r_total = args.restarts
+    mine = [i for i in range(r_total) if i % world == rank]
+    x_dev = synth_device(n_total, d, k, 1234 + idx, 0, device, torch.float64)      # replicated: same seed on every rank
+    lead = VBEngine(k, d, device=device)
+    lead.load_data(x_dev)
+    del x_dev
+    model = gaussianmixture.LearnModel(k, d, seed=0)
+    members = [lead] + [VBEngine(k, d, device=device, fused_comm=False).share_data_from(lead) for _ in mine[1:]]
+    n_sub = int(np.sqrt(n_total))
+    big = 1 << 30
+    for i, e in zip(mine, members):
+        rng = np.random.default_rng([7, i])                      # a different subsample per restart, as `_init_subsampling`
+        m0 = np.empty((k, d)); winv0 = np.empty((k, d, d))
+        for c in range(k):
+            rows = torch.as_tensor(rng.choice(n_total, size=n_sub, replace=False, shuffle=False), device=device)
+            sub = lead.x[rows].cpu().numpy() + lead.center
+            m0[c] = sub.sum(axis=0) / n_sub
+            cen = sub - m0[c]
+            winv0[c] = cen.T @ cen / n_sub * model.hn_nus[c] + np.eye(d) * 1e-5
+        e.set_prior(model.h0_alpha_vec, model.h0_m_vecs, model.h0_kappas, model.h0_nus, model.h0_w_mats_inv,
+                    model._ln_b_h0_w_nus, model._ln_c_h0_alpha)
+        e._alloc_state(args.steps + warmup + 4096)
+        e.set_params(model.hn_alpha_vec, m0, model.hn_kappas, model.hn_nus, winv0)
+        e._max_itr, e._tol, e._launched = big, 0.0, 0
+    cap = int(lead.lib.bgmm_batch_capacity(k, d)) if not args.no_batch else 1
+    batches = [members[i:i + cap] for i in range(0, len(members), cap)] if cap >= 2 else [[e] for e in members]
+    runner = RestartBatch(lead, cap) if cap >= 2 else None
+
+    def sweep(b, ev=None):
+        if ev is not None:
+            ev[0].record()
+        if len(b) >= 2:
+            runner.pass_only(b)
+        else:
+            b[0].pass_only()
+        if ev is not None:
+            ev[1].record()
+        for e in b:
+            e._small(_lib.SMALL_ITERATE, big, 0.0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(warmup):
+        for b in batches:
+            sweep(b)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in batches]
+           for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sum(e.kernel_launches for e in members)
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        for bi, b in enumerate(batches):
+            sweep(b, evs[s][bi])
+    e1.record()
+    launches = sum(e.kernel_launches for e in members) - launches0
+    barrier()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    pass_ms = torch.tensor([np.mean([sum(a.elapsed_time(b) for a, b in step) for step in evs])], device=device,
+                           dtype=torch.float64)                   # all sweeps of one step on this rank
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pass_ms, op=dist.ReduceOp.MAX)
+    n_tail = int(1500.0 / max(float(ms_total.item()) / args.steps, 1e-3)) + 1
+    for _ in range(min(n_tail, 2000)):
+        for b in batches:
+            sweep(b)
+    torch.cuda.synchronize(device)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total, pass_ms = float(ms_total.item()), float(pass_ms.item())
+    ms_per_step = ms_total / args.steps
+    value = r_total * n_total * k / (ms_per_step * 1e-3)
+    hist_ok = True
+    for e in members:
+        h = e.state[e.off["vlhist"]: e.off["vlhist"] + warmup + args.steps].cpu().numpy()
+        hist_ok = hist_ok and bool(np.all(np.isfinite(h)) and np.all(np.diff(h[1:]) >= -1e-9 * np.abs(h[1:-1])))
+    tracked = load_peaks()
+    r_max = -(-r_total // world)
+    flops = r_max * alg_flops_per_iter(n_total, d, k)            # the busiest rank's restarts
+    ach = flops / (pass_ms * 1e-3) / 1e12
+    executed = r_max * n_total * 4 * k * (1 + d + d * (d + 1) // 2)      # 2 GEMMs x 2 flops x K x P per sample
+    roofline = {"bound": "tensor", "achieved": ach, "peak": tracked["fp64_tflops"], "unit": "TFLOP/s",
+                "frac": ach / tracked["fp64_tflops"], "traffic": None,
+                "kernel": "bgmm::e_large_kernel + bgmm::m_large_kernel (batched: %d restarts per sweep)" % cap,
+                "kernel_ms": pass_ms, "kernel_share_of_step": pass_ms / ms_per_step,
+                "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": n_total * d * 8 * len(batches),
+                "executed_flops_per_launch": executed,
+                "executed_frac_of_pipe": executed / (pass_ms * 1e-3) / 1e12 / tracked["fp64_tflops"],
+                "peak_source": "FP64 tensor pipe (DMMA.8x8x4), " + tracked["source"]}
+
+    # e2e: the public API with the restarts spread over the ranks; selection checked against the reference's rule
+    e2e = None
+    sel = None
+    if not args.no_e2e:
+        for e in members:
+            del e
+        del members, batches, runner, lead
+        torch.cuda.empty_cache()
+        x_host_t = torch.empty((n_total, d), dtype=torch.float64).pin_memory()
+        x_host_t.copy_(synth_device(n_total, d, k, 1234 + idx, 0, device, torch.float64))
+        x_host = x_host_t.numpy()
+        lm = gaussianmixture.LearnModel(k, d, seed=0, device=device, restart_group=group)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            lm.update_posterior(x_host, max_itr=1, num_init=min(r_total, 2 * world), tolerance=0.0)      # warm-up call
+        with contextlib.redirect_stdout(buf), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            barrier()
+            t0 = time.perf_counter()
+            lm.update_posterior(x_host, max_itr=args.steps, num_init=r_total, tolerance=0.0)
+            _ = float(lm.vl)
+            torch.cuda.synchronize(device)
+            dt = time.perf_counter() - t0
+        dt_t = torch.tensor([dt], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+        dt = float(dt_t.item())
+        ok, kept, n_seen = selection_follows_reference_rule(buf.getvalue())
+        sel = {"follows_reference_rule": bool(ok and n_seen == r_total), "kept_restart": kept, "restarts": n_seen}
+        e2e = {"value": r_total * n_total * k * args.steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(x_host.nbytes / args.steps), "d2h_bytes_per_step": 0, "seconds": dt,
+               "host_buffer": "pinned",
+               "api": f"LearnModel(restart_group=...).update_posterior(x_host, max_itr=steps, num_init={r_total}, tolerance=0.0): "
+                      "upload + host initialisations + all restarts + all-gather of their records + selection + final E-step"}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: GMM VB N={n_total} D={d} K={k} float64, num_init={r_total} restarts spread over "
+                                   f"{world} GPU(s) (X replicated), {cap} restarts per shared sweep; one step = one VB iteration "
+                                   f"of every restart",
+                       "l2": f"X resident in HBM, {n_total * d * 8 / 1e6:.0f} MB per sweep (> 126 MB L2), no flush needed",
+                       "init": "subsampling-style, a different subsample per restart; default priors; tolerance=0.0"},
+            "restart_iters_per_s": r_total * 1e3 / ms_per_step, "elbo_finite_and_monotone": hist_ok,
+            "roofline": roofline, "e2e": e2e, "selection": sel, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,6 +512,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity block (world > 1)")
+    ap.add_argument("--restarts", type=int, default=0,
+                    help="restart mode (C5): this many restarts spread over the GPUs, X replicated (default 64 for --config c5)")
+    ap.add_argument("--no-batch", action="store_true", help="restart mode: one sweep per restart (no bgmm_pass_batched)")
     ap.add_argument("--variant", default="auto", choices=["auto", "simple", "dmma", "f32", "large"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -353,6 +537,11 @@ def main():
         dist.init_process_group("nccl", device_id=device)
         group = dist.group.WORLD
     warmup = max(args.warmup, 3)
+    if args.restarts == 0 and args.config == "c5":
+        args.restarts = 64
+    if args.restarts > 1:
+        bench_restarts(args, world, rank, local_rank, device, group)
+        return
 
     n_total, d, k, precision, idx = CONFIGS[args.config]
     if args.scaling == "weak":
