@@ -61,6 +61,10 @@ def load():
     lib.bgmm_pass_batched.argtypes = [vp, i64, i32, i32, i32, ctypes.POINTER(vp), vp, vp, vp, vp]
     lib.bgmm_batch_capacity.restype = i32
     lib.bgmm_batch_capacity.argtypes = [i32, i32]
+    lib.bgmm_pred_logdensity.restype = i32
+    lib.bgmm_pred_logdensity.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp]
+    lib.bgmm_dirichlet1.restype = i32
+    lib.bgmm_dirichlet1.argtypes = [vp, i64, i32, ctypes.c_uint64, i64, vp]
     lib.bgmm_pass_supported.restype = i32
     lib.bgmm_pass_supported.argtypes = [i32, i32, i32, i32]
     lib.bgmm_pass_resolve.restype = i32

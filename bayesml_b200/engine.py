@@ -309,7 +309,10 @@ class VBEngine:
         with torch.cuda.device(self.device):
             self._alloc_state(self._max_itr + 1)
             if r_init is not None:
-                r_dev = torch.as_tensor(np.ascontiguousarray(r_init, dtype=np.float64)).to(self.device)
+                if isinstance(r_init, torch.Tensor):
+                    r_dev = r_init.to(self.device, dtype=torch.float64).contiguous()
+                else:
+                    r_dev = torch.as_tensor(np.ascontiguousarray(r_init, dtype=np.float64)).to(self.device)
                 self._pass(r_in=r_dev, force=1)
             else:
                 self._pass()
@@ -410,6 +413,34 @@ class VBEngine:
         # refine_smats() recomputes it in the two-pass centred form from the materialised r if that is ever wanted
         out["centred"] = bool(host[self.off["stats"] + self.K * self.off["pitch"] + 2] > 0.5)
         return out
+
+    def pred_log_density(self, ck, hk, nuk):
+        """ln of the predictive mixture-of-Student-t density of every resident row (bgmm_pred_logdensity): the quadratic
+        forms come from one bgmm_pass with the parameter set loaded by set_params (Lambda_k = p_lambda_mats[k]).
+        -> numpy array [n_local]."""
+        K, n = self.K, self.n_local
+        with torch.cuda.device(self.device):
+            lnrho = torch.empty((n, K), dtype=torch.float64, device=self.device)
+            self.pass_only(lnrho_out=lnrho, force=1)            # rows are independent: no cross-rank exchange
+            cur = int(self.ctrl[_lib.CTRL_CUR].item())
+            acst = self._pview(cur, "acst", K)
+            consts = torch.as_tensor(np.ascontiguousarray(np.stack([ck, hk, nuk]), dtype=np.float64)).to(self.device)
+            out = torch.empty(n, dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.bgmm_pred_logdensity(lnrho.data_ptr(), n, K, acst.data_ptr(), consts[0].data_ptr(),
+                                                     consts[1].data_ptr(), consts[2].data_ptr(), out.data_ptr(),
+                                                     self._stream()), "bgmm_pred_logdensity")
+            self.kernel_launches += 1
+            return out.cpu().numpy()
+
+    def draw_dirichlet1(self, seed, row_offset=0):
+        """(n_local, K) responsibilities ~ Dirichlet(1_K) drawn on the device (bgmm_dirichlet1; Philox, keyed by the
+        global row index) -> device tensor."""
+        with torch.cuda.device(self.device):
+            r = torch.empty((self.n_local, self.K), dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.bgmm_dirichlet1(r.data_ptr(), self.n_local, self.K, int(seed) & (2 ** 64 - 1), int(row_offset),
+                                                self._stream()), "bgmm_dirichlet1")
+            self.kernel_launches += 1
+        return r
 
     def refine_smats(self):
         """s_mats of the last final_pass in the reference's two-pass centred form (:730-732): one more sweep over X with

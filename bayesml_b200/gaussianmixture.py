@@ -10,7 +10,9 @@ reference's), restart bookkeeping and the predictive parameters.
 
 Additive, defaulted options (do not exist in the reference): `device`, `precision` ('float64' | 'float32'),
 `process_group` (torch.distributed group: rows of x are this rank's shard; statistics are all-reduced),
-`restart_group` (torch.distributed group: x is replicated and the `num_init` restarts are spread over the ranks).
+`restart_group` (torch.distributed group: x is replicated and the `num_init` restarts are spread over the ranks),
+`device_init` (draw the 'random_responsibility' initial responsibilities on the device: same distribution, NOT numpy's
+random stream), and the method `pred_log_density(x)` (batch log predictive density on the device).
 """
 import warnings
 
@@ -66,7 +68,8 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
     """
 
     def __init__(self, c_num_classes, c_degree, h0_alpha_vec=None, h0_m_vecs=None, h0_kappas=None, h0_nus=None,
-                 h0_w_mats=None, seed=None, *, device=None, precision="float64", process_group=None, restart_group=None):
+                 h0_w_mats=None, seed=None, *, device=None, precision="float64", process_group=None, restart_group=None,
+                 device_init=False):
         self.c_degree = _check.pos_int(c_degree, 'c_degree', ParameterFormatError)
         self.c_num_classes = _check.pos_int(c_num_classes, 'c_num_classes', ParameterFormatError)
         self.rng = np.random.default_rng(seed)
@@ -78,6 +81,7 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
                 f"bayesml_b200.gaussianmixture supports c_degree <= {MAX_DEGREE} (got {D}); there is no CPU fallback")
         self._device, self._precision, self._group = device, precision, process_group
         self._restart_group = restart_group
+        self._device_init = bool(device_init)
         self._engine_obj = None
         self._extra_engines = []
 
@@ -325,6 +329,11 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         """Dirichlet(1) responsibilities per row (:734-735); the statistics are computed on the device.  With a
         process group every rank draws the global stream and keeps the rows of its shard."""
         n_total = n if n_total is None else n_total
+        if self._device_init:
+            # one 64-bit draw from self.rng keys a counter-based generator on the device (bgmm_dirichlet1): the rows of a
+            # shard are those of the global draw, whatever the sharding; the host stream advances by ONE value per restart
+            seed = int(self.rng.integers(0, 2 ** 63 - 1))
+            return self._engine().draw_dirichlet1(seed, offset)
         return self.rng.dirichlet(np.ones(self.c_num_classes), n_total)[offset:offset + n]
 
     # ------------------------------------------------------------------ the fit (:802-896)
@@ -364,7 +373,10 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
                 self._init_subsampling(x, offset, n_total)
             elif init_type == 'random_responsibility':
                 r_init = self._init_random_responsibility(x.shape[0], offset, n_total)
-                r_init = r_init.copy() if keep_r else None    # copy: do not keep the (n_total, K) draw alive through a view
+                if not keep_r:
+                    r_init = None
+                elif isinstance(r_init, np.ndarray):
+                    r_init = r_init.copy()                     # do not keep the (n_total, K) draw alive through a view
             else:
                 raise ValueError(
                     f'init_type={init_type} is unsupported. '
@@ -720,6 +732,29 @@ class LearnModel(base.Posterior, base.PredictiveMixin):
         scale = self.hn_kappas * self.p_nus / (self.hn_kappas + 1)
         self.p_lambda_mats[:] = scale[:, None, None] * self.hn_w_mats
         return self
+
+    def pred_log_density(self, x):
+        """ln p(x_new | x^n) of every row of x under the predictive distribution, the mixture of Student-t distributions
+        `sum_k p_pi_k St(x | p_mu_k, p_lambda_k, p_nu_k)` (reference docs: gaussianmixture/__init__.py:86-97).
+
+        Extension (the reference only evaluates this density one point at a time, inside `make_prediction(loss="0-1")`,
+        :1086-1099): the quadratic forms run through the same device kernels as the E-step, the Student-t / log-sum-exp
+        epilogue in bgmm_pred_logdensity.  Uses the current p_* parameters (`calc_pred_dist()` first, as for
+        `make_prediction`).  -> numpy.ndarray, shape (N,)."""
+        x = self._check_x(x)
+        K, D = self.c_num_classes, self.c_degree
+        if K > 64:
+            raise ParameterFormatError("pred_log_density supports c_num_classes <= 64")
+        eng = self._engine()
+        eng.load_data(x)
+        self._push_prior(eng)
+        # a parameter set whose E[Lambda_k] = nu W equals p_lambda_mats[k]: nu = D + 2, W^-1 = nu * p_lambda^-1
+        nu = np.full(K, D + 2.0)
+        winv = nu[:, None, None] * np.linalg.inv(self.p_lambda_mats)
+        eng.set_params(np.ones(K), self.p_mu_vecs, np.ones(K), nu, winv)
+        ck = (np.log(self.p_pi_vec) + gammaln((self.p_nus + D) / 2.0) - gammaln(self.p_nus / 2.0)
+              + 0.5 * np.linalg.slogdet(self.p_lambda_mats)[1] - D / 2.0 * np.log(self.p_nus * np.pi))
+        return eng.pred_log_density(ck, (self.p_nus + D) / 2.0, self.p_nus)
 
     def make_prediction(self, loss="squared"):
         """Predict a new data point: mixture mean ("squared") or the highest weighted mode ("0-1") (:1072-1102)."""

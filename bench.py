@@ -512,6 +512,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity block (world > 1)")
+    ap.add_argument("--n", type=int, default=0, help="diagnostics: override the row count of the config (not a bench line)")
     ap.add_argument("--restarts", type=int, default=0,
                     help="restart mode (C5): this many restarts spread over the GPUs, X replicated (default 64 for --config c5)")
     ap.add_argument("--no-batch", action="store_true", help="restart mode: one sweep per restart (no bgmm_pass_batched)")
@@ -544,6 +545,8 @@ def main():
         return
 
     n_total, d, k, precision, idx = CONFIGS[args.config]
+    if args.n > 0:
+        n_total = args.n
     if args.scaling == "weak":
         n_total = n_total * world
     n_local = n_total // world + (1 if rank < n_total % world else 0)

@@ -195,6 +195,20 @@ int bgmm_pass_resolve(int K, int D, int dtype, int variant, int has_r_in);
 int bgmm_small(int K, int D, double* state, int mode, int max_itr, double tol, int hist_len, const void* comm_desc,
                void* stream);
 
+/* ---- either side of the loop ----
+ * bgmm_pred_logdensity: out[n] = ln sum_k exp(ck[k] - hk[k] * log1p(Delta2_nk / nuk[k])), the log predictive density of the
+ *   mixture of Student-t distributions (/root/reference/bayesml/gaussianmixture/__init__.py:86-97; the reference evaluates
+ *   it one point at a time through scipy.stats.multivariate_t, _gaussianmixture.py:1086-1099).  Delta2_nk is recovered from
+ *   lnrho[n][K] (bgmm_pass output for a parameter set with Lambda_k = p_lambda_mats[k]) and that set's constants acst[K]
+ *   (state: params[cur] + BGMM_P_ACST): lnrho = acst - Delta2 / 2.  Caller supplies (device pointers)
+ *   ck = ln p_pi + lnGamma((nu+D)/2) - lnGamma(nu/2) + ln|Lambda|/2 - D/2 ln(nu pi),  hk = (nu + D)/2,  nuk = p_nus.  K <= 64. */
+int bgmm_pred_logdensity(const double* lnrho, int64_t n, int K, const double* acst, const double* ck, const double* hk,
+                         const double* nuk, double* out, void* stream);
+/* bgmm_dirichlet1: r_out[n][K] ~ Dirichlet(1_K) per row (`_init_random_responsibility` :734-735 on the device).
+ *   Philox4x32-10 keyed by `seed`, counter = (row_offset + local row, pair index): independent of the sharding.  This is
+ *   NOT numpy's PCG64 / ziggurat stream: same distribution, different numbers (opt-in, `device_init=True`). */
+int bgmm_dirichlet1(double* r_out, int64_t n, int K, uint64_t seed, int64_t row_offset, void* stream);
+
 /* ---- multi-GPU exchange over NVLink peer memory (no reference counterpart: the reference is single-process) ----
  * Row-sharded fit: the per-iteration all-reduce of state.STATS is fused into bgmm_small.  Every rank owns an exchange
  * block  [2][stats_len] doubles | [2][BGMM_MAX_RANKS] uint64 stamps  allocated by bgmm_comm_alloc (cudaMalloc, zeroed)

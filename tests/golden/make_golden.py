@@ -116,6 +116,15 @@ def run_case(name, x, k, d, seed, fit_kwargs, prior_kwargs=None, latent_x=None, 
     for f in ("p_pi_vec", "p_mu_vecs", "p_nus", "p_lambda_mats"):
         payload["pred_" + f] = np.array(getattr(model, f))
     if latent_x is not None:
+        # log predictive density of the rows of latent_x: the mixture of Student-t distributions of
+        # bayesml/gaussianmixture/__init__.py:86-97, evaluated with the function the reference itself calls for that
+        # density (scipy.stats.multivariate_t, _gaussianmixture.py:1093) on the reference's own p_* parameters
+        from scipy.special import logsumexp
+        from scipy.stats import multivariate_t
+        comp = np.stack([np.log(model.p_pi_vec[j])
+                         + multivariate_t.logpdf(latent_x, loc=model.p_mu_vecs[j], shape=np.linalg.inv(model.p_lambda_mats[j]),
+                                                 df=model.p_nus[j]) for j in range(k)], axis=1)
+        payload["pred_logdens"] = logsumexp(comp, axis=1)
         payload["latent_x"] = latent_x
         payload["latent_onehot"] = model.estimate_latent_vars(latent_x, loss="0-1")
         payload["latent_r"] = np.array(model.estimate_latent_vars(latent_x, loss="squared"))
