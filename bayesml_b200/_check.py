@@ -49,6 +49,16 @@ def float_vec(val, val_name, exception_class):
     raise exception_class(val_name + " must be a 1-dimensional numpy.ndarray.")
 
 
+def float_vec_sum_1(val, val_name, exception_class):
+    """1-dimensional numeric ndarray whose elements sum to 1 within sqrt(eps) (reference _check.py:219-225)."""
+    if type(val) is np.ndarray and val.ndim == 1 and abs(val.sum() - 1.0) <= np.sqrt(np.finfo(np.float64).eps):
+        if np.issubdtype(val.dtype, np.integer):
+            return val.astype(float)
+        if np.issubdtype(val.dtype, np.floating):
+            return val
+    raise exception_class(val_name + " must be a 1-dimensional numpy.ndarray, and the sum of its elements must equal to 1.")
+
+
 def float_vecs(val, val_name, exception_class):
     """Numeric ndarray with ndim >= 1 (reference _check.py:203-209)."""
     if type(val) is np.ndarray and val.ndim >= 1:

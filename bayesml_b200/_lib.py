@@ -65,6 +65,8 @@ def load():
     lib.bgmm_pred_logdensity.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp, vp]
     lib.bgmm_dirichlet1.restype = i32
     lib.bgmm_dirichlet1.argtypes = [vp, i64, i32, ctypes.c_uint64, i64, vp]
+    lib.bgmm_gen_sample.restype = i32
+    lib.bgmm_gen_sample.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, ctypes.c_uint64, i64, vp]
     lib.bgmm_pass_supported.restype = i32
     lib.bgmm_pass_supported.argtypes = [i32, i32, i32, i32]
     lib.bgmm_pass_resolve.restype = i32

@@ -22,6 +22,53 @@ def _load_dict(filename):
     return obj
 
 
+class Generative(metaclass=ABCMeta):
+    """Data generative model: parameters, their prior hyperparameters h_*, sampling (reference base.py:8-137)."""
+
+    @abstractmethod
+    def set_h_params(self): ...
+
+    @abstractmethod
+    def get_h_params(self): ...
+
+    @abstractmethod
+    def gen_params(self): ...
+
+    @abstractmethod
+    def set_params(self): ...
+
+    @abstractmethod
+    def get_params(self): ...
+
+    @abstractmethod
+    def gen_sample(self): ...
+
+    @abstractmethod
+    def save_sample(self): ...
+
+    def save_h_params(self, filename):
+        """Pickle the dict returned by get_h_params() (reference base.py:17-31)."""
+        _dump(self.get_h_params(), filename)
+
+    def load_h_params(self, filename):
+        """Positional load of a pickled hyperparameter dict into set_h_params (reference base.py:33-57)."""
+        self.set_h_params(*_load_dict(filename).values())
+        return self
+
+    def save_params(self, filename):
+        """Pickle the dict returned by get_params() (reference base.py:68-83)."""
+        _dump(self.get_params(), filename)
+
+    def load_params(self, filename):
+        """Positional load of a pickled parameter dict into set_params (reference base.py:85-103)."""
+        with open(filename, "rb") as f:
+            obj = pickle.load(f)
+        if type(obj) is not dict:
+            raise ParameterFormatError(filename + " must be a pickled python dictionary obtained by ``GenModel.save_params()``")
+        self.set_params(*obj.values())
+        return self
+
+
 class Posterior(metaclass=ABCMeta):
     """Posterior over the parameters: h0_* (initial) and hn_* (updated) hyperparameters."""
 

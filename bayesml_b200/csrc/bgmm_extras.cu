@@ -79,9 +79,63 @@ __global__ void __launch_bounds__(256) dirichlet1_kernel(double* __restrict__ r,
     for (int j = 0; j < K; ++j) out[j] *= inv;
 }
 
+// GenModel.gen_sample on the device (/root/reference/bayesml/gaussianmixture/_gaussianmixture.py:241-264: a Python loop,
+// one `rng.choice` + one `rng.multivariate_normal` per sample): one thread per sample, class from the inverse CDF of pi,
+// x = mu_z + L_z eps with L_z = chol(Lambda_z^-1) and Box-Muller normals from Philox keyed by (seed, global row).
+__global__ void __launch_bounds__(128) gen_sample_kernel(double* __restrict__ x, int32_t* __restrict__ z, const int64_t n,
+                                                         const int K, const int D, const double* __restrict__ cdf,
+                                                         const double* __restrict__ mu, const double* __restrict__ chol,
+                                                         const unsigned long long seed, const int64_t row_offset) {
+    extern __shared__ double eps_s[];                           // [128][D + 1]: this thread's standard normals
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long g = (unsigned long long)(row_offset + i);
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    double* eps = eps_s + threadIdx.x * (D + 1);
+    const uint4 v0 = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), 0u, 0x47454e53u), key);
+    const double u = uniform_open(v0.x, v0.y);
+    int k = 0;
+    while (k < K - 1 && u > cdf[k]) ++k;
+    for (int j = 0; j < D; j += 2) {
+        const uint4 v = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(1 + (j >> 1)), 0x47454e53u), key);
+        const double rad = sqrt(-2.0 * log(uniform_open(v.x, v.y))), ang = 6.283185307179586476925286766559 * uniform_open(v.z, v.w);
+        double sn, cs;
+        sincos(ang, &sn, &cs);
+        eps[j] = rad * cs;
+        if (j + 1 < D) eps[j + 1] = rad * sn;
+    }
+    const double* L = chol + (int64_t)k * D * D;
+    const double* m = mu + (int64_t)k * D;
+    for (int a = 0; a < D; ++a) {
+        double acc = m[a];
+        for (int b = 0; b <= a; ++b) acc = fma(L[a * D + b], eps[b], acc);
+        x[i * D + a] = acc;
+    }
+    z[i] = k;
+}
+
 }  // namespace bgmm
 
 using namespace bgmm;
+
+extern "C" int bgmm_gen_sample(double* x_out, int32_t* z_out, int64_t n, int K, int D, const double* cdf, const double* mu,
+                               const double* chol, uint64_t seed, int64_t row_offset, void* stream) {
+    if (n < 0 || K <= 0 || D <= 0 || D > 256 || row_offset < 0 || cdf == nullptr || mu == nullptr || chol == nullptr ||
+        ((x_out == nullptr || z_out == nullptr) && n > 0)) {
+        set_error("bgmm_gen_sample: bad argument (n=%lld K=%d D=%d; D <= 256)", (long long)n, K, D);
+        return BGMM_EINVAL;
+    }
+    if (n == 0) return BGMM_OK;
+    const size_t smem = sizeof(double) * 128 * (size_t)(D + 1);
+    if (smem > 48 * 1024) {
+        int rc = check_cuda(cudaFuncSetAttribute(gen_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                            "cudaFuncSetAttribute(gen_sample_kernel)");
+        if (rc) return rc;
+    }
+    gen_sample_kernel<<<(unsigned)((n + 127) / 128), 128, smem, (cudaStream_t)stream>>>(x_out, z_out, n, K, D, cdf, mu, chol,
+                                                                                        (unsigned long long)seed, row_offset);
+    return check_cuda(cudaGetLastError(), "gen_sample_kernel launch");
+}
 
 extern "C" int bgmm_pred_logdensity(const double* lnrho, int64_t n, int K, const double* acst, const double* ck,
                                     const double* hk, const double* nuk, double* out, void* stream) {

@@ -25,12 +25,177 @@ from scipy.stats import wishart as ss_wishart
 from . import _check, base
 from ._exceptions import CriteriaError, DataFormatError, ParameterFormatError, ResultWarning
 
-__all__ = ["LearnModel"]
+__all__ = ["GenModel", "LearnModel"]
 
 MAX_DEGREE = 160            # limit of the device path: bgmm_small keeps a D x D matrix in shared memory
 
 _HN_NAMES = ("hn_alpha_vec", "hn_m_vecs", "hn_kappas", "hn_nus", "hn_w_mats", "hn_w_mats_inv")
 _VL_NAMES = ("_vl_p_x", "_vl_p_z", "_vl_p_pi", "_vl_p_mu_lambda", "_vl_q_z", "_vl_q_pi", "_vl_q_mu_lambda", "vl")
+
+
+class GenModel(base.Generative):
+    """The stochastic data generative model (reference :19-366): pi ~ Dir(h_alpha), (mu_k, Lambda_k) ~ Gauss-Wishart,
+    z ~ Cat(pi), x ~ N(mu_z, Lambda_z^-1).  Same constructor, parameters and methods as the reference class.
+
+    `gen_sample(sample_size)` is the reference's per-sample loop (`rng.choice` + `rng.multivariate_normal`, :259-263: the
+    identical random stream, 116 us per sample); `gen_sample(sample_size, device="cuda:0")` draws the same distribution on the
+    device in one kernel (bgmm_gen_sample; counter-based Philox, NOT numpy's stream) and can leave the sample there
+    (`as_numpy=False`) for `LearnModel.update_posterior` / `bench.py`."""
+
+    def __init__(self, c_num_classes, c_degree, pi_vec=None, mu_vecs=None, lambda_mats=None, h_alpha_vec=None,
+                 h_m_vecs=None, h_kappas=None, h_nus=None, h_w_mats=None, seed=None):
+        self.c_degree = _check.pos_int(c_degree, 'c_degree', ParameterFormatError)
+        self.c_num_classes = _check.pos_int(c_num_classes, 'c_num_classes', ParameterFormatError)
+        self.rng = np.random.default_rng(seed)
+        K, D = self.c_num_classes, self.c_degree
+        self.pi_vec = np.ones(K) / K
+        self.mu_vecs = np.zeros((K, D))
+        self.lambda_mats = np.tile(np.eye(D), (K, 1, 1))
+        self.h_alpha_vec = np.ones(K) / 2
+        self.h_m_vecs = np.zeros((K, D))
+        self.h_kappas = np.ones(K)
+        self.h_nus = np.ones(K) * D
+        self.h_w_mats = np.tile(np.eye(D), (K, 1, 1))
+        self.set_params(pi_vec, mu_vecs, lambda_mats)
+        self.set_h_params(h_alpha_vec, h_m_vecs, h_kappas, h_nus, h_w_mats)
+
+    def get_constants(self):
+        """{"c_num_classes", "c_degree"} (:87-96)."""
+        return {"c_num_classes": self.c_num_classes, "c_degree": self.c_degree}
+
+    def _last_dim(self, arr, name, what="self.c_degree"):
+        if arr.shape[-1] != self.c_degree:
+            raise ParameterFormatError(f"{name}.shape[-1] must coincide with {what}: "
+                                       f"{name}.shape[-1] = {arr.shape[-1]}, self.c_degree = {self.c_degree}")
+
+    def set_h_params(self, h_alpha_vec=None, h_m_vecs=None, h_kappas=None, h_nus=None, h_w_mats=None):
+        """Set the hyperparameters of the prior (:98-156)."""
+        if h_alpha_vec is not None:
+            _check.pos_floats(h_alpha_vec, 'h_alpha_vec', ParameterFormatError)
+            self.h_alpha_vec[:] = h_alpha_vec
+        if h_m_vecs is not None:
+            _check.float_vecs(h_m_vecs, 'h_m_vecs', ParameterFormatError)
+            self._last_dim(h_m_vecs, 'h_m_vecs')
+            self.h_m_vecs[:] = h_m_vecs
+        if h_kappas is not None:
+            _check.pos_floats(h_kappas, 'h_kappas', ParameterFormatError)
+            self.h_kappas[:] = h_kappas
+        if h_nus is not None:
+            _check.pos_floats(h_nus, 'h_nus', ParameterFormatError)
+            if np.any(h_nus <= self.c_degree - 1):
+                raise ParameterFormatError("All the values of h_nus must be greater than self.c_degree - 1: "
+                                           f"self.c_degree = {self.c_degree}, h_nus = {h_nus}")
+            self.h_nus[:] = h_nus
+        if h_w_mats is not None:
+            _check.pos_def_sym_mats(h_w_mats, 'h_w_mats', ParameterFormatError)
+            self._last_dim(h_w_mats, 'h_w_mats')
+            self.h_w_mats[:] = h_w_mats
+        return self
+
+    def get_h_params(self):
+        """Live references to the hyperparameters (:158-172)."""
+        return {"h_alpha_vec": self.h_alpha_vec, "h_m_vecs": self.h_m_vecs, "h_kappas": self.h_kappas,
+                "h_nus": self.h_nus, "h_w_mats": self.h_w_mats}
+
+    def gen_params(self):
+        """Draw pi, Lambda_k, mu_k from the prior with the reference's random stream (:174-181)."""
+        self.pi_vec[:] = self.rng.dirichlet(self.h_alpha_vec)
+        for k in range(self.c_num_classes):
+            self.lambda_mats[k] = ss_wishart.rvs(df=self.h_nus[k], scale=self.h_w_mats[k], random_state=self.rng)
+            self.mu_vecs[k] = self.rng.multivariate_normal(mean=self.h_m_vecs[k],
+                                                           cov=np.linalg.inv(self.h_kappas[k] * self.lambda_mats[k]))
+        return self
+
+    def set_params(self, pi_vec=None, mu_vecs=None, lambda_mats=None):
+        """Set the parameters of the sampling distribution (:183-221)."""
+        if pi_vec is not None:
+            _check.float_vec_sum_1(pi_vec, 'pi_vec', ParameterFormatError)
+            if pi_vec.shape[0] != self.c_num_classes:
+                raise ParameterFormatError("pi_vec.shape[0] must coincide with self.c_num_classes: "
+                                           f"pi_vec.shape[0] = {pi_vec.shape[0]}, self.c_num_classes = {self.c_num_classes}")
+            self.pi_vec[:] = pi_vec
+        if mu_vecs is not None:
+            _check.float_vecs(mu_vecs, 'mu_vecs', ParameterFormatError)
+            self._last_dim(mu_vecs, 'mu_vecs')
+            self.mu_vecs[:] = mu_vecs
+        if lambda_mats is not None:
+            _check.pos_def_sym_mats(lambda_mats, 'lambda_mats', ParameterFormatError)
+            self._last_dim(lambda_mats, 'lambda_mats')
+            self.lambda_mats[:] = lambda_mats
+        return self
+
+    def get_params(self):
+        """Live references to pi_vec, mu_vecs, lambda_mats (:223-231)."""
+        return {"pi_vec": self.pi_vec, "mu_vecs": self.mu_vecs, "lambda_mats": self.lambda_mats}
+
+    def gen_sample(self, sample_size, *, device=None, as_numpy=True):
+        """Generate a sample (:233-264) -> (x (sample_size, c_degree) float64, z (sample_size, c_num_classes) one-hot int).
+
+        device=None: the reference's loop and random stream.  device="cuda:i": one device kernel (same distribution, its own
+        counter-based stream seeded from self.rng); with as_numpy=False, x and the class indices z (int32, NOT one-hot) stay
+        on the device as torch tensors."""
+        _check.pos_int(sample_size, 'sample_size', DataFormatError)
+        K, D = self.c_num_classes, self.c_degree
+        cov = np.linalg.inv(self.lambda_mats)
+        if device is None:
+            z = np.zeros((sample_size, K), dtype=int)
+            x = np.empty((sample_size, D))
+            for i in range(sample_size):
+                k = self.rng.choice(K, p=self.pi_vec)
+                z[i, k] = 1
+                x[i] = self.rng.multivariate_normal(mean=self.mu_vecs[k], cov=cov[k])
+            return x, z
+        import torch
+        from . import _lib
+        lib = _lib.load()
+        dev = torch.device(device)
+        seed = int(self.rng.integers(0, 2 ** 63 - 1))
+        with torch.cuda.device(dev):
+            consts = [torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+                      for a in (np.cumsum(self.pi_vec), self.mu_vecs, np.linalg.cholesky(cov))]
+            x_dev = torch.empty((sample_size, D), dtype=torch.float64, device=dev)
+            z_dev = torch.empty(sample_size, dtype=torch.int32, device=dev)
+            _lib.check(lib.bgmm_gen_sample(x_dev.data_ptr(), z_dev.data_ptr(), sample_size, K, D, consts[0].data_ptr(),
+                                           consts[1].data_ptr(), consts[2].data_ptr(), seed, 0,
+                                           torch.cuda.current_stream(dev).cuda_stream), "bgmm_gen_sample")
+            if not as_numpy:
+                torch.cuda.current_stream(dev).synchronize()
+                return x_dev, z_dev
+            return x_dev.cpu().numpy(), np.eye(K, dtype=int)[z_dev.cpu().numpy()]
+
+    def save_sample(self, filename, sample_size):
+        """gen_sample, then np.savez_compressed(filename, x=x, z=z) (:266-283)."""
+        x, z = self.gen_sample(sample_size)
+        np.savez_compressed(filename, x=x, z=z)
+
+    def visualize_model(self, sample_size=100):
+        """Print the parameters and plot a sample with the component densities for c_degree <= 2 (:285-366); needs matplotlib."""
+        if self.c_degree > 2:
+            raise ParameterFormatError("if c_degree > 2, it is impossible to visualize the model by this function.")
+        print(f"pi_vec:\n {self.pi_vec}")
+        print(f"mu_vecs:\n {self.mu_vecs}")
+        print(f"lambda_mats:\n {self.lambda_mats}")
+        import matplotlib.pyplot as plt
+        from scipy.stats import multivariate_normal as ss_mvn
+        cov = np.linalg.inv(self.lambda_mats)
+        sample, _ = self.gen_sample(sample_size)
+        fig, axes = plt.subplots()
+        lo, hi = sample.min(axis=0), sample.max(axis=0)
+        lo, hi = lo - (hi - lo) * 0.25, hi + (hi - lo) * 0.25
+        if self.c_degree == 1:
+            grid = np.linspace(lo[0], hi[0], 1000)
+            dens = sum(self.pi_vec[k] * ss_mvn.pdf(grid, self.mu_vecs[k], cov[k]) for k in range(self.c_num_classes))
+            axes.plot(grid, dens)
+            axes.hist(sample, density=True)
+            axes.set_xlabel("x"); axes.set_ylabel("Density or frequency")
+        else:
+            gx, gy = np.meshgrid(np.linspace(lo[0], hi[0], 1000), np.linspace(lo[1], hi[1], 1000))
+            grid = np.stack([gx, gy], axis=-1)
+            dens = sum(self.pi_vec[k] * ss_mvn.pdf(grid, self.mu_vecs[k], cov[k]) for k in range(self.c_num_classes))
+            axes.contourf(gx, gy, dens, cmap='Blues')
+            axes.scatter(sample[:, 0], sample[:, 1], color='tab:orange')
+            axes.set_xlabel("x[0]"); axes.set_ylabel("x[1]")
+        plt.show()
 
 
 class _LazyDeviceArray:

@@ -208,6 +208,12 @@ int bgmm_pred_logdensity(const double* lnrho, int64_t n, int K, const double* ac
  *   Philox4x32-10 keyed by `seed`, counter = (row_offset + local row, pair index): independent of the sharding.  This is
  *   NOT numpy's PCG64 / ziggurat stream: same distribution, different numbers (opt-in, `device_init=True`). */
 int bgmm_dirichlet1(double* r_out, int64_t n, int K, uint64_t seed, int64_t row_offset, void* stream);
+/* bgmm_gen_sample: `GenModel.gen_sample` (:241-264, a per-sample Python loop in the reference) on the device:
+ *   z_out[n] (int32 class index) ~ Cat(pi) from the cumulative sums cdf[K], x_out[n][D] = mu[z] + chol[z] eps with
+ *   chol[k] = lower Cholesky factor of Lambda_k^-1 ([K][D][D]) and eps ~ N(0, I) (Philox + Box-Muller, keyed by `seed` and
+ *   the global row index row_offset + i).  Same distribution as the reference, NOT numpy's random stream.  D <= 256. */
+int bgmm_gen_sample(double* x_out, int32_t* z_out, int64_t n, int K, int D, const double* cdf, const double* mu,
+                    const double* chol, uint64_t seed, int64_t row_offset, void* stream);
 
 /* ---- multi-GPU exchange over NVLink peer memory (no reference counterpart: the reference is single-process) ----
  * Row-sharded fit: the per-iteration all-reduce of state.STATS is fused into bgmm_small.  Every rank owns an exchange
