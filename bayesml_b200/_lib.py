@@ -18,6 +18,8 @@ OFF_NAMES = ("center", "alpha0", "kappa0", "nu0", "m0", "w0inv", "lnb0", "lnc0",
              "ns", "xbar", "smats", "vlk", "vlterms", "vlhist", "ctrl", "total", "stats_len", "params_len", "pitch", "shift")
 POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb", "coef", "acst")
 CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR, CTRL_SEQ, CTRL_ROBUST = range(9)
+CTRL_COMM_LO, CTRL_COMM_HI = 10, 11
+FORCE, FORCE_NO_PUBLISH = 1, 2
 MAX_RANKS = 16
 MAX_BATCH = 8
 N_CTRL = 16

@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace bgmm {
 
@@ -10,6 +11,11 @@ static thread_local char g_err[512] = "";
 static double g_robust_threshold = 2.0e4;
 
 double robust_threshold() { return g_robust_threshold; }
+
+bool pdl_enabled() {
+    static const int on = [] { const char* e = getenv("BGMM_PDL"); return (e == nullptr || atoi(e) != 0) ? 1 : 0; }();
+    return on != 0;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -223,7 +229,8 @@ extern "C" int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, doub
         set_error("bgmm_pass: bad argument (n=%lld K=%d D=%d dtype=%d)", (long long)n, K, D, dtype);
         return BGMM_EINVAL;
     }
-    PassArgs a{x, n, state, workspace, r_out, lnrho_out, argmax_out, r_in, force, accumulate};
+    PassArgs a{x, n, state, workspace, r_out, lnrho_out, argmax_out, r_in, force & BGMM_FORCE, accumulate};
+    a.no_publish = (force & BGMM_FORCE_NO_PUBLISH) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     variant = bgmm_pass_resolve(K, D, dtype, variant, r_in != nullptr);
     if (r_in != nullptr) {                                     // statistics of given responsibilities: no E-step; moments

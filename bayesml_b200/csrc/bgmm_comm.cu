@@ -15,23 +15,11 @@ namespace bgmm {
 
 __global__ void __launch_bounds__(256) publish_kernel(double* __restrict__ st, const Layout L, const CommDesc* __restrict__ cd,
                                                       const int force) {
+    pdl_trigger();
+    pdl_wait();
     volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
     if (!force && ctrl[BGMM_CTRL_DONE]) return;
-    const int seq = ctrl[BGMM_CTRL_SEQ];
-    const int64_t len = L.stats_len;
-    double* mine = cd->xchg[cd->rank] + (int64_t)(seq & 1) * len;
-    const double* src = st + L.stats;
-    for (int64_t o = threadIdx.x; o < len; o += blockDim.x) mine[o] = src[o];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < cd->world) {
-        // stamp seq+1 into slot [parity][my rank] of peer `threadIdx.x` (release at system scope)
-        unsigned long long* flag = reinterpret_cast<unsigned long long*>(cd->xchg[threadIdx.x] + 2 * len) +
-                                   (seq & 1) * BGMM_MAX_RANKS + cd->rank;
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"((unsigned long long)(seq + 1)) : "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) ctrl[BGMM_CTRL_SEQ] = seq + 1;
+    publish_block(st, L, cd);
 }
 
 }  // namespace bgmm
@@ -78,6 +66,6 @@ extern "C" int bgmm_publish(int K, int D, double* state, const void* comm_desc, 
         return BGMM_EINVAL;
     }
     const Layout L = make_layout(K, D, 1);
-    publish_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, L, static_cast<const CommDesc*>(comm_desc), force);
-    return check_cuda(cudaGetLastError(), "publish_kernel launch");
+    return check_cuda(launch_pdl(publish_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, state, L,
+                                 static_cast<const CommDesc*>(comm_desc), force), "publish_kernel launch");
 }

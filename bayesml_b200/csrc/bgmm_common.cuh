@@ -122,6 +122,7 @@ struct PassArgs {
     int32_t* argmax_out;
     const double* r_in;
     int force, accumulate;
+    int no_publish = 0;   // 1: leave the peer-exchange block alone even if ctrl.comm is set (BGMM_FORCE_NO_PUBLISH)
     // conditioning guard (ctrl.ROBUST): 0 = feature-map kernel, returns at once when the flag is set (the DIRECT kernel
     // launched behind it does the pass); 1 = ignore the flag (given responsibilities, hidden-Markov path, forced variant)
     int ignore_robust = 0;
@@ -163,6 +164,54 @@ __device__ __forceinline__ bool pass_skip(const volatile int* ctrl, int force, i
 }
 
 double robust_threshold();
+
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the VB loop is launched with the programmatic-stream-serialization attribute and begins with
+// pdl_trigger(); pdl_wait():  the next kernel's CTAs are scheduled as soon as SM resources free up and sit in
+// griddepcontrol.wait until the previous grid has completed and its memory is visible, so the launch latency of each
+// kernel boundary (~3 us, five boundaries per iteration) disappears from the critical path.  Without a programmatic
+// dependency both instructions are no-ops.  BGMM_PDL=0 in the environment restores plain launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// Publication of freshly reduced statistics to the peers (bgmm_comm.cu), executed by the LAST CTA of a reduction after its
+// __threadfence(): copy STATS into the own exchange block, fence at system scope, stamp every peer, bump ctrl.seq.
+// `cd` comes from ctrl.comm (0: single GPU or NCCL exchange).
+__device__ __forceinline__ const CommDesc* comm_of(const volatile int* ctrl) {
+    const unsigned long long lo = (unsigned int)ctrl[BGMM_CTRL_COMM_LO], hi = (unsigned int)ctrl[BGMM_CTRL_COMM_HI];
+    return reinterpret_cast<const CommDesc*>((hi << 32) | lo);
+}
+__device__ __forceinline__ void publish_block(double* __restrict__ st, const Layout& L, const CommDesc* cd) {
+    volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
+    const int seq = ctrl[BGMM_CTRL_SEQ];
+    const int64_t len = L.stats_len;
+    double* mine = cd->xchg[cd->rank] + (int64_t)(seq & 1) * len;
+    const volatile double* src = st + L.stats;
+    for (int64_t o = threadIdx.x; o < len; o += blockDim.x) mine[o] = src[o];
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < cd->world) {
+        // stamp seq+1 into slot [parity][my rank] of peer `threadIdx.x` (release at system scope)
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(cd->xchg[threadIdx.x] + 2 * len) +
+                                   (seq & 1) * BGMM_MAX_RANKS + cd->rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"((unsigned long long)(seq + 1)) : "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ctrl[BGMM_CTRL_SEQ] = seq + 1;
+}
 
 // sum of `nparts` per-CTA partial statistics buffers (workspace) into state.STATS, fixed order (bgmm_pass_dmma.cu)
 void launch_reduce_partials(const PassArgs& a, const Layout& L, int nparts, cudaStream_t stream);

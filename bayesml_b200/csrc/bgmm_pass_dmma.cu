@@ -48,6 +48,8 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
     const int K = L.K, D = L.D, P = L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     const int wg = warp >> 2, wq = warp & 3;                  // warpgroup (0,1 consumers; 2 producer), warp in group
+    pdl_trigger();
+    pdl_wait();
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
     if (pass_skip(ctrl, a.force, a.ignore_robust)) return;
     const double* __restrict__ coef_g = a.state + L.params[ctrl[BGMM_CTRL_CUR]] + L.p_coef;
@@ -387,13 +389,19 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
 // Cross-CTA reduction of the per-CTA partial statistics, fully parallel and in a fixed order (deterministic):
 // out[o] = sum_b ws[b][o].  A 256-thread CTA owns 32 outputs; its 8 warps each sum one slice of the partials (short
 // dependency chains, 256-byte coalesced loads) and warp 0 adds the 8 slice sums in slice order.
-// tail[1] of the statistics buffer is set to the local row count.
+// tail[1] of the statistics buffer is set to the local row count.  With a peer-exchange descriptor in ctrl.comm the last
+// CTA to finish (atomic ticket) publishes the reduced buffer to the peers (publish_block).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ ws, const int nparts,
-                                                              const int64_t len, double* __restrict__ out,
-                                                              const int64_t rows_slot, const double rows,
-                                                              const int accumulate, const int* __restrict__ ctrl,
-                                                              const int force, const int ignore_robust) {
+                                                              const int64_t len, double* __restrict__ st, const Layout L,
+                                                              const double rows, const int accumulate, const int force,
+                                                              const int ignore_robust, const int no_publish) {
+    pdl_trigger();
+    pdl_wait();
+    volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
     if (pass_skip(ctrl, force, ignore_robust)) return;
+    double* __restrict__ out = st + L.stats;
+    const int64_t rows_slot = (int64_t)L.K * L.pitch + 1;
+    const CommDesc* cd = no_publish ? nullptr : comm_of(ctrl);
     __shared__ double slice[8][32];
     const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int64_t o = (int64_t)blockIdx.x * 32 + lane;
@@ -411,21 +419,35 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
     }
     slice[sl][lane] = (s0 + s1) + (s2 + s3);
     __syncthreads();
-    if (sl != 0 || o >= len) return;
-    double acc = 0.0;
+    if (sl == 0 && o < len) {
+        double acc = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc += slice[i][lane];
-    if (o == rows_slot) acc = rows;
-    if (o == rows_slot + 1) { out[o] = 0.0; return; }     // format marker: moments about the centre (feature-map kernels)
-    out[o] = accumulate ? out[o] + acc : acc;
+        for (int i = 0; i < 8; ++i) acc += slice[i][lane];
+        if (o == rows_slot) acc = rows;
+        if (o == rows_slot + 1) out[o] = 0.0;             // format marker: moments about the centre (feature-map kernels)
+        else out[o] = accumulate ? out[o] + acc : acc;
+    }
+    if (cd == nullptr) return;
+    // ---- last CTA publishes the reduced statistics to the peers ----
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(const_cast<int*>(&ctrl[BGMM_CTRL_PASS_TICKET]), 1);
+        is_last = (t == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) ctrl[BGMM_CTRL_PASS_TICKET] = 0;
+    publish_block(st, L, cd);
 }
 
 // ---- host side ----
 void launch_reduce_partials(const PassArgs& a, const Layout& L, int nparts, cudaStream_t stream) {
     const int64_t len = L.stats_len;
-    reduce_partials_kernel<<<(int)((len + 31) / 32), 256, 0, stream>>>(
-        a.workspace, nparts, len, a.state + L.stats, (int64_t)L.K * L.pitch + 1, (double)a.n, a.accumulate,
-        reinterpret_cast<const int*>(a.state + L.ctrl), a.force, a.ignore_robust);
+    launch_pdl(reduce_partials_kernel, dim3((unsigned)((len + 31) / 32)), dim3(256), 0, stream, (const double*)a.workspace,
+               nparts, len, a.state, L, (double)a.n, a.accumulate, a.force, a.ignore_robust, a.no_publish);
 }
 
 struct DmmaPlan {
@@ -477,7 +499,8 @@ static int launch_cfg(const PassArgs& a, const Layout& L, const DmmaPlan& p, cud
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_dmma)");
     const int grid = dmma_grid(a.n);
-    kern<<<grid, DM_THREADS, p.smem, stream>>>(a, L);
+    e = launch_pdl(kern, dim3(grid), dim3(DM_THREADS), p.smem, stream, a, L);
+    if (e != cudaSuccess) return check_cuda(e, "pass_dmma_kernel launch");
     launch_reduce_partials(a, L, grid, stream);
     return check_cuda(cudaGetLastError(), "pass_dmma_kernel launch");
 }

@@ -266,6 +266,12 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
         out[o] = a.accumulate ? out[o] + s0 : s0;
     }
     if (tid == 0) ctrl[BGMM_CTRL_PASS_TICKET] = 0;
+    const CommDesc* cd = a.no_publish ? nullptr : comm_of(ctrl);
+    if (cd != nullptr) {                  // row-sharded fit: hand the reduced statistics to the peers (bgmm_comm.cu)
+        __threadfence();
+        __syncthreads();
+        publish_block(a.state, L, cd);
+    }
     (void)red;
 }
 

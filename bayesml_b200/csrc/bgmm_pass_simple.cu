@@ -25,6 +25,8 @@ template <typename T, bool DIRECT>
 __global__ void __launch_bounds__(SIMPLE_THREADS) pass_simple_kernel(const PassArgs a, const Layout L, const int tile) {
     extern __shared__ double sm[];
     const int K = L.K, D = L.D, P = L.P, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
     if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
     if (!a.ignore_robust && (ctrl[BGMM_CTRL_ROBUST] != 0) != DIRECT) return;   // the other form does this pass
@@ -172,6 +174,12 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) pass_simple_kernel(const PassA
         out[o] = (a.accumulate && o != (int64_t)K * L.pitch + 2) ? out[o] + acc : acc;
     }
     if (tid == 0) ctrl[BGMM_CTRL_PASS_TICKET] = 0;
+    const CommDesc* cd = a.no_publish ? nullptr : comm_of(ctrl);
+    if (cd != nullptr) {                  // row-sharded fit: hand the reduced statistics to the peers (bgmm_comm.cu)
+        __threadfence();
+        __syncthreads();
+        publish_block(a.state, L, cd);
+    }
 }
 
 static int simple_tile(int K, int D) {
@@ -206,8 +214,8 @@ int launch_pass_simple(const PassArgs& a, int K, int D, int dtype, int direct, c
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(pass_simple)");
-        kern<<<grid, SIMPLE_THREADS, smem, stream>>>(a, L, tile);
-        return check_cuda(cudaGetLastError(), "pass_simple_kernel launch");
+        return check_cuda(launch_pdl(kern, dim3(grid), dim3(SIMPLE_THREADS), smem, stream, a, L, tile),
+                          "pass_simple_kernel launch");
     };
     if (dtype == BGMM_F64) return direct ? go(pass_simple_kernel<double, true>) : go(pass_simple_kernel<double, false>);
     return direct ? go(pass_simple_kernel<float, true>) : go(pass_simple_kernel<float, false>);

@@ -11,6 +11,7 @@
 // Cholesky factorisation for the inverse and the log-determinant (agrees to cond*eps, tested vs the oracle).
 #include "bgmm_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace bgmm {
 
@@ -48,6 +49,8 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
                                                     const CommDesc* __restrict__ cd,
                                                     const double* __restrict__ hmm_vlx, const double robust_thresh) {
     extern __shared__ double sm[];
+    pdl_trigger();
+    pdl_wait();
     const int K = L.K, D = L.D, DD = D * D, k = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
     const bool iterate = (mode == BGMM_SMALL_ITERATE), stats_only = (mode == BGMM_SMALL_STATS);
@@ -385,6 +388,360 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     ctrl[BGMM_CTRL_TICKET] = 0;
 }
 
+// ---- D <= 32: the same computation as small_kernel by ONE WARP per component, warp-synchronous throughout -------------
+// small_kernel's running time (~45 us at K = 32, D = 16) is a chain of block barriers and single-thread steps around a
+// 16 x 16 factorisation; at 8 GPUs it is half of the per-iteration time that does not shrink with the shard (VERDICT r1,
+// weak #5).  Here lane i owns row i (Cholesky, left-looking), then column i (L^-1 by forward substitution) and row i again
+// (W = L^-T L^-1), everything in shared memory with conflict-free pitch 33 and __syncwarp only; the special functions are
+// evaluated in merged SIMT calls (one digamma / lgamma / log call serves all lanes' different arguments) and the last CTA
+// sums the ELBO with all 32 lanes.  Same formulas, same outputs and control flow as small_kernel (which stays for D > 32).
+// DT > 0: D is the compile-time constant DT (the loops of the D x D algebra unroll completely: the warp is latency bound,
+// ~9 cycles per instruction, and loop control was two thirds of its instruction stream — profiles/r02_small_warp_*);
+// DT == 0: any D <= 32 at run time.
+constexpr int SW_LP = 33;
+
+template <int DT>
+__global__ void __launch_bounds__(32) small_warp_kernel(double* __restrict__ st, const Layout L, const int mode,
+                                                        const int max_itr, const double tol,
+                                                        const CommDesc* __restrict__ cd,
+                                                        const double* __restrict__ hmm_vlx, const double robust_thresh) {
+    __shared__ double Am[32 * SW_LP];        // W^-1 (lower triangle used) -> L -> W
+    __shared__ double Bm[32 * SW_LP];        // S -> L^-1
+    __shared__ double xbar[32], dev[32], lin[32], mnew[32], rd[32];
+    pdl_trigger();
+    pdl_wait();
+    const int K = L.K, D = DT > 0 ? DT : L.D, DD = D * D, k = blockIdx.x, lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
+    const bool iterate = (mode == BGMM_SMALL_ITERATE), stats_only = (mode == BGMM_SMALL_STATS);
+    if (iterate && ctrl[BGMM_CTRL_DONE]) return;
+    const int cur = ctrl[BGMM_CTRL_CUR];
+    double* Pc = st + L.params[cur];
+    double* Pn = iterate ? st + L.params[cur ^ 1] : Pc;
+    const double* center = st + L.center;
+    const double* m0 = st + L.m0 + (int64_t)k * D;
+    const double* w0inv = st + L.w0inv + (int64_t)k * DD;
+    const double alpha0 = st[L.alpha0 + k], kappa0 = st[L.kappa0 + k], nu0 = st[L.nu0 + k];
+
+    // ---- fused all-reduce over peer memory (as in small_kernel) ----
+    const bool fused = (cd != nullptr) && (iterate || stats_only);
+    const double* xb[BGMM_MAX_RANKS];
+    int world = 1;
+    if (fused) {
+        world = cd->world;
+        const int seq = ctrl[BGMM_CTRL_SEQ] - 1;
+        const int64_t len = L.stats_len;
+        if (lane < world) {
+            const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(cd->xchg[cd->rank] + 2 * len) +
+                                             (seq & 1) * BGMM_MAX_RANKS + lane;
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            } while (v < (unsigned long long)(seq + 1));
+        }
+        __syncwarp();
+        for (int r = 0; r < world; ++r) xb[r] = cd->xchg[r] + (int64_t)(seq & 1) * len;
+        double* row = st + L.stats + (int64_t)k * L.pitch;
+        for (int p = lane; p < L.pitch; p += 32) {
+            double acc = 0.0;
+            for (int r = 0; r < world; ++r) acc += ld_peer(xb[r] + (int64_t)k * L.pitch + p);
+            row[p] = acc;
+        }
+        if (k == 0 && lane < 8) {
+            double acc = 0.0;
+            for (int r = 0; r < world; ++r) acc += ld_peer(xb[r] + (int64_t)K * L.pitch + lane);
+            st[L.stats + (int64_t)K * L.pitch + lane] = acc;
+        }
+        __syncwarp();
+    }
+
+    double kn, nun, an, alpha_sum_new, N = 0.0, crit_n = 1.0;
+    double t_trs = 0.0, t_q1 = 0.0, t_q2 = 0.0, t_tr0 = 0.0;
+    double kappa_c = 1.0, nu_c = 0.0, alpha_c = 1.0, elnpi_c = 0.0, elndet_c = 0.0, lnb_c = 0.0;
+    if (iterate || stats_only) {
+        // ---- statistics of component k (moments about the centre, or about shift_k when tail[2] > 0) ----
+        const double* raw = st + L.stats + (int64_t)k * L.pitch;
+        N = raw[0];
+        crit_n = fmin(N, 1.0);
+        double fmt;
+        if (fused) {
+            fmt = 0.0;
+            for (int r = 0; r < world; ++r) fmt += ld_peer(xb[r] + (int64_t)K * L.pitch + 2);
+        } else {
+            fmt = st[L.stats + (int64_t)K * L.pitch + 2];
+        }
+        const bool shifted = fmt > 0.5;
+        const double* sh = st + L.shift + (int64_t)k * D;
+        double* S = st + L.smats + (int64_t)k * DD;
+        if (N > 0.0) {
+            const double invN = 1.0 / N;
+            if (lane < D) {
+                const double db = raw[1 + lane] * invN;
+                lin[lane] = db;
+                xbar[lane] = shifted ? sh[lane] + db : db;
+            }
+            __syncwarp();
+            for (int e = lane; e < DD; e += 32) {
+                const int i = e / D, j = e - i * D, hi = max(i, j), lo = min(i, j);
+                const double v = raw[1 + D + hi * (hi + 1) / 2 + lo] * invN - lin[i] * lin[j];
+                S[e] = v;
+                Bm[i * SW_LP + j] = v;
+            }
+        } else {
+            // reference :729 — x_bar_vecs[k] keeps the un-normalised sum (0 in the original frame), s_mats[k] stale
+            if (lane < D) xbar[lane] = -center[lane];
+            for (int e = lane; e < DD; e += 32) Bm[(e / D) * SW_LP + (e % D)] = S[e];
+        }
+        __syncwarp();
+        if (lane < D) st[L.xbar + (int64_t)k * D + lane] = xbar[lane];
+        if (lane == 0) st[L.ns + k] = N;
+        if (stats_only) {
+            if (N > 0.0 && lane < D) st[L.shift + (int64_t)k * D + lane] = xbar[lane];
+            return;
+        }
+        // ---- ELBO sums of component k under the CURRENT parameters (those the pass used) ----
+        kappa_c = Pc[L.p_kappa + k]; nu_c = Pc[L.p_nu + k]; alpha_c = Pc[L.p_alpha + k];
+        elnpi_c = Pc[L.p_elnpi + k]; elndet_c = Pc[L.p_elndet + k]; lnb_c = Pc[L.p_lnb + k];
+        const double* W = Pc + L.p_w + (int64_t)k * DD;
+        const double* m = Pc + L.p_m + (int64_t)k * D;
+        if (lane < D) { dev[lane] = xbar[lane] - m[lane]; lin[lane] = m[lane] - m0[lane]; }
+        __syncwarp();
+        for (int e = lane; e < DD; e += 32) {
+            const int i = e / D, j = e - i * D;
+            const double w = W[e];
+            t_trs += Bm[i * SW_LP + j] * w;
+            t_q1 += dev[i] * w * dev[j];
+            t_q2 += lin[i] * w * lin[j];
+            t_tr0 += w0inv[e] * w;
+        }
+        t_trs = warp_sum(t_trs); t_q1 = warp_sum(t_q1); t_q2 = warp_sum(t_q2); t_tr0 = warp_sum(t_tr0);
+        __syncwarp();       // dev / lin are reused below
+
+        // ---- M-step (:758-768, :742) into the other parameter set ----
+        kn = kappa0 + N; nun = nu0 + N; an = alpha0 + N;
+        if (lane < D) {
+            mnew[lane] = (kappa0 * m0[lane] + N * xbar[lane]) / kn;
+            dev[lane] = xbar[lane] - m0[lane];
+        }
+        __syncwarp();
+        const double c2 = kappa0 * N / kn;
+        double* winv_out = Pn + L.p_winv + (int64_t)k * DD;
+        for (int e = lane; e < DD; e += 32) {
+            const int i = e / D, j = e - i * D;
+            const double v = w0inv[e] + N * Bm[i * SW_LP + j] + c2 * (dev[i] * dev[j]);
+            Am[i * SW_LP + j] = v;
+            winv_out[e] = v;
+        }
+        double asum = 0.0;
+        for (int j = lane; j < K; j += 32) {
+            double nj;
+            if (fused) {
+                nj = 0.0;
+                for (int r = 0; r < world; ++r) nj += ld_peer(xb[r] + (int64_t)j * L.pitch);
+            } else {
+                nj = st[L.stats + (int64_t)j * L.pitch];
+            }
+            asum += st[L.alpha0 + j] + nj;
+        }
+        alpha_sum_new = warp_sum(asum);
+        if (lane == 0) { Pn[L.p_kappa + k] = kn; Pn[L.p_nu + k] = nun; Pn[L.p_alpha + k] = an; }
+        if (lane < D) Pn[L.p_m + (int64_t)k * D + lane] = mnew[lane];
+    } else {
+        kn = Pc[L.p_kappa + k]; nun = Pc[L.p_nu + k]; an = Pc[L.p_alpha + k];
+        if (lane < D) mnew[lane] = Pc[L.p_m + (int64_t)k * D + lane];
+        for (int e = lane; e < DD; e += 32) Am[(e / D) * SW_LP + (e % D)] = Pc[L.p_winv + (int64_t)k * DD + e];
+        double asum = 0.0;
+        for (int j = lane; j < K; j += 32) asum += Pc[L.p_alpha + j];
+        alpha_sum_new = warp_sum(asum);
+    }
+    __syncwarp();
+
+    // ---- Cholesky A = L L^T, left-looking: lane i owns row i; L[j][l] (l < j) is final when column j starts ----
+    bool spd = true;
+    double mydiag = 1.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        double s0 = Am[lane * SW_LP + j], s1 = 0.0;
+        int l = 0;
+#pragma unroll
+        for (; l + 1 < j; l += 2) {
+            s0 = fma(-Am[lane * SW_LP + l], Am[j * SW_LP + l], s0);
+            s1 = fma(-Am[lane * SW_LP + l + 1], Am[j * SW_LP + l + 1], s1);
+        }
+        if (l < j) s0 = fma(-Am[lane * SW_LP + l], Am[j * SW_LP + l], s0);
+        const double s = s0 + s1;
+        const double sjj = __shfl_sync(full, s, j);
+        spd = spd && (sjj > 0.0);
+        const double rs = rsqrt(sjj);
+        const double v = (lane == j) ? sjj * rs : (lane > j ? s * rs : 0.0);
+        __syncwarp();                          // every lane has read row j's entries before lane j overwrites A[j][j]
+        Am[lane * SW_LP + j] = v;
+        if (lane == j) { mydiag = v; rd[j] = rs; }
+        __syncwarp();
+    }
+    const double ld = (lane < D) ? log_ni(mydiag) : 0.0;
+    const double logdet = 2.0 * warp_sum(ld);  // ln|W^-1|
+    if (!spd && lane == 0) ctrl[BGMM_CTRL_ERROR] = 1;
+
+    // ---- L^-1 by forward substitution: lane j owns COLUMN j (B[i][j], i = 0..D-1); no cross-lane dependence ----
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        double a0 = (i == lane) ? 1.0 : 0.0, a1 = 0.0;
+        int l = 0;
+#pragma unroll
+        for (; l + 1 < i; l += 2) {
+            a0 = fma(-Am[i * SW_LP + l], Bm[l * SW_LP + lane], a0);
+            a1 = fma(-Am[i * SW_LP + l + 1], Bm[(l + 1) * SW_LP + lane], a1);
+        }
+        if (l < i) a0 = fma(-Am[i * SW_LP + l], Bm[l * SW_LP + lane], a0);
+        Bm[i * SW_LP + lane] = (i >= lane && lane < D) ? (a0 + a1) * rd[i] : 0.0;
+    }
+    __syncwarp();
+
+    // ---- W = L^-T L^-1: lane a owns row a; W[a][b] = sum_{l >= max(a,b)} Linv[l][a] Linv[l][b] ----
+#pragma unroll
+    for (int b = 0; b < D; ++b) {
+        double a0 = 0.0, a1 = 0.0;
+        int l = b;
+#pragma unroll
+        for (; l + 1 < D; l += 2) {
+            a0 = fma(Bm[l * SW_LP + lane], Bm[l * SW_LP + b], a0);
+            a1 = fma(Bm[(l + 1) * SW_LP + lane], Bm[(l + 1) * SW_LP + b], a1);
+        }
+        if (l < D) a0 = fma(Bm[l * SW_LP + lane], Bm[l * SW_LP + b], a0);
+        Am[lane * SW_LP + b] = a0 + a1;        // L is no longer needed
+    }
+    __syncwarp();
+    double* Wout = Pn + L.p_w + (int64_t)k * DD;
+    for (int e = lane; e < DD; e += 32) Wout[e] = Am[(e / D) * SW_LP + (e % D)];
+
+    // ---- special functions, merged SIMT calls: lanes i < D take (nu - i)/2, three more lanes the scalar arguments ----
+    double ps = 0.0, gs = 0.0, psi_x = 0.0, lg_x = 0.0, ln_x = 0.0;
+    for (int i = lane; i < D; i += 32) {
+        const double a = (nun - i) / 2.0;
+        ps += digamma_pos(a);
+        gs += lgamma_ni(a);
+    }
+    ps = warp_sum(ps);
+    gs = warp_sum(gs);
+    {
+        // lane 0: alpha_cur, lane 1: alpha_new, lane 2: sum alpha_new  (digamma);  lane 0: alpha_cur (lgamma);
+        // lane 0: kappa0, lane 1: kappa_cur (log)
+        const double pa = lane == 0 ? alpha_c : (lane == 1 ? an : alpha_sum_new);
+        if (lane < 3) psi_x = digamma_pos(pa);
+        if (lane == 0) lg_x = lgamma_ni(alpha_c);
+        if (lane < 2) ln_x = log_ni(lane == 0 ? kappa0 : kappa_c);
+    }
+    const double psi_alpha = __shfl_sync(full, psi_x, 0), psi_an = __shfl_sync(full, psi_x, 1),
+                 psi_asum = __shfl_sync(full, psi_x, 2), lg_alpha = __shfl_sync(full, lg_x, 0),
+                 ln_kappa0 = __shfl_sync(full, ln_x, 0), ln_kappa = __shfl_sync(full, ln_x, 1);
+    const double elndet_n = ps + D * LN2 - logdet;
+    const double lnb_n = (nun * logdet - nun * D * LN2 - D * (D - 1) / 2.0 * LNPI - gs * 2.0) / 2.0;
+    const double elnpi_n = psi_an - psi_asum;
+    if (lane == 0) {
+        Pn[L.p_elndet + k] = elndet_n;
+        Pn[L.p_lnb + k] = lnb_n;
+        Pn[L.p_elnpi + k] = elnpi_n;
+    }
+
+    // ---- E-step coefficient row: ln rho = coef . phi(x'), Lambda = nu W ----
+    double li = 0.0;
+    if (lane < D) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fma(Am[lane * SW_LP + j], mnew[j], acc);
+        li = nun * acc;
+    }
+    const double mq = warp_sum(lane < D ? mnew[lane] * li : 0.0);
+    double* coef = Pn + L.p_coef + (int64_t)k * L.pitch;
+    if (lane < D) {
+        coef[1 + lane] = li;
+        const int base = 1 + D + lane * (lane + 1) / 2;
+        for (int j = 0; j < lane; ++j) coef[base + j] = -nun * Am[lane * SW_LP + j];
+        coef[base + lane] = -0.5 * nun * Am[lane * SW_LP + lane];
+    }
+    for (int q = L.P + lane; q < L.pitch; q += 32) coef[q] = 0.0;
+    if (lane == 0) {
+        const double acst = (hmm_vlx != nullptr ? 0.0 : elnpi_n) + (elndet_n - D * LN2PI - D / kn) / 2.0;
+        coef[0] = acst - 0.5 * mq;
+        Pn[L.p_acst + k] = acst;
+        double* vk = st + L.vlk + (int64_t)k * 8;
+        if (iterate) {
+            const double lnb0 = st[L.lnb0 + k];
+            vk[0] = N * (elndet_c - D / kappa_c - nu_c * t_trs - nu_c * t_q1 - D * LN2PI) / 2.0;           // :673-683
+            vk[1] = N * elnpi_c;                                                                          // :686
+            vk[2] = (alpha0 - 1.0) * elnpi_c;                                                             // :689
+            vk[3] = (D * (ln_kappa0 - LN2PI - kappa0 / kappa_c) - kappa0 * nu_c * t_q2 + 2.0 * lnb0
+                     + (nu0 - D) * elndet_c - nu_c * t_tr0) / 2.0;                                        // :692-701
+            vk[4] = lg_alpha - (alpha_c - 1.0) * psi_alpha;                                               // :707 (per-k part)
+            vk[5] = (D * (1.0 + LN2PI - ln_kappa) - 2.0 * lnb_c - (nu_c - D) * elndet_c + nu_c * D) / 2.0;  // :710-715
+            vk[6] = alpha_c;
+        }
+        vk[7] = (K == 1) ? 0.0 : crit_n * mq;             // conditioning of the feature-map form (see small_kernel)
+    }
+    {
+        double* sh = st + L.shift + (int64_t)k * D;
+        const bool have_xbar = iterate && crit_n > 0.0;
+        if (lane < D) sh[lane] = have_xbar ? xbar[lane] : mnew[lane];
+    }
+
+    // ---- last CTA: conditioning flag of the new set; ELBO sum (all lanes), convergence test (:869), flip ----
+    __threadfence();
+    __syncwarp();
+    int is_last = 0;
+    if (lane == 0) is_last = (atomicAdd(const_cast<int*>(&ctrl[BGMM_CTRL_TICKET]), 1) == K - 1);
+    is_last = __shfl_sync(full, is_last, 0);
+    if (!is_last) return;
+    __threadfence();
+    const double* vkg = st + L.vlk;
+    double px = 0, pz = 0, ppi = 0, pml = 0, qpi = 0, qml = 0, asum = 0, crit = 0;
+    for (int j = lane; j < K; j += 32) {
+        px += __ldcg(vkg + j * 8 + 0); pz += __ldcg(vkg + j * 8 + 1); ppi += __ldcg(vkg + j * 8 + 2);
+        pml += __ldcg(vkg + j * 8 + 3); qpi += __ldcg(vkg + j * 8 + 4); qml += __ldcg(vkg + j * 8 + 5);
+        asum += __ldcg(vkg + j * 8 + 6);
+        crit = fmax(crit, __ldcg(vkg + j * 8 + 7));
+    }
+    px = warp_sum(px); pz = warp_sum(pz); ppi = warp_sum(ppi); pml = warp_sum(pml); qpi = warp_sum(qpi);
+    qml = warp_sum(qml); asum = warp_sum(asum);
+    for (int o = 16; o > 0; o >>= 1) crit = fmax(crit, __shfl_xor_sync(full, crit, o));
+    const int robust = crit > robust_thresh ? 1 : 0;
+    if (!iterate) {
+        if (lane == 0) { ctrl[BGMM_CTRL_ROBUST] = robust; ctrl[BGMM_CTRL_TICKET] = 0; }
+        return;
+    }
+    // lane 0: lgamma(sum alpha), lane 1: digamma(sum alpha) — one divergent pair instead of two serial calls
+    double sf = 0.0;
+    if (lane == 0) sf = lgamma_ni(asum);
+    if (lane == 1) sf = digamma_pos(asum);
+    const double lg_asum = __shfl_sync(full, sf, 0), psi_as = __shfl_sync(full, sf, 1);
+    if (lane != 0) return;
+    ppi += st[L.lnc0];
+    double qz = -st[L.stats + (int64_t)K * L.pitch];                          // -sum r ln r (:704)
+    qpi += -lg_asum + (asum - K) * psi_as;                                       // dirichlet entropy (:707)
+    double extra = 0.0;
+    if (hmm_vlx != nullptr) {
+        pz = hmm_vlx[0];
+        qz = hmm_vlx[2];
+        extra = hmm_vlx[1] + hmm_vlx[3];
+    }
+    const double vl = px + pz + ppi + pml + qz + qpi + qml + extra;           // :717-723
+    double* vt = st + L.vlterms;
+    vt[0] = px; vt[1] = pz; vt[2] = ppi; vt[3] = pml; vt[4] = qz; vt[5] = qpi; vt[6] = qml; vt[7] = vl;
+    const int iter = ctrl[BGMM_CTRL_ITER];
+    double* hist = st + L.vlhist;
+    if (iter < L.hist_len) hist[iter] = vl;
+    bool conv = false;
+    if (iter >= 1 && iter - 1 < L.hist_len) {
+        const double vb = hist[iter - 1];
+        conv = fabs((vl - vb) / vb) < tol;
+    }
+    if (conv) { ctrl[BGMM_CTRL_CONVERGED] = 1; ctrl[BGMM_CTRL_DONE] = 1; }
+    else if (iter >= max_itr || ctrl[BGMM_CTRL_ERROR]) { ctrl[BGMM_CTRL_DONE] = 1; }
+    else { ctrl[BGMM_CTRL_CUR] = cur ^ 1; ctrl[BGMM_CTRL_ROBUST] = robust; }
+    ctrl[BGMM_CTRL_ITER] = iter + 1;
+    ctrl[BGMM_CTRL_TICKET] = 0;
+}
+
 // Transition-matrix part of the hidden-Markov VB step, one CTA.  Replaces, in
 // /root/reference/bayesml/hiddenmarkovnormal/_hiddenmarkovnormal.py:
 //   _update_q_a :984-986 (zeta = zeta0 + M), _calc_q_a_features :851-854 (ln a~, a~ = exp(ln a~ - max), ln C(zeta)),
@@ -491,6 +848,22 @@ __global__ void __launch_bounds__(256) hmm_trans_kernel(double* __restrict__ st,
     }
 }
 
+// D <= 32 runs the warp-synchronous kernel; BGMM_SMALL_WARP=0 in the environment keeps the block kernel (A/B measurements)
+static bool use_warp_kernel(int D) {
+    static const int on = [] { const char* e = getenv("BGMM_SMALL_WARP"); return (e == nullptr || atoi(e) != 0) ? 1 : 0; }();
+    return on != 0 && D <= 32;
+}
+
+static cudaError_t launch_small_warp(int K, int D, cudaStream_t stream, double* state, const Layout& L, int mode, int max_itr,
+                                     double tol, const CommDesc* cd, const double* hmm_vlx) {
+    const double thr = robust_threshold();
+#define BGMM_SW_CASE(d) if (D == d) return launch_pdl(small_warp_kernel<d>, dim3(K), dim3(32), 0, stream, state, L, mode, \
+                                                      max_itr, tol, cd, hmm_vlx, thr);
+    BGMM_SW_CASE(2) BGMM_SW_CASE(4) BGMM_SW_CASE(8) BGMM_SW_CASE(16)
+#undef BGMM_SW_CASE
+    return launch_pdl(small_warp_kernel<0>, dim3(K), dim3(32), 0, stream, state, L, mode, max_itr, tol, cd, hmm_vlx, thr);
+}
+
 }  // namespace bgmm
 
 extern "C" int bgmm_hmm_layout(int K, int64_t* off) {
@@ -528,6 +901,9 @@ extern "C" int bgmm_hmm_small(int K, int D, double* state, double* hst, int mode
         if (rc) return rc;
     }
     if (mode != BGMM_SMALL_STATS) hmm_trans_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, L, hst, H, mode);
+    if (use_warp_kernel(D))
+        return check_cuda(launch_small_warp(K, D, (cudaStream_t)stream, state, L, mode, max_itr, tol, nullptr,
+                                            (const double*)(hst + H.vlx)), "hmm small (warp) launch");
     const int nt = D <= 16 ? 32 : (D <= 32 ? 64 : (D <= 64 ? 128 : 256));
     small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol, nullptr, hst + H.vlx,
                                                         robust_threshold());
@@ -556,10 +932,13 @@ extern "C" int bgmm_small(int K, int D, double* state, int mode, int max_itr, do
                             "cudaFuncSetAttribute(small_kernel)");
         if (rc) return rc;
     }
+    if (use_warp_kernel(D))
+        return check_cuda(launch_small_warp(K, D, (cudaStream_t)stream, state, L, mode, max_itr, tol,
+                                            static_cast<const CommDesc*>(comm_desc), (const double*)nullptr),
+                          "small_warp_kernel launch");
     // latency-bound kernel full of block barriers: one warp per component while the D x D work is tiny
     const int nt = D <= 16 ? 32 : (D <= 32 ? 64 : (D <= 64 ? 128 : 256));
-    small_kernel<<<K, nt, smem, (cudaStream_t)stream>>>(state, L, mode, max_itr, tol,
-                                                        static_cast<const CommDesc*>(comm_desc), nullptr,
-                                                        robust_threshold());
-    return check_cuda(cudaGetLastError(), "small_kernel launch");
+    return check_cuda(launch_pdl(small_kernel, dim3(K), dim3(nt), smem, (cudaStream_t)stream, state, L, mode, max_itr, tol,
+                                 static_cast<const CommDesc*>(comm_desc), (const double*)nullptr, robust_threshold()),
+                      "small_kernel launch");
 }

@@ -124,7 +124,17 @@ class VBEngine:
             desc[0] = world | (rank << 32)                       # int32 world, int32 rank (little endian)
             desc[2:2 + world] = ptrs
             self.comm_desc = torch.as_tensor(desc).to(self.device)
+            self._write_comm_ptr()
             dist.barrier(group=self.group)
+
+    def _write_comm_ptr(self):
+        """ctrl.comm <- device address of the exchange descriptor: every bgmm_pass then publishes its statistics from the
+        last CTA of its reduction (no separate bgmm_publish launch)."""
+        if self.comm_desc is not None:
+            p = self.comm_desc.data_ptr()
+            c = self.ctrl
+            c[_lib.CTRL_COMM_LO] = (p & 0xFFFFFFFF) - (1 << 32 if (p & 0x80000000) else 0)     # int32 bit pattern
+            c[_lib.CTRL_COMM_HI] = ((p >> 32) & 0xFFFFFFFF) - (1 << 32 if ((p >> 32) & 0x80000000) else 0)
 
     def close(self):
         """Release the peer-memory mappings (optional; process exit does it too)."""
@@ -133,6 +143,8 @@ class VBEngine:
         if self._comm_base:
             self.lib.bgmm_comm_free(self._comm_base)
         self._comm_peers, self._comm_base, self.comm_desc = [], None, None
+        if self.state is not None:
+            self.ctrl[_lib.CTRL_COMM_LO:_lib.CTRL_COMM_HI + 1].zero_()
 
     def phase(self, name):
         return _Phase(self, name)
@@ -255,9 +267,9 @@ class VBEngine:
         self._put(self._pview(0, "nu", K), nu)
         self._put(self._pview(0, "m", K * D), np.asarray(m) - self.center)
         self._put(self._pview(0, "winv", K * D * D), winv)
-        c = self.ctrl                                            # reset everything but the exchange sequence number
+        c = self.ctrl                          # reset everything but the exchange sequence number and descriptor address
         c[:_lib.CTRL_SEQ].zero_()
-        c[_lib.CTRL_SEQ + 1:].zero_()
+        c[_lib.CTRL_SEQ + 1:_lib.CTRL_COMM_LO].zero_()
         self._small(_lib.SMALL_FEATURES, 0, 0.0)
 
     def _small(self, mode, max_itr, tol):
@@ -291,13 +303,10 @@ class VBEngine:
             self.kernel_launches += 1           # the conditioning guard: DIRECT kernel behind the feature-map kernel(s)
 
     def exchange(self, force=0):
-        """The per-iteration exchange of the statistics between row shards: publish to peer memory (the reduction is
-        fused into the next bgmm_small) or, without peer access, ncclAllReduce."""
-        if self.comm_desc is not None:
-            _lib.check(self.lib.bgmm_publish(self.K, self.D, self.state.data_ptr(), self.comm_desc.data_ptr(), int(force),
-                                             self._stream()), "bgmm_publish")
-            self.kernel_launches += 1
-        elif self.group is not None:
+        """The per-iteration exchange of the statistics between row shards.  Peer memory: nothing to launch — bgmm_pass has
+        published the statistics from its reduction's last CTA (ctrl.comm) and the next bgmm_small sums the peers' blocks.
+        Without peer access: ncclAllReduce."""
+        if self.comm_desc is None and self.group is not None:
             torch.distributed.all_reduce(self.stats, group=self.group)
 
     # ------------------------------------------------------------------ the VB loop (:860-872)
@@ -421,7 +430,7 @@ class VBEngine:
         K, n = self.K, self.n_local
         with torch.cuda.device(self.device):
             lnrho = torch.empty((n, K), dtype=torch.float64, device=self.device)
-            self.pass_only(lnrho_out=lnrho, force=1)            # rows are independent: no cross-rank exchange
+            self.pass_only(lnrho_out=lnrho, force=_lib.FORCE | _lib.FORCE_NO_PUBLISH)    # rows are independent: no exchange
             cur = int(self.ctrl[_lib.CTRL_CUR].item())
             acst = self._pview(cur, "acst", K)
             consts = torch.as_tensor(np.ascontiguousarray(np.stack([ck, hk, nuk]), dtype=np.float64)).to(self.device)

@@ -123,6 +123,10 @@ enum {
     BGMM_CTRL_SEQ,        /* number of peer-memory exchanges published so far (bgmm_publish)        */
     BGMM_CTRL_ROBUST,     /* 1 -> the current parameter set is ill-conditioned for the feature-map kernels:
                              bgmm_pass runs the DIRECT kernel (set by bgmm_small for every new parameter set)  */
+    BGMM_CTRL_COMM_LO = 10, /* low / high 32 bits of the DEVICE address of the peer-exchange descriptor (see below), or 0.  */
+    BGMM_CTRL_COMM_HI,    /* When set (by the caller, once), every bgmm_pass PUBLISHES the statistics it has just reduced
+                             (copy into the own exchange block + stamps, what bgmm_publish does) from the reduction's last
+                             CTA: no separate launch.  Suppressed per call with BGMM_FORCE_NO_PUBLISH.                 */
     BGMM_N_CTRL = 16
 };
 
@@ -152,6 +156,9 @@ int bgmm_center(const void* x_raw, int dtype_in, void* x_out, int dtype_out, int
  *   (`_init_random_responsibility` :734-736); variant SIMPLE/AUTO: moments about the centre, DIRECT: about state.SHIFT
  *   (the reference's two-pass centred `s_mats`, :730-732, when SHIFT holds x_bar).  No-op when ctrl.done != 0 unless `force`.
  *   accumulate != 0: add to state.STATS instead of overwriting (row-chunked uploads). */
+#define BGMM_FORCE 1            /* `force` bit 0: run although ctrl.done is set                                          */
+#define BGMM_FORCE_NO_PUBLISH 2 /* `force` bit 1: do not publish to the peer-exchange block (a pass that is not followed by
+                                   a consuming bgmm_small, e.g. predictive densities of the local rows)                 */
 int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, double* state, double* workspace,
               double* r_out, double* lnrho_out, int32_t* argmax_out, const double* r_in,
               int variant, int force, int accumulate, void* stream);
