@@ -36,11 +36,15 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    tmp = LIB_PATH + ".tmp.so"              # built beside the target and renamed: a reader never sees a half-written library
     cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(res.stderr)
     return LIB_PATH
