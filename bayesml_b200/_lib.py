@@ -17,7 +17,7 @@ SMALL_FEATURES, SMALL_ITERATE, SMALL_STATS = 0, 1, 2
 OFF_NAMES = ("center", "alpha0", "kappa0", "nu0", "m0", "w0inv", "lnb0", "lnc0", "params0", "params1", "stats",
              "ns", "xbar", "smats", "vlk", "vlterms", "vlhist", "ctrl", "total", "stats_len", "params_len", "pitch", "shift")
 POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb", "coef", "acst")
-CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR, CTRL_SEQ, CTRL_ROBUST = range(9)
+CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR, CTRL_SEQ, CTRL_ROBUST, CTRL_CRIT = range(10)
 CTRL_COMM_LO, CTRL_COMM_HI = 10, 11
 FORCE, FORCE_NO_PUBLISH = 1, 2
 MAX_RANKS = 16
@@ -69,6 +69,8 @@ def load():
     lib.bgmm_dirichlet1.argtypes = [vp, i64, i32, ctypes.c_uint64, i64, vp]
     lib.bgmm_gen_sample.restype = i32
     lib.bgmm_gen_sample.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, ctypes.c_uint64, i64, vp]
+    lib.bgmm_tc_selftest.restype = i32
+    lib.bgmm_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.bgmm_pass_supported.restype = i32
     lib.bgmm_pass_supported.argtypes = [i32, i32, i32, i32]
     lib.bgmm_pass_resolve.restype = i32

@@ -94,6 +94,7 @@ struct ScanBufs {
     double* ps;            // [nch][K][K] xi-sum partials
     double* plc;           // [nch]       sum ln c partials
     double* pgl;           // [nch]       sum gamma ln rho partials
+    double* seq2;          // two-level sweep: group matrices [72][K][K], log scales [72][K], boundary vectors [72][K]
 };
 
 __device__ __forceinline__ const double* current_at(const double* st, const Layout& L, const double* hst, const HmmLayout& H) {
@@ -226,6 +227,26 @@ __global__ void __launch_bounds__(128) hmm_cs_kernel(const ScanPlan sp, const do
 // The normaliser of the forward sweep is sum_j w_j (the rows of T sum to one), formed redundantly by every lane in a
 // fixed order instead of a shuffle reduction after the matrix-vector product.
 constexpr int SEQ_T = 128;
+// Two-level sweep (r02).  The recurrence over nch - 1 chunk matrices is sequential (~0.3 us per step: one shared-memory
+// exchange, K dependent FMAs, a reciprocal), 1.2 ms per direction at 4096 chunks.  It is a product of matrices, so it is cut
+// into groups of SEQ_GLEN steps:
+//   mode 1 (grid = groups x start-state blocks): the recurrence over ONE group's steps from every unit vector -> the
+//           group's transfer matrix (rows normalised, log scale kept: forward; true scale: backward) — the chunk-level
+//           phase A one level up;
+//   mode 2 (one CTA): the same sequential sweep, over the <= 64 group matrices -> the vector at every group boundary;
+//   mode 3 (grid = groups): the recurrence over one group's steps from its boundary vector, writing every chunk's vector.
+// mode 0 is the single-CTA sweep over everything (few chunks).  Same arithmetic per step in all modes; the association
+// of the matrix products differs (1e-16 relative), the order of every sum is fixed.
+constexpr int SEQ_GLEN = 64;
+struct SeqLevel {
+    int mode, nsteps, ngroups;
+    const double* tf;      // [.][K][K] matrices the steps read (chunk transfer matrices, or group matrices in mode 2)
+    const double* ls;      // [.][K]    their log scales
+    double* vb;            // [.][K]    vectors the steps write (chunk boundary vectors, or group boundary vectors in mode 2)
+    double* tg;            // [ngroups][K][K] mode 1 output
+    double* lsg;           // [ngroups][K]    mode 1 output
+    const double* vbg;     // [ngroups][K]    mode 3 input: the vector at the start of every group
+};
 __device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
@@ -243,7 +264,7 @@ __host__ __device__ inline int seq_batch(int K) {
 template <int KP, bool FWD>
 __global__ void __launch_bounds__(SEQ_T) hmm_seq_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
                                                         const double* __restrict__ hst, const HmmLayout H,
-                                                        const int force, const ScanBufs B) {
+                                                        const int force, const SeqLevel lv) {
     extern __shared__ __align__(16) double sq[];
     __shared__ __align__(16) double lines[2][32];
     const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
@@ -252,37 +273,48 @@ __global__ void __launch_bounds__(SEQ_T) hmm_seq_kernel(const ScanPlan sp, const
     const int K = sp.K, KK = K * K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb_chunk = seq_batch(K);
     const int stride = KK + K + 8;                       // per chunk: matrix [K][K] | e [K] | {exp(max), ...}
-    const int nsteps = sp.nch - 1;                       // forward: chunks 0 .. nch-2; backward: chunks nch-1 .. 1
+    // this CTA's range of sequential positions [s_lo, s_lo + nsteps): everything (modes 0, 2) or one group (modes 1, 3)
+    const int grp = (lv.mode == 1 || lv.mode == 3) ? (int)blockIdx.x : 0;
+    const int s_lo = grp * SEQ_GLEN;
+    const int nsteps = (lv.mode == 1 || lv.mode == 3) ? min(SEQ_GLEN, lv.nsteps - s_lo) : lv.nsteps;
     const int nbatch = (nsteps + nb_chunk - 1) / nb_chunk;
+    const int n_items = lv.nsteps + 1;                   // chunks (modes 0, 1, 3) or groups + 1 (mode 2) along the sweep
     const bool mine = lane < K;
-    double a = 0.0;
+    // item (chunk / group) handled at sequential position s, and the item whose vector that step produces
+    auto chunk_of = [&](int s) { return (FWD || lv.mode == 2) ? s : n_items - 1 - s; };
+    auto out_of = [&](int s) { return (FWD || lv.mode == 2) ? s + 1 : n_items - 2 - s; };
+    double a = 0.0, lsacc = 0.0;
     if (warp == 0) {
-        if (FWD) {
-            const double* Pc = st + L.params[ctrl[BGMM_CTRL_CUR]];
-            double pmax = -INFINITY;
-            for (int k = 0; k < K; ++k) pmax = fmax(pmax, Pc[L.p_elnpi + k]);
-            a = mine ? exp(Pc[L.p_elnpi + lane] - pmax) : 0.0;
-            if (mine) B.vb[lane] = a;
+        if (lv.mode == 1) {
+            a = (lane == (int)blockIdx.y) ? 1.0 : 0.0;   // unit vector of start state blockIdx.y
+        } else if (lv.mode == 3) {
+            a = mine ? lv.vbg[(int64_t)grp * K + lane] : 0.0;
+            if (grp == 0 && mine) lv.vb[(int64_t)chunk_of(0) * K + lane] = a;
         } else {
-            a = mine ? 1.0 : 0.0;
-            if (mine) B.vb[(int64_t)(sp.nch - 1) * K + lane] = a;
+            if (FWD) {
+                const double* Pc = st + L.params[ctrl[BGMM_CTRL_CUR]];
+                double pmax = -INFINITY;
+                for (int k = 0; k < K; ++k) pmax = fmax(pmax, Pc[L.p_elnpi + k]);
+                a = mine ? exp(Pc[L.p_elnpi + lane] - pmax) : 0.0;
+            } else {
+                a = mine ? 1.0 : 0.0;
+            }
+            if (mine) lv.vb[(int64_t)chunk_of(0) * K + lane] = a;
         }
     }
-    // chunk handled at sequential position s
-    auto chunk_of = [&](int s) { return FWD ? s : sp.nch - 1 - s; };
     auto load_batch = [&](int b, int t0, int nt) {       // threads t0 .. t0+nt-1 of the CTA
         double* dst = sq + (size_t)(b & 1) * nb_chunk * stride;
         const int s0 = b * nb_chunk, cnt = min(nb_chunk, nsteps - s0);
         for (int q = 0; q < cnt; ++q) {
-            const int c = chunk_of(s0 + q);
-            const double* src = B.tf + (int64_t)c * KK;
+            const int c = chunk_of(s_lo + s0 + q);
+            const double* src = lv.tf + (int64_t)c * KK;
             // asynchronous copies: a whole batch is in flight at once (a load -> store loop would serialise on latency)
             if ((K & 1) == 0) {             // K even: every row pair is 16-byte aligned on both sides (stride is even too)
                 for (int e = 2 * (tid - t0); e < KK; e += 2 * nt) cp_async16(dst + q * stride + e, src + e);
-                for (int e = 2 * (tid - t0); e < K; e += 2 * nt) cp_async16(dst + q * stride + KK + e, B.ls + (int64_t)c * K + e);
+                for (int e = 2 * (tid - t0); e < K; e += 2 * nt) cp_async16(dst + q * stride + KK + e, lv.ls + (int64_t)c * K + e);
             } else {
                 for (int e = tid - t0; e < KK; e += nt) cp_async8(dst + q * stride + e, src + e);
-                for (int e = tid - t0; e < K; e += nt) cp_async8(dst + q * stride + KK + e, B.ls + (int64_t)c * K + e);
+                for (int e = tid - t0; e < K; e += nt) cp_async8(dst + q * stride + KK + e, lv.ls + (int64_t)c * K + e);
             }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -361,17 +393,26 @@ __global__ void __launch_bounds__(SEQ_T) hmm_seq_kernel(const ScanPlan sp, const
                     n1 = fma(u.y, m[1], n1); w1 += u.y;
                 }
                 const double nv = (n0 + n1) + (n2 + n3);
-                const int c = chunk_of(s0 + q);
+                const int64_t o = out_of(s_lo + s0 + q);
                 if (FWD) {
-                    a = nv * (1.0 / ((w0 + w1) + (w2 + w3)));          // the reciprocal runs beside the dot product
-                    if (mine) B.vb[(int64_t)(c + 1) * K + lane] = a;
+                    const double wsum = (w0 + w1) + (w2 + w3);
+                    // the reciprocal runs beside the dot product.  wsum == 0 only in mode 1: a unit start state that the
+                    // first chunk makes impossible — its row is exactly zero with log scale -inf, as in phase A
+                    a = nv * (wsum > 0.0 ? 1.0 / wsum : 0.0);
+                    if (lv.mode == 1) lsacc += log(wsum);              // off the dependent chain (a does not wait for it)
                 } else {
                     a = nv * sc_c;
-                    if (mine) B.vb[(int64_t)(c - 1) * K + lane] = a;
                 }
+                if (lv.mode != 1 && mine) lv.vb[o * K + lane] = a;
             }
         }
         __syncthreads();
+    }
+    if (lv.mode == 1 && warp == 0) {
+        // row blockIdx.y of this group's transfer matrix: the end vector of the run from that unit vector (+ its log scale)
+        const int64_t row = (int64_t)grp * K + blockIdx.y;
+        if (mine) lv.tg[row * K + lane] = a;
+        if (lane == 0) lv.lsg[row] = FWD ? lsacc : 0.0;
     }
 }
 
@@ -612,7 +653,31 @@ static int64_t scan_ws_doubles(int K, int64_t n) {
     const int64_t KK = (int64_t)K * K;
     // transfer matrices + log scales + boundary vectors + S partials + the two scalar partial arrays
     // + rhohat [n][K], row max [n], chat [n]
-    return nch * KK + nch * K + nch * K + nch * KK + 2 * nch + 64 + n * K + 3 * n;
+    // + the two-level sweep's group matrices, log scales and boundary vectors (<= 64 + 1 groups)
+    return nch * KK + nch * K + nch * K + nch * KK + 2 * nch + 64 + n * K + 3 * n + 72 * (KK + 2 * K) + 2;
+}
+
+// Phase B of one direction: the single-CTA sweep, or (>= 4 groups of SEQ_GLEN steps) group matrices -> group sweep -> expansion
+template <int KP, bool FWD>
+static void launch_seq(const ScanPlan& sp, double* st, const Layout& L, double* hst, const HmmLayout& H, int force,
+                       const ScanBufs& B, size_t smem_seq, cudaStream_t stream) {
+    const int K = sp.K, nsteps = sp.nch - 1;
+    const int ngroups = (nsteps + SEQ_GLEN - 1) / SEQ_GLEN;
+    static const int two_level = [] { const char* e = getenv("BGMM_HMM_TWO_LEVEL"); return (e == nullptr || atoi(e) != 0) ? 1 : 0; }();
+    SeqLevel lv{0, nsteps, ngroups, B.tf, B.ls, B.vb, nullptr, nullptr, nullptr};
+    if (!two_level || ngroups < 4) {
+        hmm_seq_kernel<KP, FWD><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, lv);
+        return;
+    }
+    double* tg = B.seq2;                                   // [ngroups][K][K]
+    double* lsg = tg + (int64_t)72 * K * K;                // [ngroups][K]
+    double* vbg = lsg + (int64_t)72 * K;                   // [ngroups + 1][K]
+    lv.mode = 1; lv.tg = tg; lv.lsg = lsg;
+    hmm_seq_kernel<KP, FWD><<<dim3(ngroups, K), SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, lv);
+    SeqLevel l2{2, ngroups - 1, ngroups, tg, lsg, vbg, nullptr, nullptr, nullptr};      // the last group's matrix is not needed
+    hmm_seq_kernel<KP, FWD><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, l2);
+    lv.mode = 3; lv.tg = nullptr; lv.lsg = nullptr; lv.vbg = vbg;
+    hmm_seq_kernel<KP, FWD><<<ngroups, SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, lv);
 }
 
 template <int KP>
@@ -632,12 +697,12 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
     // boundary vectors: either {basis runs, sequential sweep} or {one warm-up window per chunk}; the device decides
     // (hmm_window) from the current A~, the kernels of the other branch return at once
     if (sp.nch > 1) hmm_fwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
-    hmm_seq_kernel<KP, true><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, B);
+    launch_seq<KP, true>(sp, st, L, hst, H, force, B, smem_seq, stream);
     hmm_window_kernel<KP, true><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_fwd_kernel<KP, 0><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_cs_kernel<<<sp.nch, 128, 0, stream>>>(sp, st, L, force, B);
     if (sp.nch > 1) hmm_bwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
-    hmm_seq_kernel<KP, false><<<1, SEQ_T, smem_seq, stream>>>(sp, st, L, hst, H, force, B);
+    launch_seq<KP, false>(sp, st, L, hst, H, force, B, smem_seq, stream);
     hmm_window_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_bwd_kernel<KP, 0><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_reduce_kernel<<<(sp.K * sp.K + 2 + 31) / 32, 256, 0, stream>>>(sp, st, L, hst, H, force, B);
@@ -935,6 +1000,7 @@ extern "C" int bgmm_hmm_pass(const void* x, int64_t n, int K, int D, double* sta
         double* rmx = B.chat + n;
         B.rowmax = rmx;
         B.ichat = rmx + n;
+        B.seq2 = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(B.ichat + n) + 15) & ~uintptr_t(15));   // cp.async 16
         a.rhohat_out = rh; a.rowmax_out = rmx;
         rc = launch_emit_small(x, n, K, D, state, L, force, lnrho, rh, rmx, s);
         if (rc == -1) {

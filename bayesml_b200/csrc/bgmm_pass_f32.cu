@@ -9,6 +9,11 @@
 // X is streamed once with coalesced vector loads (D*4 bytes per sample); r never touches HBM.  The whitened form keeps
 // (x' - m'_k) explicit, so fp32 cancellation does not grow with the distance of a component from the centre.
 // The kernel is FP32-issue bound, not HBM bound (8 components per 8-byte sample).
+// Two E-step forms, chosen per launch from the conditioning criterion bgmm_small leaves in ctrl.CRIT (§2 of DESIGN.md):
+//   crit <= 128 (BASELINE C3: 107): the feature-map form  c_k + b_k.x' + x'^T Q_k x'  — 5 FMAs per (sample, component) at
+//                D = 2 on the phi values the statistics need anyway; fp32 error ~ 6e-8 * crit * sqrt(P) <= 2e-5 in ln rho;
+//   otherwise:   the whitened form, 9 operations, which keeps (x' - m'_k) explicit and does not degrade with crit.
+// OUT = false is the loop instantiation (no r / ln rho / argmax stores, no argmax tracking).
 // Replaces `_update_q_z` :772-784, `_calc_n_x_bar_s` :725-732, `xlogy` :704 (reference GMM file) in fp32 mode; parity
 // bar 1e-4 relative against the fp64 oracle fed the same fp32-rounded X.
 #include "bgmm_common.cuh"
@@ -43,7 +48,9 @@ struct F32Params {                   // per component, fp32, in shared memory
     float a2;                        // ln rho constant in base 2
 };
 
-template <int D>
+constexpr int F32_FEAT_CRIT = 128;   // feature-map E-step up to this value of ctrl.CRIT
+
+template <int D, bool OUT>
 __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a, const Layout L) {
     constexpr int P = 1 + D + D * (D + 1) / 2;
     constexpr int NW = F32_THREADS / 32;
@@ -56,6 +63,7 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
     if (pass_skip(ctrl, a.force, a.ignore_robust)) return;
     const double* Pc = a.state + L.params[ctrl[BGMM_CTRL_CUR]];
     const float* __restrict__ x = static_cast<const float*>(a.x);
+    const bool feat = ctrl[BGMM_CTRL_CRIT] <= F32_FEAT_CRIT;   // uniform: which E-step form this launch uses
 
     // ---- prologue: whitening factors of Lambda_k = nu_k W_k (fp64 Cholesky of a D x D matrix per component) ----
     if (tid < F32_KMAX) {
@@ -81,6 +89,14 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
             const double ak = Pc[L.p_elnpi + k] + 0.5 * (Pc[L.p_elndet + k] - D * 1.837877066409345483560659472811 - D / kappa);
             q.a2 = (float)(ak * 1.4426950408889634074);
             if (!ok) ctrl[BGMM_CTRL_ERROR] = 1;
+            if (feat) {
+                // the same slots hold the feature-map coefficients in base 2: a2 <- constant, m[i] <- linear, lt[(i,j)] <- quadratic
+                const double* cf = Pc + L.p_coef + (int64_t)k * L.pitch;
+                const double l2e = 1.4426950408889634074;
+                q.a2 = (float)(cf[0] * l2e);
+                for (int i = 0; i < D; ++i) q.m[i] = (float)(cf[1 + i] * l2e);
+                for (int i = 0; i < D * (D + 1) / 2; ++i) q.lt[i] = (float)(cf[1 + D + i] * l2e);
+            }
         } else {
             for (int i = 0; i < D; ++i) q.m[i] = 0.f;
             for (int i = 0; i < D * (D + 1) / 2; ++i) q.lt[i] = 0.f;
@@ -163,9 +179,30 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
 #pragma unroll
         for (int i = 0; i < D; ++i) { xv[i] = xn1[i]; xn1[i] = xn2[i]; }
         load_row(n + 2 * stride, xn2);
+        // statistics features about the global centre: phi = [1, x, x_i x_j (i >= j)] (also the E-step's in the feature form)
+        float phi[P];
+        phi[0] = 1.f;
+#pragma unroll
+        for (int i = 0; i < D; ++i) phi[1 + i] = xv[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) phi[1 + D + i * (i + 1) / 2 + j] = xv[i] * xv[j];
         // E-step
         float l2[F32_KMAX];
         float mx = -3.0e38f;
+        if (feat) {
+#pragma unroll
+            for (int k = 0; k < F32_KMAX; ++k) {
+                float v = kRegParams ? pa2[kRegParams ? k : 0] : prm[k].a2;
+#pragma unroll
+                for (int i = 0; i < D; ++i) v = fmaf(kRegParams ? pm[kRegParams ? k : 0][i] : prm[k].m[i], phi[1 + i], v);
+#pragma unroll
+                for (int i = 0; i < NLT; ++i) v = fmaf(kRegParams ? plt[kRegParams ? k : 0][i] : prm[k].lt[i], phi[1 + D + i], v);
+                l2[k] = v;
+                mx = fmaxf(mx, v);
+            }
+        } else {
 #pragma unroll
         for (int k = 0; k < F32_KMAX; ++k) {
             float d[D];
@@ -183,7 +220,8 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
             l2[k] = (kRegParams ? pa2[kRegParams ? k : 0] : prm[k].a2) - qf;
             mx = fmaxf(mx, l2[k]);
         }
-        if (a.lnrho_out != nullptr && valid) {
+        }
+        if (OUT && a.lnrho_out != nullptr && valid) {
 #pragma unroll
             for (int k = 0; k < F32_KMAX; ++k)          // unrolled + guarded: keeps l2[] in registers
                 if (k < K) a.lnrho_out[n * K + k] = (double)l2[k] * 0.693147180559945309417232121458;
@@ -198,32 +236,23 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
         }
         const float inv = valid ? rcp_approx(s) : 0.f;  // 1 <= s <= K
         if (valid) ent += 0.693147180559945309f * (dot * inv - lg2_approx(s));
-        // statistics about the global centre: phi = [1, x, x_i x_j (i >= j)]
-        float phi[P];
-        phi[0] = 1.f;
-#pragma unroll
-        for (int i = 0; i < D; ++i) phi[1 + i] = xv[i];
-#pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) phi[1 + D + i * (i + 1) / 2 + j] = xv[i] * xv[j];
         int best = 0;
         float bestv = -1.f;
 #pragma unroll
         for (int k = 0; k < F32_KMAX; ++k) {
             const float r = e[k] * inv;
             e[k] = r;
-            if (r > bestv) { bestv = r; best = k; }
+            if (OUT) { if (r > bestv) { bestv = r; best = k; } }
             acc[k][0] += r;
 #pragma unroll
             for (int p = 1; p < P; ++p) acc[k][p] = fmaf(r, phi[p], acc[k][p]);
         }
-        if (a.r_out != nullptr && valid) {
+        if (OUT && a.r_out != nullptr && valid) {
 #pragma unroll
             for (int k = 0; k < F32_KMAX; ++k)
                 if (k < K) a.r_out[n * K + k] = (double)e[k];
         }
-        if (a.argmax_out != nullptr && valid) a.argmax_out[n] = best;
+        if (OUT && a.argmax_out != nullptr && valid) a.argmax_out[n] = best;
         if (++pending == F32_FLUSH) flush();
     }
     flush();
@@ -277,11 +306,11 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
 
 bool f32_supported(int K, int D, int dtype) { return dtype == BGMM_F32 && D >= 1 && D <= 3 && K <= F32_KMAX; }
 
-template <int D>
+template <int D, bool OUT>
 static int f32_grid(int64_t n) {
     int dev = 0, sms = 148, occ = 1;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_f32_kernel<D>, F32_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_f32_kernel<D, OUT>, F32_THREADS, 0);
     if (occ < 1) occ = 1;
     const int64_t want = (n + F32_THREADS - 1) / F32_THREADS;
     int64_t cap = (int64_t)sms * occ;                          // one resident wave: persistent grid-stride CTAs
@@ -300,9 +329,11 @@ int launch_pass_f32(const PassArgs& a, int K, int D, int dtype, cudaStream_t str
         return BGMM_ENOSUP;
     }
     const Layout L = make_layout(K, D, 1);
-    if (D == 1) pass_f32_kernel<1><<<f32_grid<1>(a.n), F32_THREADS, 0, stream>>>(a, L);
-    else if (D == 2) pass_f32_kernel<2><<<f32_grid<2>(a.n), F32_THREADS, 0, stream>>>(a, L);
-    else pass_f32_kernel<3><<<f32_grid<3>(a.n), F32_THREADS, 0, stream>>>(a, L);
+    const bool out = a.r_out != nullptr || a.lnrho_out != nullptr || a.argmax_out != nullptr;
+#define BGMM_F32_CASE(d, o) if (D == d && out == o) pass_f32_kernel<d, o><<<f32_grid<d, o>(a.n), F32_THREADS, 0, stream>>>(a, L);
+    BGMM_F32_CASE(1, false) BGMM_F32_CASE(1, true) BGMM_F32_CASE(2, false) BGMM_F32_CASE(2, true)
+    BGMM_F32_CASE(3, false) BGMM_F32_CASE(3, true)
+#undef BGMM_F32_CASE
     return check_cuda(cudaGetLastError(), "pass_f32_kernel launch");
 }
 

@@ -351,8 +351,10 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     double crit = 0.0;
     for (int j = 0; j < K; ++j) crit = fmax(crit, vk[j * 8 + 7]);
     const int robust = crit > robust_thresh ? 1 : 0;
+    const int critq = crit < 1073741824.0 ? (int)ceil(crit) : 1073741824;     // NaN -> the large value
     if (!iterate) {
         ctrl[BGMM_CTRL_ROBUST] = robust;
+        ctrl[BGMM_CTRL_CRIT] = critq;
         ctrl[BGMM_CTRL_TICKET] = 0;
         return;
     }
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
     }
     if (conv) { ctrl[BGMM_CTRL_CONVERGED] = 1; ctrl[BGMM_CTRL_DONE] = 1; }
     else if (iter >= max_itr || ctrl[BGMM_CTRL_ERROR]) { ctrl[BGMM_CTRL_DONE] = 1; }   // error: queued launches become no-ops
-    else { ctrl[BGMM_CTRL_CUR] = cur ^ 1; ctrl[BGMM_CTRL_ROBUST] = robust; }
+    else { ctrl[BGMM_CTRL_CUR] = cur ^ 1; ctrl[BGMM_CTRL_ROBUST] = robust; ctrl[BGMM_CTRL_CRIT] = critq; }
     ctrl[BGMM_CTRL_ITER] = iter + 1;
     ctrl[BGMM_CTRL_TICKET] = 0;
 }
@@ -705,8 +707,9 @@ __global__ void __launch_bounds__(32) small_warp_kernel(double* __restrict__ st,
     qml = warp_sum(qml); asum = warp_sum(asum);
     for (int o = 16; o > 0; o >>= 1) crit = fmax(crit, __shfl_xor_sync(full, crit, o));
     const int robust = crit > robust_thresh ? 1 : 0;
+    const int critq = crit < 1073741824.0 ? (int)ceil(crit) : 1073741824;     // NaN -> the large value
     if (!iterate) {
-        if (lane == 0) { ctrl[BGMM_CTRL_ROBUST] = robust; ctrl[BGMM_CTRL_TICKET] = 0; }
+        if (lane == 0) { ctrl[BGMM_CTRL_ROBUST] = robust; ctrl[BGMM_CTRL_CRIT] = critq; ctrl[BGMM_CTRL_TICKET] = 0; }
         return;
     }
     // lane 0: lgamma(sum alpha), lane 1: digamma(sum alpha) — one divergent pair instead of two serial calls
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(32) small_warp_kernel(double* __restrict__ st,
     }
     if (conv) { ctrl[BGMM_CTRL_CONVERGED] = 1; ctrl[BGMM_CTRL_DONE] = 1; }
     else if (iter >= max_itr || ctrl[BGMM_CTRL_ERROR]) { ctrl[BGMM_CTRL_DONE] = 1; }
-    else { ctrl[BGMM_CTRL_CUR] = cur ^ 1; ctrl[BGMM_CTRL_ROBUST] = robust; }
+    else { ctrl[BGMM_CTRL_CUR] = cur ^ 1; ctrl[BGMM_CTRL_ROBUST] = robust; ctrl[BGMM_CTRL_CRIT] = critq; }
     ctrl[BGMM_CTRL_ITER] = iter + 1;
     ctrl[BGMM_CTRL_TICKET] = 0;
 }

@@ -1,0 +1,110 @@
+// tcgen05 / TMEM primitives for sm_100a (inline PTX) used by the fp32-mode tensor-core kernels (bgmm_pass_tf32.cu).
+// Conventions follow the CUTLASS SM100 descriptors (cute/arch/mma_sm100_desc.hpp): shared-memory matrix descriptors in the
+// no-swizzle ("interleave") canonical layout made of 8 x 16-byte core matrices, instruction descriptor for kind::tf32 with
+// fp32 accumulators in tensor memory.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bgmm {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- tensor memory ----
+// one full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *slot (shared memory)
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (the tensor core reads operands through it)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- descriptors ----
+// Shared-memory matrix descriptor, no swizzle.  A core matrix is 8 rows x 16 bytes, stored contiguously (128 bytes).
+//   K-major operand  (rows = M or N index, 16-byte chunk = 4 consecutive k):   LBO = byte distance between the two k-chunks
+//                     of one MMA (K = 8 tf32), SBO = byte distance between consecutive 8-row groups;
+//   MN-major operand (rows = k index, 16-byte chunk = 4 consecutive m or n):   SBO = byte distance between consecutive
+//                     4-element chunks along M / N, LBO = byte distance between consecutive 8-row k groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+    return d;                                 // base offset 0, lbo mode 0, layout type 0 (no swizzle)
+}
+// Instruction descriptor for kind::tf32: fp32 accumulate, A and B tf32, M x N tile, K-major (0) or MN-major (1) operands.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] . B[smem];  issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// mbarrier arrive when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+// ---- tensor memory -> registers: lane = row of the accumulator tile, this warp's 32 lanes, 32 consecutive columns ----
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- 3xTF32 split: v = hi + lo with hi = round-to-nearest tf32 (unbiased), lo = the exact remainder (the MMA reads its
+//      top 19 bits); hi*hi + hi*lo + lo*hi keeps ~21 bits of every product ----
+__device__ __forceinline__ float tf32_hi(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// canonical no-swizzle offsets (in floats) of element (row, col) of a tile whose row groups / chunks are laid out as stated
+//   K-major tile [rows][kcols]: core (row / 8, col / 4) at (row / 8) * sbo_f + (col / 4) * lbo_f
+__device__ __forceinline__ int kmajor_off(int row, int col, int lbo_f, int sbo_f) {
+    return (row >> 3) * sbo_f + (col >> 2) * lbo_f + (row & 7) * 4 + (col & 3);
+}
+//   MN-major tile [krows][mncols]: core (k / 8, mn / 4) at (mn / 4) * sbo_f + (k / 8) * lbo_f
+__device__ __forceinline__ int mnmajor_off(int k, int mn, int lbo_f, int sbo_f) {
+    return (mn >> 2) * sbo_f + (k >> 3) * lbo_f + (k & 7) * 4 + (mn & 3);
+}
+
+}  // namespace tc
+}  // namespace bgmm

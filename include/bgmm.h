@@ -123,6 +123,8 @@ enum {
     BGMM_CTRL_SEQ,        /* number of peer-memory exchanges published so far (bgmm_publish)        */
     BGMM_CTRL_ROBUST,     /* 1 -> the current parameter set is ill-conditioned for the feature-map kernels:
                              bgmm_pass runs the DIRECT kernel (set by bgmm_small for every new parameter set)  */
+    BGMM_CTRL_CRIT,       /* the conditioning criterion itself, ceil(min(crit, 2^30)), for kernels with their own limit
+                             (the fp32 kernel takes the feature-map E-step up to 128)                                 */
     BGMM_CTRL_COMM_LO = 10, /* low / high 32 bits of the DEVICE address of the peer-exchange descriptor (see below), or 0.  */
     BGMM_CTRL_COMM_HI,    /* When set (by the caller, once), every bgmm_pass PUBLISHES the statistics it has just reduced
                              (copy into the own exchange block + stamps, what bgmm_publish does) from the reduction's last
@@ -221,6 +223,12 @@ int bgmm_dirichlet1(double* r_out, int64_t n, int K, uint64_t seed, int64_t row_
  *   the global row index row_offset + i).  Same distribution as the reference, NOT numpy's random stream.  D <= 256. */
 int bgmm_gen_sample(double* x_out, int32_t* z_out, int64_t n, int K, int D, const double* cdf, const double* mu,
                     const double* chol, uint64_t seed, int64_t row_offset, void* stream);
+
+/* ---- 5th-generation tensor cores (fp32 mode) ----
+ * bgmm_tc_selftest: D[128][N] = A[128][Kd] . B[N][Kd]^T with tcgen05.mma kind::tf32 (operands staged in shared memory in the
+ * no-swizzle canonical layout, K-major or MN-major; accumulator in tensor memory, read back with tcgen05.ld) — the unit test
+ * of the descriptor conventions the fp32-mode kernels use.  A, B, D: device float32 arrays, row-major as written. */
+int bgmm_tc_selftest(const float* A, const float* B, float* D, int N, int Kd, int a_mn_major, int b_mn_major, void* stream);
 
 /* ---- multi-GPU exchange over NVLink peer memory (no reference counterpart: the reference is single-process) ----
  * Row-sharded fit: the per-iteration all-reduce of state.STATS is fused into bgmm_small.  Every rank owns an exchange

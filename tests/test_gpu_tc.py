@@ -1,0 +1,32 @@
+"""GPU: the tcgen05 / tensor-memory conventions (csrc/bgmm_tc.cuh) — D = A . B^T with kind::tf32 for every operand layout."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tf32(a):
+    return (np.ascontiguousarray(a, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+# K-major operands only: with either operand MN-major in the no-swizzle layout the B200 returned an all-zero tile for
+# kind::tf32 (measured in round 2, scratch note in DESIGN.md §4.7), so the fp32-mode kernels stage every operand K-major.
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0)])
+@pytest.mark.parametrize("n,kd", [(16, 8), (64, 24), (256, 32), (32, 64)])
+def test_tcgen05_tf32_matmul(n, kd, a_mn, b_mn):
+    import torch
+    from bayesml_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n + kd)
+    a = rng.normal(size=(128, kd)).astype(np.float32)
+    b = rng.normal(size=(n, kd)).astype(np.float32)
+    ad, bd = torch.as_tensor(a).cuda(), torch.as_tensor(b).cuda()
+    dd = torch.zeros((128, n), dtype=torch.float32, device="cuda")
+    _lib.check(lib.bgmm_tc_selftest(ad.data_ptr(), bd.data_ptr(), dd.data_ptr(), n, kd, a_mn, b_mn,
+                                    torch.cuda.current_stream().cuda_stream), "bgmm_tc_selftest")
+    torch.cuda.synchronize()
+    want = _tf32(a).astype(np.float64) @ _tf32(b).astype(np.float64).T       # the tensor core reads the top 19 bits
+    got = dd.cpu().numpy()
+    assert np.allclose(got, want, rtol=0, atol=2e-5 * np.sqrt(kd)), np.max(np.abs(got - want))
