@@ -27,7 +27,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import FP64_PEAK_TFLOPS, ClockSampler, blas_threads  # noqa: E402
+from bench import ClockSampler, blas_threads, load_peaks  # noqa: E402
+FP64_PEAK_TFLOPS = load_peaks()["fp64_tflops"]
 
 METRIC = "VB iters/sec (N*K elements*states/s) HMM"
 UNIT = "element*states/s"
