@@ -9,14 +9,14 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libbgmm.so")
 
 # constants mirrored from include/bgmm.h (checked against bgmm_abi_version at load time)
-ABI_VERSION = 3
+ABI_VERSION = 4
 F64, F32 = 0, 1
-PASS_AUTO, PASS_SIMPLE, PASS_DMMA, PASS_F32, PASS_LARGE, PASS_DIRECT = 0, 1, 2, 3, 4, 5
+PASS_AUTO, PASS_SIMPLE, PASS_DMMA, PASS_F32, PASS_LARGE, PASS_DIRECT, PASS_TF32 = 0, 1, 2, 3, 4, 5, 6
 SMALL_FEATURES, SMALL_ITERATE, SMALL_STATS = 0, 1, 2
 
 OFF_NAMES = ("center", "alpha0", "kappa0", "nu0", "m0", "w0inv", "lnb0", "lnc0", "params0", "params1", "stats",
              "ns", "xbar", "smats", "vlk", "vlterms", "vlhist", "ctrl", "total", "stats_len", "params_len", "pitch", "shift")
-POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb", "coef", "acst")
+POFF_NAMES = ("alpha", "kappa", "nu", "m", "winv", "w", "elnpi", "elndet", "lnb", "coef", "acst", "linv")
 CTRL_CUR, CTRL_ITER, CTRL_DONE, CTRL_CONVERGED, CTRL_TICKET, CTRL_PASS_TICKET, CTRL_ERROR, CTRL_SEQ, CTRL_ROBUST, CTRL_CRIT = range(10)
 CTRL_COMM_LO, CTRL_COMM_HI = 10, 11
 FORCE, FORCE_NO_PUBLISH = 1, 2
@@ -71,6 +71,8 @@ def load():
     lib.bgmm_gen_sample.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, ctypes.c_uint64, i64, vp]
     lib.bgmm_tc_selftest.restype = i32
     lib.bgmm_tc_selftest.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.bgmm_tf32_workspace_doubles.restype = i64
+    lib.bgmm_tf32_workspace_doubles.argtypes = [i32, i32, i64]
     lib.bgmm_pass_supported.restype = i32
     lib.bgmm_pass_supported.argtypes = [i32, i32, i32, i32]
     lib.bgmm_pass_resolve.restype = i32

@@ -12,7 +12,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libbgmm.so")
 SOURCES = ["bgmm_api.cu", "bgmm_small.cu", "bgmm_pass_simple.cu", "bgmm_pass_dmma.cu", "bgmm_pass_f32.cu", "bgmm_comm.cu", "bgmm_pass_large.cu",
-           "bgmm_hmm.cu", "bgmm_extras.cu", "bgmm_tc_selftest.cu"]
+           "bgmm_hmm.cu", "bgmm_extras.cu", "bgmm_tc_selftest.cu", "bgmm_pass_tf32.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
 

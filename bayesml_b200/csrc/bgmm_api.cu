@@ -41,6 +41,9 @@ int64_t f32_workspace_doubles(int K, int D);
 bool large_supported(int K, int D, int dtype);
 int launch_pass_large(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream);
 int64_t large_workspace_doubles(int K, int D);
+bool tf32_pass_supported(int K, int D, int dtype);
+int launch_pass_tf32(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream);
+int64_t tf32_workspace_doubles(int K, int D, int64_t n);
 int launch_pass_batched(const void* x, int64_t n, int K, int D, const BatchDesc& bd, double* sup, double* workspace,
                         double* r_scratch, cudaStream_t stream);
 
@@ -110,7 +113,7 @@ extern "C" int bgmm_layout(int K, int D, int hist_len, int64_t* off, int64_t* po
     poff[BGMM_P_ALPHA] = L.p_alpha; poff[BGMM_P_KAPPA] = L.p_kappa; poff[BGMM_P_NU] = L.p_nu; poff[BGMM_P_M] = L.p_m;
     poff[BGMM_P_WINV] = L.p_winv; poff[BGMM_P_W] = L.p_w; poff[BGMM_P_ELNPI] = L.p_elnpi;
     poff[BGMM_P_ELNDET] = L.p_elndet; poff[BGMM_P_LNB] = L.p_lnb; poff[BGMM_P_COEF] = L.p_coef;
-    poff[BGMM_P_ACST] = L.p_acst;
+    poff[BGMM_P_ACST] = L.p_acst; poff[BGMM_P_LINV] = L.p_linv;
     return BGMM_OK;
 }
 
@@ -204,11 +207,17 @@ extern "C" int bgmm_pass_batched(const void* x, int64_t n, int K, int D, int R, 
     return rc;
 }
 
+extern "C" int64_t bgmm_tf32_workspace_doubles(int K, int D, int64_t n) {
+    if (K <= 0 || D <= 0 || n < 0) return 0;
+    return tf32_workspace_doubles(K, D, n);
+}
+
 extern "C" int bgmm_pass_supported(int K, int D, int dtype, int variant) {
     if (K <= 0 || D <= 0 || (dtype != BGMM_F64 && dtype != BGMM_F32)) return 0;
     if (variant == BGMM_PASS_DMMA) return dmma_supported(K, D, dtype) ? 1 : 0;
     if (variant == BGMM_PASS_F32) return f32_supported(K, D, dtype) ? 1 : 0;
     if (variant == BGMM_PASS_LARGE) return large_supported(K, D, dtype) ? 1 : 0;
+    if (variant == BGMM_PASS_TF32) return tf32_pass_supported(K, D, dtype) ? 1 : 0;
     return variant == BGMM_PASS_SIMPLE || variant == BGMM_PASS_AUTO || variant == BGMM_PASS_DIRECT;
 }
 
@@ -218,6 +227,7 @@ extern "C" int bgmm_pass_resolve(int K, int D, int dtype, int variant, int has_r
     if (dmma_supported(K, D, dtype)) return BGMM_PASS_DMMA;
     if (large_supported(K, D, dtype)) return BGMM_PASS_LARGE;
     if (f32_supported(K, D, dtype)) return BGMM_PASS_F32;
+    if (tf32_pass_supported(K, D, dtype)) return BGMM_PASS_TF32;
     return BGMM_PASS_SIMPLE;
 }
 
@@ -260,6 +270,9 @@ extern "C" int bgmm_pass(const void* x, int64_t n, int K, int D, int dtype, doub
             return BGMM_ENOSUP;
         }
         rc = launch_pass_dmma(a, K, D, dtype, s);
+    } else if (variant == BGMM_PASS_TF32) {
+        a.crit_limit = 4096;
+        rc = launch_pass_tf32(a, K, D, dtype, s);
     } else if (variant == BGMM_PASS_SIMPLE) {
         rc = launch_pass_simple(a, K, D, dtype, 0, s);
     } else {

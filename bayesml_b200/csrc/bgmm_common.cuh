@@ -15,7 +15,7 @@ struct Layout {
     int64_t center, alpha0, kappa0, nu0, m0, w0inv, lnb0, lnc0, params[2], stats, ns, xbar, smats, vlk, vlterms,
         vlhist, ctrl, total, stats_len, params_len, shift;
     // offsets inside one parameter set
-    int64_t p_alpha, p_kappa, p_nu, p_m, p_winv, p_w, p_elnpi, p_elndet, p_lnb, p_coef, p_acst;
+    int64_t p_alpha, p_kappa, p_nu, p_m, p_winv, p_w, p_elnpi, p_elndet, p_lnb, p_coef, p_acst, p_linv;
 };
 
 __host__ __device__ inline int64_t align8(int64_t v) { return (v + 7) & ~int64_t(7); }
@@ -36,6 +36,7 @@ __host__ __device__ inline Layout make_layout(int K, int D, int hist_len) {
     L.p_lnb = o;    o += align8(K);
     L.p_coef = o;   o += (int64_t)K * L.pitch;
     L.p_acst = o;   o += align8(K);
+    L.p_linv = o;   o += align8(KDD);
     L.params_len = o;
     o = 0;
     L.center = o;  o += align8(D);
@@ -126,6 +127,8 @@ struct PassArgs {
     // conditioning guard (ctrl.ROBUST): 0 = feature-map kernel, returns at once when the flag is set (the DIRECT kernel
     // launched behind it does the pass); 1 = ignore the flag (given responsibilities, hidden-Markov path, forced variant)
     int ignore_robust = 0;
+    int crit_limit = 0;   // > 0: this pass hands over to the DIRECT kernel when ctrl.CRIT exceeds it (fp32-mode kernels have a
+                          // lower limit than the fp64 threshold behind ctrl.ROBUST); 0: ctrl.ROBUST decides
     int lnrho_only = 0;   // large-regime E kernel: write ln rho only (no softmax / r / entropy): the HMM emission pass
     double* rhohat_out = nullptr;   // with lnrho_only: exp(ln rho - row max) [n][K] and the row max [n] (scan inputs)
     double* rowmax_out = nullptr;
@@ -159,8 +162,11 @@ __host__ __device__ inline HmmLayout make_hmm_layout(int K) {
 // Entry test of every pass kernel: queued launches after convergence are no-ops (ctrl.done), and the feature-map kernels
 // stand down when bgmm_small has flagged the current parameter set as ill-conditioned (ctrl.robust): the DIRECT kernel
 // launched behind them does that pass.
-__device__ __forceinline__ bool pass_skip(const volatile int* ctrl, int force, int ignore_robust) {
-    return (!force && ctrl[BGMM_CTRL_DONE]) || (!ignore_robust && ctrl[BGMM_CTRL_ROBUST]);
+__device__ __forceinline__ bool robust_set(const volatile int* ctrl, int crit_limit) {
+    return crit_limit > 0 ? ctrl[BGMM_CTRL_CRIT] > crit_limit : ctrl[BGMM_CTRL_ROBUST] != 0;
+}
+__device__ __forceinline__ bool pass_skip(const volatile int* ctrl, int force, int ignore_robust, int crit_limit = 0) {
+    return (!force && ctrl[BGMM_CTRL_DONE]) || (!ignore_robust && robust_set(ctrl, crit_limit));
 }
 
 double robust_threshold();

@@ -394,11 +394,12 @@ pass_dmma_kernel(const PassArgs a, const Layout L) {
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ ws, const int nparts,
                                                               const int64_t len, double* __restrict__ st, const Layout L,
                                                               const double rows, const int accumulate, const int force,
-                                                              const int ignore_robust, const int no_publish) {
+                                                              const int ignore_robust, const int no_publish,
+                                                              const int crit_limit) {
     pdl_trigger();
     pdl_wait();
     volatile int* ctrl = reinterpret_cast<volatile int*>(st + L.ctrl);
-    if (pass_skip(ctrl, force, ignore_robust)) return;
+    if (pass_skip(ctrl, force, ignore_robust, crit_limit)) return;
     double* __restrict__ out = st + L.stats;
     const int64_t rows_slot = (int64_t)L.K * L.pitch + 1;
     const CommDesc* cd = no_publish ? nullptr : comm_of(ctrl);
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
 void launch_reduce_partials(const PassArgs& a, const Layout& L, int nparts, cudaStream_t stream) {
     const int64_t len = L.stats_len;
     launch_pdl(reduce_partials_kernel, dim3((unsigned)((len + 31) / 32)), dim3(256), 0, stream, (const double*)a.workspace,
-               nparts, len, a.state, L, (double)a.n, a.accumulate, a.force, a.ignore_robust, a.no_publish);
+               nparts, len, a.state, L, (double)a.n, a.accumulate, a.force, a.ignore_robust, a.no_publish, a.crit_limit);
 }
 
 struct DmmaPlan {

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(SIMPLE_THREADS) pass_simple_kernel(const PassA
     pdl_wait();
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
     if (!a.force && ctrl[BGMM_CTRL_DONE]) return;
-    if (!a.ignore_robust && (ctrl[BGMM_CTRL_ROBUST] != 0) != DIRECT) return;   // the other form does this pass
+    if (!a.ignore_robust && robust_set(ctrl, a.crit_limit) != DIRECT) return;   // the other form does this pass
     const double* __restrict__ Pc = a.state + L.params[ctrl[BGMM_CTRL_CUR]];
     const double* __restrict__ coef = Pc + L.p_coef;
     const double* __restrict__ mvec = Pc + L.p_m;              // [K][D] (DIRECT)

@@ -1,0 +1,694 @@
+// bgmm_pass, fp32-mode tensor-core variant (BGMM_PASS_TF32) for sm_100a: tcgen05.mma kind::tf32 with 3xTF32 operands,
+// fp32 accumulators in tensor memory, read back with tcgen05.ld.  X is float32 ("fp32 mode", BASELINE.json north_star (1)).
+//
+// Which formulation (profiles/r02_fp32_precision_study.json, tools/fp32_precision_study.py): in fp32 the feature-map E-step
+// loses eps32 * crit (2e-4 in ln rho at C2's geometry with a 3xTF32 split), the WHITENED form does not:
+//     y_nk = sqrt(nu_k) Linv_k (x_n - m_k)      ln rho_nk = a_k - |y_nk|^2 / 2          (7e-6 at C2 in fp32)
+// and it is one GEMM:  Y[n][(k, j)] = [x_n, 1] . B,  B[(k, j)][i] = s_k Linv_k[j][i],  B[(k, j)][D] = -s_k (Linv_k m_k)[j],
+// s_k = sqrt(nu_k log2(e) / 2)  (so ln rho in base 2 is a2_k - |y|^2), with the row norms, the softmax over k, the entropy
+// term and r in the epilogue of the thread that owns the row (a TMEM lane is a sample: no shuffles at all).
+//
+//   tf32_prep_kernel    per iteration: B (hi / lo parts, already in the shared-memory operand layout) and a2 from the
+//                       parameter set (Linv comes from bgmm_small: BGMM_P_LINV);
+//   pass_tf32_e_kernel  persistent, one CTA (128 threads) per SM, 128-sample tiles: the [x, 1] tile is split into
+//                       tf32 hi + lo and staged K-major in shared memory (two stages); ONE thread issues, per 256-column
+//                       chunk of (component, dimension) pairs, the three products hi.hi + hi.lo + lo.hi into one of two
+//                       TMEM buffers and commits to an mbarrier; all four warps read the chunk back (tcgen05.ld, lane =
+//                       sample), accumulate |y|^2 per component, and the next chunk's MMAs run meanwhile;
+//                       r (float32, [n][KP]) goes to HBM for the statistics kernel — 4 KP bytes per sample.
+// Operands are staged K-major in the no-swizzle canonical layout (bgmm_tc.cuh; verified on the B200 by
+// tests/test_gpu_tc.py).  Replaces `_update_q_z` :772-783 of the reference GMM file in fp32 mode; bar 1e-4.
+#include "bgmm_common.cuh"
+#include "bgmm_mma.cuh"
+#include "bgmm_tc.cuh"
+#include <math.h>
+
+namespace bgmm {
+
+constexpr int TF_TILE = 128;                 // samples per tile = TMEM lanes = threads
+constexpr int TF_NMAX = 256;                 // columns of one MMA / one TMEM buffer
+
+struct Tf32Plan {
+    bool ok;
+    int D, K, DP, KD, KP, cpc, nchunks, nmma;    // padded dims; components per chunk; chunk count; MMA N
+    size_t smem_e;
+};
+
+static Tf32Plan plan_tf32(int K, int D) {
+    Tf32Plan p{};
+    p.D = D; p.K = K;
+    p.DP = D <= 4 ? 4 : (D <= 8 ? 8 : (D <= 16 ? 16 : 32));
+    p.KD = (D + 1 + 7) & ~7;
+    p.KP = (K + 3) & ~3;
+    p.cpc = (TF_NMAX / p.DP) & ~3;
+    if (p.cpc > p.KP) p.cpc = p.KP;
+    p.nchunks = (p.KP + p.cpc - 1) / p.cpc;
+    p.nmma = p.cpc * p.DP;
+    // B (hi, lo) for every chunk + two stages of A (hi, lo) + a2 + barriers
+    p.smem_e = sizeof(float) * ((size_t)2 * p.nchunks * p.nmma * p.KD + (size_t)2 * 2 * TF_TILE * p.KD + 64 + 12 * TF_TILE + TF_TILE * 68) + 256;
+    p.ok = D >= 1 && D <= 31 && K >= 1 && K <= 64 && p.KD <= 32 && p.smem_e <= 220 * 1024 && (p.nmma % 16) == 0;
+    return p;
+}
+
+bool tf32_supported(int K, int D, int dtype) { return dtype == BGMM_F32 && plan_tf32(K, D).ok; }
+
+// floats of global scratch: the operand image of B (hi, lo) + a2
+int64_t tf32_image_floats(int K, int D) {
+    const Tf32Plan p = plan_tf32(K, D);
+    return p.ok ? (int64_t)2 * p.nchunks * p.nmma * p.KD + 64 : 0;
+}
+
+// ---- per iteration: the whitening operand, split and laid out as the E kernel's shared-memory image ----
+// image = [part (hi, lo)][chunk][K-major tile: nmma rows x KD cols, LBO = 128 B, SBO = (KD / 4) * 128 B] then a2[64]
+__global__ void __launch_bounds__(256) tf32_prep_kernel(const double* __restrict__ st, const Layout L, float* __restrict__ img,
+                                                        const int DP, const int KD, const int KP, const int cpc,
+                                                        const int nchunks, const int nmma, const int force,
+                                                        const int crit_limit) {
+    pdl_trigger();
+    pdl_wait();
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (pass_skip(ctrl, force, 0, crit_limit)) return;
+    const int K = L.K, D = L.D;
+    const double* Pc = st + L.params[ctrl[BGMM_CTRL_CUR]];
+    const int64_t part = (int64_t)nchunks * nmma * KD;
+    const int lbo_f = 32, sbo_f = (KD / 4) * 32;
+    const int total = nchunks * nmma * KD;
+    for (int e = blockIdx.x * 256 + threadIdx.x; e < total; e += gridDim.x * 256) {
+        const int ch = e / (nmma * KD), rem = e - ch * nmma * KD;
+        const int n = rem / KD, i = rem - n * KD;                // row n = (local component, dimension j), column i
+        const int c = ch * cpc + n / DP, j = n % DP;
+        double v = 0.0;
+        if (c < K && j < D) {
+            const double s = sqrt(Pc[L.p_nu + c] * (0.5 * 1.4426950408889634074));
+            const double* Li = Pc + L.p_linv + (int64_t)c * D * D + (int64_t)j * D;      // row j of Linv_c
+            if (i < D) v = s * Li[i];
+            else if (i == D) {
+                const double* m = Pc + L.p_m + (int64_t)c * D;
+                double acc = 0.0;
+                for (int l = 0; l <= j; ++l) acc += Li[l] * m[l];
+                v = -s * acc;
+            }
+        }
+        const float hi = tc::tf32_hi((float)v);
+        const float lo = (float)(v - (double)hi);
+        const int64_t o = (int64_t)ch * nmma * KD + tc::kmajor_off(n, i, lbo_f, sbo_f);
+        img[o] = hi;
+        img[part + o] = lo;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        img[2 * part + c] = c < K ? (float)(Pc[L.p_acst + c] * 1.4426950408889634074) : -1.0e30f;
+    }
+}
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// r_f32 [n][KP] float32: the hand-over to the statistics kernel.  Optional float64 outputs as in the other variants.
+// 512 threads = 4 groups of 4 warps.  A TMEM lane (= sample row) is readable by the warps w with w % 4 == lane / 32, so the
+// four groups share every row and split its COLUMNS: group q reads the q-th 64-column batch of every chunk.  One warp per
+// scheduler (the first version, 128 threads) left the epilogue latency bound at ~11 cycles per instruction — 4.1 ms at C2
+// against 0.6 ms of tensor-core time; four warps per scheduler hide it.  The softmax over k then spans four threads:
+// max, sum and the entropy dot product are combined through shared memory ([4][128] floats, two block barriers).
+constexpr int TE_THREADS = 512;
+
+// OUT = false: the loop instantiation (no float64 ln rho / r / arg-max outputs: their predicated-off stores and conversions
+// were 11 % of the issue slots of the first version).
+template <int DP, int KD, bool OUT>
+__global__ void __launch_bounds__(TE_THREADS, 1)
+pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ img, float* __restrict__ r_f32,
+                   double* __restrict__ ews, const int KP, const int cpc, const int nchunks, const int nmma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
+    volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
+    if (pass_skip(ctrl, a.force, a.ignore_robust, a.crit_limit)) return;
+    const int K = L.K, D = L.D, tid = threadIdx.x, warp = tid >> 5;
+    const int rowt = tid & 127, gq = tid >> 7;                  // sample row of the tile; column group
+    const float* __restrict__ x = static_cast<const float*>(a.x);
+    constexpr int KCH = KD / 4, KGR = KD / 8;
+    constexpr int A_LBO = 32, A_SBO = KCH * 32;                 // floats: k-chunks adjacent, then the next 8-row group
+    constexpr int CPCMAX = TF_NMAX / DP, NCHMAX = DP / 4;       // CPCMAX * NCHMAX = 64 components at most
+    constexpr int CPB = 64 / DP > 0 ? 64 / DP : 1;              // components per 64-column batch
+    constexpr int NL = NCHMAX * CPB;                            // components this thread can own (<= 16)
+    const int64_t bpart = (int64_t)nchunks * nmma * KD;
+    float* Bs = reinterpret_cast<float*>(smem_raw);            // [2 parts][nchunks][nmma x KD]
+    float* As = Bs + 2 * bpart;                                // [2 stages][2 parts][128 x KD]
+    float* a2s = As + 2 * 2 * TF_TILE * KD;                    // [64]
+    float* xch = a2s + 64;                                     // [3][4][128]: max, sum, dot of every column group
+    float* rst = xch + 3 * 4 * TF_TILE;                        // [128][KP + 4]: r tile staged for coalesced row stores
+    const int RSP = KP + 4;                                    // pitch: 16-byte aligned, rows 4 banks apart
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(rst + TF_TILE * (64 + 4));  // [2] MMAs of TMEM buffer b complete
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 2);
+    __shared__ double red[40];
+
+    for (int64_t e = tid; e < 2 * bpart; e += TE_THREADS) Bs[e] = img[e];
+    for (int e = tid; e < 64; e += TE_THREADS) a2s[e] = img[2 * bpart + e];
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp == 0) tc::tmem_alloc<512>(tslot);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = *tslot;
+    const uint32_t idesc = tc::make_idesc_tf32(128, nmma, 0, 0);
+    const uint32_t b_lbo = 4 * 32, b_sbo = 4 * KCH * 32, a_lbo = 4 * A_LBO, a_sbo = 4 * A_SBO;    // bytes
+
+    const int64_t ntiles = (a.n + TF_TILE - 1) / TF_TILE;
+    const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total_g = my_tiles * nchunks;                 // chunks of this CTA, in issue order
+
+    auto stage_tile = [&](int64_t lt) {                         // local tile lt -> A stage lt & 1; k-chunks kc = gq, gq + 4, ..
+        const int64_t row = (blockIdx.x + lt * gridDim.x) * TF_TILE + rowt;
+        float* Ah = As + (size_t)(lt & 1) * 2 * TF_TILE * KD;
+        float* Al = Ah + TF_TILE * KD;
+        const bool valid = row < a.n;
+#pragma unroll
+        for (int kc0 = 0; kc0 < KCH; kc0 += 4) {
+            const int kc = kc0 + gq;
+            if (kc < KCH) {
+                float h[4], l[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int i = 4 * kc + q;
+                    const float v = (valid && i < D) ? __ldg(x + row * D + i) : ((valid && i == D) ? 1.0f : 0.0f);
+                    h[q] = tc::tf32_hi(v);
+                    l[q] = v - h[q];
+                }
+                const int o = tc::kmajor_off(rowt, 4 * kc, A_LBO, A_SBO);
+                *reinterpret_cast<float4*>(Ah + o) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(Al + o) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+        }
+    };
+    auto issue_chunk = [&](int64_t g) {                          // thread 0 only
+        tc::fence_after_sync();
+        const int64_t lt = g / nchunks;
+        const int ch = (int)(g - lt * nchunks);
+        const uint32_t d_tmem = tbase + (uint32_t)(g & 1) * TF_NMAX;
+        const uint32_t ah = tc::smem_u32(As + (size_t)(lt & 1) * 2 * TF_TILE * KD), al = ah + 4 * TF_TILE * KD;
+        const uint32_t bh = tc::smem_u32(Bs + (size_t)ch * nmma * KD), bl = bh + 4 * (uint32_t)bpart;
+        uint32_t accum = 0;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {                            // hi.hi, hi.lo, lo.hi
+            const uint32_t aa = s == 2 ? al : ah, bb = s == 1 ? bl : bh;
+#pragma unroll
+            for (int ks = 0; ks < KGR; ++ks) {
+                tc::mma_tf32(d_tmem, tc::make_smem_desc(aa + 2 * ks * a_lbo, a_lbo, a_sbo),
+                             tc::make_smem_desc(bb + 2 * ks * b_lbo, b_lbo, b_sbo), idesc, accum);
+                accum = 1;
+            }
+        }
+        tc::mma_commit(&mbar[g & 1]);
+    };
+
+    float ent = 0.f;
+    int64_t next_g = 0;                                          // next chunk to issue (meaningful in thread 0)
+    if (my_tiles > 0) {
+        stage_tile(0);
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            while (next_g < total_g && next_g < 2 && next_g / nchunks <= 0) issue_chunk(next_g++);
+        }
+    }
+    for (int64_t lt = 0; lt < my_tiles; ++lt) {
+        // stage the next tile now: its MMAs can then start as soon as a TMEM buffer frees up
+        if (lt + 1 < my_tiles) stage_tile(lt + 1);
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            const int64_t g0 = lt * nchunks;                     // chunks g0, g0+1 may be in flight already
+            while (next_g < total_g && next_g < g0 + 2 && next_g / nchunks <= lt + 1) issue_chunk(next_g++);
+        }
+        const int64_t row = (blockIdx.x + lt * gridDim.x) * TF_TILE + rowt;
+        const bool valid = row < a.n;
+        // this thread's components: chunk ch, batch gq, u = 0 .. CPB-1  ->  component ch * cpc + gq * CPB + u  (local slot ch * CPB + u)
+        float l2[NL];
+#pragma unroll
+        for (int c = 0; c < NL; ++c) l2[c] = -1.0e30f;
+#pragma unroll
+        for (int ch = 0; ch < NCHMAX; ++ch) {
+            if (ch < nchunks) {                                  // uniform
+                const int64_t g = lt * nchunks + ch;
+                if (warp == 0) mbar_wait(&mbar[g & 1], (uint32_t)((g >> 1) & 1));     // one warp polls, the block barrier releases the rest
+                __syncthreads();
+                tc::fence_after_sync();
+                const uint32_t t0 = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(g & 1) * TF_NMAX + 64 * gq;
+                if (gq * CPB < cpc) {                            // uniform per warp: this 64-column batch holds components
+                    uint32_t v[4][16];
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) tc::tmem_ld16_async(t0 + 16 * h, v[h]);
+                    tc::tmem_wait_ld();
+                    if constexpr (DP >= 16) {
+#pragma unroll
+                        for (int u = 0; u < CPB; ++u) {
+                            float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                            for (int h = 0; h < DP / 16; ++h)
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2) {
+                                    const float y0 = __uint_as_float(v[u * (DP / 16) + h][j]);
+                                    const float y1 = __uint_as_float(v[u * (DP / 16) + h][j + 1]);
+                                    q0 = fmaf(y0, y0, q0);
+                                    q1 = fmaf(y1, y1, q1);
+                                }
+                            l2[ch * CPB + u] = a2s[ch * cpc + gq * CPB + u] - (q0 + q1);
+                        }
+                    } else {
+                        constexpr int PER = 16 / DP;             // components per 16-column load
+#pragma unroll
+                        for (int h = 0; h < 4; ++h)
+#pragma unroll
+                            for (int u = 0; u < PER; ++u) {
+                                float q = 0.f;
+#pragma unroll
+                                for (int j = 0; j < DP; ++j) {
+                                    const float y = __uint_as_float(v[h][u * DP + j]);
+                                    q = fmaf(y, y, q);
+                                }
+                                l2[ch * CPB + h * PER + u] = a2s[ch * cpc + gq * CPB + h * PER + u] - q;
+                            }
+                    }
+                }
+                tc::fence_before_sync();
+                __syncthreads();                                 // every warp has drained TMEM buffer g & 1
+                if (tid == 0) {
+                    while (next_g < total_g && next_g <= g + 2 && next_g / nchunks <= lt + 1) issue_chunk(next_g++);
+                }
+            }
+        }
+        // ---- softmax over k: four threads per row, combined through shared memory ----
+        // component of local slot (ch, u): ch * cpc + gq * CPB + u; slots beyond KP hold -1e30 (a2 of padded components) or
+        // were never written (initial -1e30)
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) mx = fmaxf(mx, l2[c]);
+        xch[gq * TF_TILE + rowt] = mx;
+        __syncthreads();
+        mx = fmaxf(fmaxf(xch[rowt], xch[TF_TILE + rowt]), fmaxf(xch[2 * TF_TILE + rowt], xch[3 * TF_TILE + rowt]));
+        float s = 0.f, dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < NL; ++c) {
+            const float z = l2[c] - mx;
+            const float e = ex2f(z);                             // padded slots: z ~ -1e30 -> 0
+            if (OUT && a.lnrho_out != nullptr && valid) {
+                const int comp = (c / CPB) * cpc + gq * CPB + (c % CPB);
+                if ((c / CPB) < nchunks && gq * CPB < cpc && comp < K) a.lnrho_out[row * K + comp] = (double)l2[c] * 0.693147180559945309417232121458;
+            }
+            l2[c] = e;
+            s += e;
+            dot = fmaf(e, fmaxf(z, -1.0e4f), dot);               // e == 0 there: keep 0 * z finite
+        }
+        xch[(4 + gq) * TF_TILE + rowt] = s;
+        xch[(8 + gq) * TF_TILE + rowt] = dot;
+        __syncthreads();
+        s = (xch[4 * TF_TILE + rowt] + xch[5 * TF_TILE + rowt]) + (xch[6 * TF_TILE + rowt] + xch[7 * TF_TILE + rowt]);
+        dot = (xch[8 * TF_TILE + rowt] + xch[9 * TF_TILE + rowt]) + (xch[10 * TF_TILE + rowt] + xch[11 * TF_TILE + rowt]);
+        const float inv = valid ? 1.0f / s : 0.f;
+        if (valid && gq == 0) ent += 0.693147180559945309f * (dot * inv - lg2f(s));
+        // r: this thread's CPB consecutive components of every chunk (CPB >= 4 -> float4 stores; CPB == 2 at DP = 32)
+#pragma unroll
+        for (int ch = 0; ch < NCHMAX; ++ch) {
+            if (ch < nchunks && gq * CPB < cpc) {
+                const int c0 = ch * cpc + gq * CPB;
+#pragma unroll
+                for (int u = 0; u < CPB; ++u) {
+                    const float rv = l2[ch * CPB + u] * inv;
+                    if (c0 + u < KP) rst[rowt * RSP + c0 + u] = rv;
+                    if (OUT && a.r_out != nullptr && valid && c0 + u < K) a.r_out[row * K + c0 + u] = (double)rv;
+                    l2[ch * CPB + u] = rv;
+                }
+            }
+        }
+        __syncthreads();
+        {   // the tile's r rows are contiguous in r_f32 ([128][KP] floats): 16-byte stores, consecutive threads consecutive addresses
+            const int64_t row0 = (blockIdx.x + lt * gridDim.x) * TF_TILE;
+            const int rows_here = (int)min((int64_t)TF_TILE, a.n - row0);
+            const int q4 = KP / 4;
+            for (int e = tid; e < rows_here * q4; e += TE_THREADS) {
+                const int rr = e / q4, c4 = e - rr * q4;
+                *reinterpret_cast<float4*>(r_f32 + (row0 + rr) * KP + 4 * c4) = *reinterpret_cast<const float4*>(rst + rr * RSP + 4 * c4);
+            }
+        }
+        if (OUT && a.argmax_out != nullptr) {                    // final pass only: arg max over the four column groups
+            int best = 0x7fffffff;
+            float bestv = -1.f;
+#pragma unroll
+            for (int c = 0; c < NL; ++c) {
+                const int comp = (c / CPB) * cpc + gq * CPB + (c % CPB);
+                if ((c / CPB) < nchunks && gq * CPB < cpc && comp < K && (l2[c] > bestv || (l2[c] == bestv && comp < best))) {
+                    bestv = l2[c]; best = comp;
+                }
+            }
+            __syncthreads();
+            xch[gq * TF_TILE + rowt] = bestv;
+            xch[(4 + gq) * TF_TILE + rowt] = __int_as_float(best);
+            __syncthreads();
+            if (gq == 0 && valid) {
+                for (int o = 1; o < 4; ++o) {
+                    const float ov = xch[o * TF_TILE + rowt];
+                    const int ok = __float_as_int(xch[(4 + o) * TF_TILE + rowt]);
+                    if (ov > bestv || (ov == bestv && ok < best)) { bestv = ov; best = ok; }
+                }
+                a.argmax_out[row] = best;
+            }
+        }
+        __syncthreads();                                         // xch is reused by the next tile
+    }
+    const double e_cta = block_sum((double)ent, red);
+    if (tid == 0) ews[blockIdx.x] = e_cta;
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<512>(tbase);
+}
+
+// ---- statistics: raw[k][p] = sum_n r_nk phi_p(x'_n) as  D[feature][component] = Phi^T . R  on the tensor cores -------
+// Contraction over SAMPLES: a 64-sample sub-tile is 8 MMA k-steps.  A = Phi^T (rows = features, MT tiles of 128) and
+// B = R^T (rows = components) are both staged K-major, i.e. TRANSPOSED with respect to the thread that produces them
+// (a thread owns a sample): scalar 4-byte stores into the canonical layout, made conflict-free by a padded k-chunk pitch of
+// 144 bytes (LBO = 144 B: banks 4 (s / 4) + s % 4 are distinct for 32 consecutive samples).  Every value is split into
+// tf32 hi (round to nearest, unbiased) + lo; hi.hi + hi.lo + lo.hi accumulate in fp32 in tensor memory over TF_FLUSH
+// sub-tiles and are then added into float64 registers (thread = feature row), so the fp32 error of a partial sum never
+// exceeds that of 1024 samples.  Moments are about the global centre (format 0), reduced by reduce_partials_kernel.
+constexpr int TM_SUB = 64;                   // samples per sub-tile
+constexpr int TM_LBO = 36;                   // floats: padded pitch of one 16-byte k-chunk column (144 B)
+constexpr int TM_SBO = (TM_SUB / 4) * TM_LBO;   // floats: one 8-row group = 16 k-chunks
+constexpr int TF_FLUSH = 16;                 // sub-tiles between TMEM -> fp64 flushes
+
+// Phi^T rows of ONE sample into the hi / lo staging tiles, features with (p & 3) == Q only; D is a compile-time constant so
+// every product index and every shared-memory offset is static (5 instructions per feature: mul, cvt, sub, 2 stores)
+template <int DT, int Q>
+__device__ __forceinline__ void gen_features(const float (&xv)[DT > 0 ? DT : 1], float* __restrict__ Ah, float* __restrict__ Al,
+                                             const int sbase) {
+    auto put = [&](int p, float v) {
+        const float h = tc::tf32_hi(v);
+        const int o = (p >> 3) * TM_SBO + (p & 7) * 4 + sbase;
+        Ah[o] = h;
+        Al[o] = v - h;
+    };
+    if (Q == 0) put(0, 1.0f);
+#pragma unroll
+    for (int i = 0; i < DT; ++i)
+        if (((1 + i) & 3) == Q) put(1 + i, xv[i]);
+#pragma unroll
+    for (int i = 0; i < DT; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j)
+            if (((1 + DT + i * (i + 1) / 2 + j) & 3) == Q) put(1 + DT + i * (i + 1) / 2 + j, xv[i] * xv[j]);
+}
+
+constexpr int TM_THREADS = 256;              // four threads per sample of a 64-sample sub-tile
+
+// MT 128-feature tiles; NB = padded component count (multiple of 16); DT = compile-time D (0: run-time D through a table)
+template <int MT, int NB, int DT>
+__global__ void __launch_bounds__(TM_THREADS, 1)
+pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r_f32, const int KP,
+                   const double* __restrict__ ews, const int n_ews) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    pdl_trigger();
+    pdl_wait();
+    volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
+    if (pass_skip(ctrl, a.force, a.ignore_robust, a.crit_limit)) return;
+    const int K = L.K, D = DT > 0 ? DT : L.D, P = L.P, tid = threadIdx.x, warp = tid >> 5;
+    const float* __restrict__ x = static_cast<const float*>(a.x);
+    constexpr int RGA = MT * 16;                                // 8-row groups of A the descriptors can reach
+    float* Ah = reinterpret_cast<float*>(smem_raw);            // [RGA][16 chunks][36]
+    float* Al = Ah + RGA * TM_SBO;
+    float* Bh = Al + RGA * TM_SBO;                             // [NB / 8][16][36]
+    float* Bl = Bh + (NB / 8) * TM_SBO;
+    float* xs = Bl + (NB / 8) * TM_SBO;                        // [64][D + 2]: x', 1, 0   (run-time D only)
+    unsigned short* ftab = reinterpret_cast<unsigned short*>(xs + (DT > 0 ? 0 : TM_SUB * (D + 2)));   // [P] (run-time D only)
+    uint64_t* mbar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(ftab + (DT > 0 ? 0 : ((P + 7) & ~7))) + 15) & ~uintptr_t(15));
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 1);
+    constexpr int TCOLS = MT * NB <= 32 ? 32 : (MT * NB <= 64 ? 64 : 128);
+
+    if (DT == 0) {
+        // feature table: phi_p = xs[.][i] * xs[.][j] with the constant columns xs[.][D] = 1, xs[.][D + 1] = 0
+        for (int p = tid; p < P; p += TM_THREADS) {
+            int i, j;
+            if (p == 0) { i = D; j = D; }
+            else if (p <= D) { i = p - 1; j = D; }
+            else {
+                const int q = p - 1 - D;
+                int r = (int)((sqrtf(8.0f * q + 1.0f) - 1.0f) * 0.5f);
+                while (r * (r + 1) / 2 > q) --r;
+                while ((r + 1) * (r + 2) / 2 <= q) ++r;
+                i = r; j = q - r * (r + 1) / 2;
+            }
+            ftab[p] = (unsigned short)((i << 8) | j);
+        }
+    }
+    for (int e = tid; e < 2 * (RGA + NB / 8) * TM_SBO; e += TM_THREADS) Ah[e] = 0.f;      // rows never written must be finite
+    if (tid == 0) mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (warp == 0) tc::tmem_alloc<TCOLS>(tslot);
+    tc::fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tbase = *tslot;
+    const uint32_t idesc = tc::make_idesc_tf32(128, NB, 0, 0);
+
+    // fp64 accumulators: warps 0-3 only (thread = feature row of every M tile)
+    double acc[MT][NB];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int c = 0; c < NB; ++c) acc[mt][c] = 0.0;
+
+    auto flush = [&]() {                                        // TMEM accumulators -> fp64 registers
+        if (warp < 4) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int c0 = 0; c0 < NB; c0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(tbase + ((uint32_t)(32 * warp) << 16) + mt * NB + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[mt][c0 + j] += (double)v[j];
+                }
+        }
+    };
+
+    const int64_t nsub = (a.n + TM_SUB - 1) / TM_SUB;
+    const int s_loc = tid & 63, qd = tid >> 6;                  // four threads per sample: features / components by index mod 4
+    const int sbase = (s_loc >> 2) * TM_LBO + (s_loc & 3);
+    uint32_t phase = 0;
+    int since_flush = 0;
+    bool pending = false;                                       // MMAs in flight reading the staging buffers
+    for (int64_t sb = blockIdx.x; sb < nsub; sb += gridDim.x) {
+        const int64_t row = sb * TM_SUB + s_loc;
+        const bool valid = row < a.n;
+        // this sample's row: global loads issued before the wait on the tensor core
+        float xv[DT > 0 ? DT : 1];
+        if (DT > 0) {
+#pragma unroll
+            for (int i = 0; i < DT; ++i) xv[i] = valid ? __ldg(x + row * DT + i) : 0.f;
+        }
+        float4 rv[(NB / 4 + 3) / 4];
+#pragma unroll
+        for (int u = 0; u < (NB / 4 + 3) / 4; ++u) {
+            const int c4 = qd + 4 * u;
+            rv[u] = (valid && c4 < KP / 4) ? *reinterpret_cast<const float4*>(r_f32 + row * KP + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (pending) {                                          // the tensor core is done with the previous sub-tile's operands
+            if (warp == 0) mbar_wait(mbar, phase);              // one warp polls, the block barrier releases the rest
+            __syncthreads();
+            phase ^= 1u;
+            tc::fence_after_sync();
+            pending = false;
+            if (since_flush == TF_FLUSH) { flush(); since_flush = 0; tc::fence_before_sync(); }
+        }
+        __syncthreads();
+        // R^T: component rows, this thread's sample column
+#pragma unroll
+        for (int u = 0; u < (NB / 4 + 3) / 4; ++u) {
+            const int c4 = qd + 4 * u;
+            if (c4 < KP / 4) {
+                const float rr[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int c = 4 * c4 + w;
+                    const float h = tc::tf32_hi(rr[w]);
+                    const int o = (c >> 3) * TM_SBO + (c & 7) * 4 + sbase;
+                    Bh[o] = h;
+                    Bl[o] = rr[w] - h;
+                }
+            }
+        }
+        // Phi^T: this thread's quarter of the feature rows
+        if (DT > 0) {
+            if (qd == 0) gen_features<DT, 0>(xv, Ah, Al, sbase);
+            else if (qd == 1) gen_features<DT, 1>(xv, Ah, Al, sbase);
+            else if (qd == 2) gen_features<DT, 2>(xv, Ah, Al, sbase);
+            else gen_features<DT, 3>(xv, Ah, Al, sbase);
+        } else {
+            for (int e = tid; e < TM_SUB * (D + 2); e += TM_THREADS) {
+                const int sr = e / (D + 2), c = e - sr * (D + 2);
+                const int64_t rr = sb * TM_SUB + sr;
+                xs[e] = c < D ? (rr < a.n ? __ldg(x + rr * D + c) : 0.f) : (c == D ? 1.f : 0.f);
+            }
+            __syncthreads();
+            const float* xr = xs + s_loc * (D + 2);
+            for (int p = qd; p < P; p += 4) {
+                const unsigned int code = ftab[p];
+                const float v = xr[code >> 8] * xr[code & 0xFF];
+                const float h = tc::tf32_hi(v);
+                const int o = (p >> 3) * TM_SBO + (p & 7) * 4 + sbase;
+                Ah[o] = h;
+                Al[o] = v - h;
+            }
+        }
+        tc::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t ah = tc::smem_u32(Ah), al = tc::smem_u32(Al), bh = tc::smem_u32(Bh), bl = tc::smem_u32(Bl);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                uint32_t accum = since_flush > 0 ? 1u : 0u;
+#pragma unroll
+                for (int sp = 0; sp < 3; ++sp) {
+                    const uint32_t aa = (sp == 2 ? al : ah) + 4 * (uint32_t)(mt * 16 * TM_SBO), bb = sp == 1 ? bl : bh;
+#pragma unroll
+                    for (int ks = 0; ks < TM_SUB / 8; ++ks) {
+                        tc::mma_tf32(tbase + mt * NB, tc::make_smem_desc(aa + 4 * 2 * ks * TM_LBO, 4 * TM_LBO, 4 * TM_SBO),
+                                     tc::make_smem_desc(bb + 4 * 2 * ks * TM_LBO, 4 * TM_LBO, 4 * TM_SBO), idesc, accum);
+                        accum = 1u;
+                    }
+                }
+            }
+            tc::mma_commit(mbar);
+        }
+        pending = true;
+        ++since_flush;
+    }
+    if (pending) {
+        mbar_wait(mbar, phase);
+        tc::fence_after_sync();
+    }
+    if (since_flush > 0) flush();
+    // ---- per-CTA partial (logical layout [K][pitch] float64) ----
+    const int64_t len = L.stats_len;
+    double* part = a.workspace + (int64_t)blockIdx.x * len;
+    for (int64_t o = tid; o < len; o += TM_THREADS) part[o] = 0.0;
+    __syncthreads();
+    if (warp < 4) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int p = mt * 128 + tid;
+            if (p < P) {
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (c < K) part[(int64_t)c * L.pitch + p] = acc[mt][c];
+            }
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        double v = 0.0;
+        for (int i = 0; i < n_ews; ++i) v += ews[i];              // fixed order: deterministic
+        part[(int64_t)K * L.pitch] = v;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<TCOLS>(tbase);
+}
+
+// ---- host side ----
+static int tf32_grid(int64_t units) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return (int)(units < 1 ? 1 : (units < sms ? units : sms));
+}
+
+struct Tf32MPlan { bool ok; int MT, NB; size_t smem; };
+static Tf32MPlan plan_tf32_m(int K, int D) {
+    Tf32MPlan m{};
+    const int P = feat_count(D);
+    m.MT = (P + 127) / 128;
+    m.NB = (K + 15) & ~15;
+    m.smem = sizeof(float) * ((size_t)2 * (m.MT * 16 + m.NB / 8) * TM_SBO + (size_t)TM_SUB * (D + 2)) +
+             sizeof(unsigned short) * ((P + 7) & ~7) + 64;
+    m.ok = m.MT >= 1 && m.MT <= 2 && m.MT * m.NB <= 64 && m.smem <= 220 * 1024;
+    return m;
+}
+
+bool tf32_pass_supported(int K, int D, int dtype) { return tf32_supported(K, D, dtype) && plan_tf32_m(K, D).ok && K >= 2; }
+
+// doubles of workspace: per-CTA partial statistics + entropy partials + the operand image + r (float32 [n][KP])
+int64_t tf32_workspace_doubles(int K, int D, int64_t n) {
+    if (!tf32_pass_supported(K, D, BGMM_F32)) return 0;
+    const Tf32Plan p = plan_tf32(K, D);
+    return (int64_t)160 * ((int64_t)K * feat_pitch(D) + 8) + 160 + (tf32_image_floats(K, D) + 1) / 2 + 8 +
+           (n * p.KP + 1) / 2 + 8;
+}
+
+template <int DP, int KD, bool OUT>
+static cudaError_t launch_e_t(const Tf32Plan& p, const PassArgs& a, const Layout& L, const float* img, float* r_f32, double* ews,
+                              int grid, cudaStream_t stream) {
+    auto kern = pass_tf32_e_kernel<DP, KD, OUT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_e);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(kern, dim3(grid), dim3(TE_THREADS), p.smem_e, stream, a, L, img, r_f32, ews, p.KP, p.cpc, p.nchunks, p.nmma);
+}
+template <int DP, int KD>
+static cudaError_t launch_e(const Tf32Plan& p, const PassArgs& a, const Layout& L, const float* img, float* r_f32, double* ews,
+                            int grid, cudaStream_t stream) {
+    const bool out = a.r_out != nullptr || a.lnrho_out != nullptr || a.argmax_out != nullptr;
+    return out ? launch_e_t<DP, KD, true>(p, a, L, img, r_f32, ews, grid, stream)
+               : launch_e_t<DP, KD, false>(p, a, L, img, r_f32, ews, grid, stream);
+}
+
+template <int MT, int NB, int DT>
+static cudaError_t launch_m_t(const Tf32MPlan& m, const PassArgs& a, const Layout& L, const float* r_f32, int KP, const double* ews,
+                              int n_ews, int grid, cudaStream_t stream) {
+    auto kern = pass_tf32_m_kernel<MT, NB, DT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
+    if (e != cudaSuccess) return e;
+    return launch_pdl(kern, dim3(grid), dim3(TM_THREADS), m.smem, stream, a, L, r_f32, KP, ews, n_ews);
+}
+// compile-time D for the common dimensions (static feature indices), the table-driven instantiation otherwise
+template <int MT, int NB>
+static cudaError_t launch_m(const Tf32MPlan& m, const PassArgs& a, const Layout& L, const float* r_f32, int KP, const double* ews,
+                            int n_ews, int grid, cudaStream_t stream) {
+    if (MT == 2 && L.D == 16) return launch_m_t<MT, NB, (MT == 2 ? 16 : 0)>(m, a, L, r_f32, KP, ews, n_ews, grid, stream);
+    if (MT == 1 && L.D == 8) return launch_m_t<MT, NB, (MT == 1 ? 8 : 0)>(m, a, L, r_f32, KP, ews, n_ews, grid, stream);
+    if (MT == 1 && L.D == 4) return launch_m_t<MT, NB, (MT == 1 ? 4 : 0)>(m, a, L, r_f32, KP, ews, n_ews, grid, stream);
+    return launch_m_t<MT, NB, 0>(m, a, L, r_f32, KP, ews, n_ews, grid, stream);
+}
+
+int launch_pass_tf32(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream) {
+    if (!tf32_pass_supported(K, D, dtype)) {
+        set_error("bgmm_pass(tf32): unsupported shape K=%d D=%d dtype=%d (float32 X, 2 <= K <= 64, D <= 31, K * P accumulators "
+                  "in 128 TMEM columns)", K, D, dtype);
+        return BGMM_ENOSUP;
+    }
+    const Tf32Plan p = plan_tf32(K, D);
+    const Tf32MPlan m = plan_tf32_m(K, D);
+    const Layout L = make_layout(K, D, 1);
+    const int64_t len = L.stats_len;
+    double* ews = a.workspace + (int64_t)160 * len;
+    float* img = reinterpret_cast<float*>(ews + 160);
+    float* r_f32 = reinterpret_cast<float*>(ews + 160 + (tf32_image_floats(K, D) + 1) / 2 + 8);
+    const int grid_e = tf32_grid((a.n + TF_TILE - 1) / TF_TILE), grid_m = tf32_grid((a.n + TM_SUB - 1) / TM_SUB);
+    cudaError_t e = launch_pdl(tf32_prep_kernel, dim3(32), dim3(256), 0, stream, (const double*)a.state, L, img, p.DP, p.KD,
+                               p.KP, p.cpc, p.nchunks, p.nmma, a.force, a.crit_limit);
+    if (e != cudaSuccess) return check_cuda(e, "tf32_prep_kernel launch");
+#define BGMM_TF_E(dp, kd) if (p.DP == dp && p.KD == kd) e = launch_e<dp, kd>(p, a, L, img, r_f32, ews, grid_e, stream);
+    BGMM_TF_E(4, 8) else BGMM_TF_E(8, 8) else BGMM_TF_E(8, 16) else BGMM_TF_E(16, 16) else BGMM_TF_E(16, 24)
+    else BGMM_TF_E(32, 24) else BGMM_TF_E(32, 32)
+    else { set_error("bgmm_pass(tf32): no E instantiation for DP=%d KD=%d", p.DP, p.KD); return BGMM_ENOSUP; }
+#undef BGMM_TF_E
+    if (e != cudaSuccess) return check_cuda(e, "pass_tf32_e_kernel launch");
+#define BGMM_TF_M(mt, nb) if (m.MT == mt && m.NB == nb) e = launch_m<mt, nb>(m, a, L, r_f32, p.KP, ews, grid_e, grid_m, stream);
+    BGMM_TF_M(1, 16) else BGMM_TF_M(1, 32) else BGMM_TF_M(1, 48) else BGMM_TF_M(1, 64) else BGMM_TF_M(2, 16) else BGMM_TF_M(2, 32)
+    else { set_error("bgmm_pass(tf32): no M instantiation for MT=%d NB=%d", m.MT, m.NB); return BGMM_ENOSUP; }
+#undef BGMM_TF_M
+    if (e != cudaSuccess) return check_cuda(e, "pass_tf32_m_kernel launch");
+    launch_reduce_partials(a, L, grid_m, stream);
+    return check_cuda(cudaGetLastError(), "pass_tf32 launch");
+}
+
+}  // namespace bgmm

@@ -269,6 +269,10 @@ __global__ void __launch_bounds__(256) small_kernel(double* __restrict__ st, con
         __syncthreads();
     }
 
+    {   // L^-1 itself: the whitening operand of the fp32-mode tensor-core E-step (zero above the diagonal)
+        double* Lo = Pn + L.p_linv + (int64_t)k * DD;
+        for (int e = tid; e < DD; e += nt) Lo[e] = (e % D <= e / D) ? A[e] : 0.0;
+    }
     // ---- W = L^-T L^-1 ----
     double* Wout = Pn + L.p_w + (int64_t)k * DD;
     for (int e = tid; e < DD; e += nt) {
@@ -599,6 +603,10 @@ __global__ void __launch_bounds__(32) small_warp_kernel(double* __restrict__ st,
         Bm[i * SW_LP + lane] = (i >= lane && lane < D) ? (a0 + a1) * rd[i] : 0.0;
     }
     __syncwarp();
+    {   // L^-1 itself: the whitening operand of the fp32-mode tensor-core E-step
+        double* Lo = Pn + L.p_linv + (int64_t)k * DD;
+        for (int e = lane; e < DD; e += 32) Lo[e] = Bm[(e / D) * SW_LP + (e % D)];
+    }
 
     // ---- W = L^-T L^-1: lane a owns row a; W[a][b] = sum_{l >= max(a,b)} Linv[l][a] Linv[l][b] ----
 #pragma unroll

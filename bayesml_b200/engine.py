@@ -51,14 +51,15 @@ class VBEngine:
             raise ValueError(f"precision must be 'float64' or 'float32', got {precision!r}")
         self.precision = precision
         self.x_code, self.x_torch_dtype = _DTYPES[precision]
-        if precision == "float32" and not self.lib.bgmm_pass_supported(self.K, self.D, _lib.F32, _lib.PASS_F32):
-            # the fp32 streaming kernel covers small D, K only; elsewhere the fp64 tensor-pipe kernels are the fast path
-            # (compute-bound, so the wider X costs nothing): keep X in fp64 on the device
+        if precision == "float32" and not (self.lib.bgmm_pass_supported(self.K, self.D, _lib.F32, _lib.PASS_F32)
+                                           or self.lib.bgmm_pass_supported(self.K, self.D, _lib.F32, _lib.PASS_TF32)):
+            # fp32 mode has two kernels: the streaming FFMA kernel (D <= 3, K <= 8) and the tcgen05 kind::tf32 kernels
+            # (D <= 31, K <= 64); any other shape keeps X in fp64 on the device and runs the fp64 kernels
             self.x_code, self.x_torch_dtype = _DTYPES["float64"]
         self.group = group
         env = os.environ.get("BAYESML_B200_PASS_VARIANT", "").lower()     # debugging / tests: force a kernel variant
         if env:
-            variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "f32": _lib.PASS_F32, "large": _lib.PASS_LARGE, "direct": _lib.PASS_DIRECT}[env]
+            variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "f32": _lib.PASS_F32, "large": _lib.PASS_LARGE, "direct": _lib.PASS_DIRECT, "tf32": _lib.PASS_TF32}[env]
         self.variant = variant
         self.hist_len = 0
         self.state = None
@@ -246,6 +247,10 @@ class VBEngine:
                                             cview.data_ptr(), self._stream()), "bgmm_center")
             self.x = out
             self.r_dev = self.lnrho_dev = self.argmax_dev = None
+            # the tcgen05 fp32-mode kernels keep r (float32, [n][K]) and their operand image in the workspace
+            need = int(self.lib.bgmm_tf32_workspace_doubles(self.K, self.D, n)) if self.x_code == _lib.F32 else 0
+            if need > self.workspace.numel():
+                self.workspace = torch.empty(need, dtype=torch.float64, device=self.device)
         return self
 
     # ------------------------------------------------------------------ prior / parameters
@@ -298,7 +303,7 @@ class VBEngine:
                                       self._stream()), "bgmm_pass")
         self.passes += 1
         resolved = self.lib.bgmm_pass_resolve(self.K, self.D, self.x_code, self.variant, int(r_in is not None))
-        self.kernel_launches += {_lib.PASS_DMMA: 2, _lib.PASS_LARGE: 5}.get(resolved, 1)
+        self.kernel_launches += {_lib.PASS_DMMA: 2, _lib.PASS_LARGE: 5, _lib.PASS_TF32: 4}.get(resolved, 1)
         if r_in is None and resolved != _lib.PASS_DIRECT and self.lib.bgmm_robust_threshold() < float("inf"):
             self.kernel_launches += 1           # the conditioning guard: DIRECT kernel behind the feature-map kernel(s)
 

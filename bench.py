@@ -39,6 +39,7 @@ UNIT = "point*comps/s"
 CONFIGS = {
     "c1": (1000, 2, 3, "float64", 0),
     "c2": (10_000_000, 16, 32, "float64", 1),
+    "c2f32": (10_000_000, 16, 32, "float32", 1),      # the C2 workload in fp32 mode: the tcgen05 kind::tf32 kernels
     "c3": (200_000_000, 2, 8, "float32", 2),
     "c4": (2_000_000, 128, 64, "float64", 3),
     "c5": (4_000_000, 32, 16, "float64", 4),
@@ -516,7 +517,7 @@ def main():
     ap.add_argument("--restarts", type=int, default=0,
                     help="restart mode (C5): this many restarts spread over the GPUs, X replicated (default 64 for --config c5)")
     ap.add_argument("--no-batch", action="store_true", help="restart mode: one sweep per restart (no bgmm_pass_batched)")
-    ap.add_argument("--variant", default="auto", choices=["auto", "simple", "dmma", "f32", "large"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "simple", "dmma", "f32", "large", "tf32", "direct"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -554,7 +555,7 @@ def main():
     x_dev = synth_device(n_local, d, k, 1234 + idx, rank, device, xdtype)
 
     variant = {"auto": _lib.PASS_AUTO, "simple": _lib.PASS_SIMPLE, "dmma": _lib.PASS_DMMA, "f32": _lib.PASS_F32,
-               "large": _lib.PASS_LARGE}[args.variant]
+               "large": _lib.PASS_LARGE, "tf32": _lib.PASS_TF32, "direct": _lib.PASS_DIRECT}[args.variant]
     eng = VBEngine(k, d, device=device, precision=precision, group=group, variant=variant)
     eng.load_data(x_dev)                       # centres into the engine's own buffer
     del x_dev
@@ -654,6 +655,8 @@ def main():
     except Exception:
         pass
     kname = {_lib.PASS_DMMA: "bgmm::pass_dmma_kernel", _lib.PASS_F32: "bgmm::pass_f32_kernel",
+             _lib.PASS_TF32: "bgmm::pass_tf32_e_kernel + bgmm::pass_tf32_m_kernel (tcgen05 kind::tf32)",
+             _lib.PASS_DIRECT: "bgmm::pass_simple_kernel<DIRECT>",
              _lib.PASS_LARGE: "bgmm::e_large_kernel + bgmm::m_large_kernel", _lib.PASS_SIMPLE: "bgmm::pass_simple_kernel"}[
         eng.lib.bgmm_pass_resolve(k, d, eng.x_code, eng.variant, 0)]
     roofline = {
@@ -668,7 +671,21 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
     }
 
-    if precision == "float32":
+    resolved = eng.lib.bgmm_pass_resolve(k, d, eng.x_code, eng.variant, 0)
+    if precision == "float32" and resolved == _lib.PASS_TF32:
+        # fp32 mode on the tensor cores: roofline = the tf32 tensor pipe.  MEASURED_PEAKS.json has dense bf16 only; kind::tf32
+        # runs at half the bf16 rate (B200_PROFILING.md: 1.1 vs 2.25 PFLOP/s nominal), so peak = measured bf16 / 2.
+        # `achieved` counts the ALGORITHMIC flops; the kernels execute 3 split products on padded tiles.
+        tf32_peak = float(peaks.get("bf16_tflops", 1640.0)) / 2.0
+        kd, dp, kp = (d + 1 + 7) // 8 * 8, (4 if d <= 4 else 8 if d <= 8 else 16 if d <= 16 else 32), (k + 3) // 4 * 4
+        p_feat = 1 + d + d * (d + 1) // 2
+        executed = n_local * 2.0 * 3.0 * (kd * kp * dp + ((p_feat + 127) // 128 * 128) * ((k + 15) // 16 * 16))
+        roofline.update({"bound": "tensor", "achieved": ach_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": ach_tflops / tf32_peak,
+                         "peak_source": "kind::tf32 dense = MEASURED_PEAKS.json bf16_tflops / 2 (no measured tf32 entry)",
+                         "executed_flops_per_launch": executed,
+                         "executed_frac_of_pipe": executed / (pass_ms * 1e-3) / 1e12 / tf32_peak})
+    elif precision == "float32":
         # fp32 mode (C3): BASELINE labels it HBM-streaming; the kernel is in fact FP32-issue bound (SURVEY.md §8d caveat),
         # so the HBM fraction is the headline roofline and the FP32 FMA-pipe fraction is reported beside it
         roofline.update({"bound": "hbm", "achieved": roofline["hbm"]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",

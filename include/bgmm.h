@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define BGMM_ABI_VERSION 3
+#define BGMM_ABI_VERSION 4
 
 /* dtype of X */
 #define BGMM_F64 0
@@ -52,6 +52,10 @@ extern "C" {
 #define BGMM_PASS_F32 3    /* fp32-mode streaming kernel: X float32, D <= 3, K <= 8 (fp64 accumulation of partials) */
 #define BGMM_PASS_LARGE 4  /* fp64 large K*P regime (D <= 128, K <= 64): E kernel (r -> HBM) + output-stationary M kernel;
                               needs r_out != NULL */
+#define BGMM_PASS_TF32 6   /* fp32 mode on the 5th-generation tensor cores (tcgen05.mma kind::tf32, 3xTF32 operands, TMEM
+                              accumulators): X float32, 2 <= K <= 64, D <= 31, K * P within 128 TMEM columns.  Whitened E-step
+                              GEMM + feature-map statistics GEMM; `workspace` must hold bgmm_tf32_workspace_doubles(K, D, n).
+                              Hands over to the DIRECT kernel above ctrl.CRIT = 4096. */
 #define BGMM_PASS_DIRECT 5 /* conditioning-safe form, any K, D: ln rho from the explicit differences (x - m_k) and
                               statistics about a per-component shift (state.SHIFT) instead of the global centre.
                               Every other variant is a feature-map kernel whose cancellation error grows like
@@ -108,6 +112,8 @@ enum {
     BGMM_P_LNB,        /* _ln_b_hn_w_nus[K]      */
     BGMM_P_COEF,       /* coef[K][PITCH]  E-step coefficient rows */
     BGMM_P_ACST,       /* a_k[K] = E[ln pi_k] + (E[ln|Lambda_k|] - D ln 2pi - D/kappa_k)/2: ln rho constant of the DIRECT form */
+    BGMM_P_LINV,       /* Linv[K][D][D]: inverse of the lower Cholesky factor of W^-1 (W = Linv^T Linv), i.e. the whitening
+                          y = sqrt(nu) Linv (x - m) with |y|^2 = (x-m)^T (nu W) (x-m); operand of the fp32-mode tensor-core E-step */
     BGMM_N_PARAM_OFFSETS
 };
 
@@ -188,7 +194,11 @@ int bgmm_pass_batched(const void* x, int64_t n, int K, int D, int R, double* con
 /* largest R (>= 1) that bgmm_pass_batched accepts for this shape (1: batching not available) */
 int bgmm_batch_capacity(int K, int D);
 
-/* 1 when `variant` (BGMM_PASS_SIMPLE / _DMMA / _F32 / _LARGE / _DIRECT) can run this shape, else 0 */
+/* doubles of workspace the TF32 variant needs for n local rows (it includes r as float32 [n][K rounded up to 4]); 0 when
+ * the shape is not supported by that variant */
+int64_t bgmm_tf32_workspace_doubles(int K, int D, int64_t n);
+
+/* 1 when `variant` (BGMM_PASS_SIMPLE / _DMMA / _F32 / _LARGE / _DIRECT / _TF32) can run this shape, else 0 */
 int bgmm_pass_supported(int K, int D, int dtype, int variant);
 /* the concrete variant BGMM_PASS_AUTO resolves to (has_r_in: statistics of given responsibilities) */
 int bgmm_pass_resolve(int K, int D, int dtype, int variant, int has_r_in);
