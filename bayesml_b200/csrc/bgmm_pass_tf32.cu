@@ -22,6 +22,7 @@
 #include "bgmm_mma.cuh"
 #include "bgmm_tc.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace bgmm {
 
@@ -110,14 +111,15 @@ __device__ __forceinline__ float lg2f(float x) { float y; asm("lg2.approx.ftz.f3
 // scheduler (the first version, 128 threads) left the epilogue latency bound at ~11 cycles per instruction — 4.1 ms at C2
 // against 0.6 ms of tensor-core time; four warps per scheduler hide it.  The softmax over k then spans four threads:
 // max, sum and the entropy dot product are combined through shared memory ([4][128] floats, two block barriers).
-constexpr int TE_THREADS = 512;
+constexpr int TE_THREADS = 512;               // epilogue / staging threads
+constexpr int TE_BLOCK = TE_THREADS + 32;    // + one warp whose elected lane issues the MMAs (no block barrier in the tile loop)
 
 // OUT = false: the loop instantiation (no float64 ln rho / r / arg-max outputs: their predicated-off stores and conversions
 // were 11 % of the issue slots of the first version).
 template <int DP, int KD, bool OUT>
-__global__ void __launch_bounds__(TE_THREADS, 1)
+__global__ void __launch_bounds__(TE_BLOCK, 1)
 pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ img, float* __restrict__ r_f32,
-                   double* __restrict__ ews, const int KP, const int cpc, const int nchunks, const int nmma) {
+                   double* __restrict__ ews, const int KP, const int cpc, const int nchunks, const int nmma, const int dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
@@ -139,12 +141,18 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
     float* rst = xch + 3 * 4 * TF_TILE;                        // [128][KP + 4]: r tile staged for coalesced row stores
     const int RSP = KP + 4;                                    // pitch: 16-byte aligned, rows 4 banks apart
     uint64_t* mbar = reinterpret_cast<uint64_t*>(rst + TF_TILE * (64 + 4));  // [2] MMAs of TMEM buffer b complete
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 2);
+    uint64_t* tfree = mbar + 2;                                // [2] TMEM buffer b drained by all 16 epilogue warps
+    uint64_t* astaged = mbar + 4;                              // [2] A stage s written (512 arrivals)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 6);
     __shared__ double red[40];
 
-    for (int64_t e = tid; e < 2 * bpart; e += TE_THREADS) Bs[e] = img[e];
-    for (int e = tid; e < 64; e += TE_THREADS) a2s[e] = img[2 * bpart + e];
-    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+    for (int64_t e = tid; e < 2 * bpart; e += TE_BLOCK) Bs[e] = img[e];
+    for (int e = tid; e < 64; e += TE_BLOCK) a2s[e] = img[2 * bpart + e];
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+        mbar_init(&tfree[0], TE_THREADS / 32); mbar_init(&tfree[1], TE_THREADS / 32);
+        mbar_init(&astaged[0], TE_THREADS); mbar_init(&astaged[1], TE_THREADS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (warp == 0) tc::tmem_alloc<512>(tslot);
     tc::fence_proxy_async();
@@ -159,22 +167,35 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
     const int64_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t total_g = my_tiles * nchunks;                 // chunks of this CTA, in issue order
 
-    auto stage_tile = [&](int64_t lt) {                         // local tile lt -> A stage lt & 1; k-chunks kc = gq, gq + 4, ..
+    // this thread's part of a tile's [x, 1] rows: k-chunks kc = gq, gq + 4, ..  The global loads are issued ONE TILE AHEAD of
+    // the staging (fetch_tile(lt + 1) right after stage_tile(lt)): their latency was 17 % of the kernel as a long-scoreboard stall
+    constexpr int NKC = (KCH + 3) / 4;
+    float xpre[NKC][4];
+    auto fetch_tile = [&](int64_t lt) {
         const int64_t row = (blockIdx.x + lt * gridDim.x) * TF_TILE + rowt;
+        const bool valid = lt < my_tiles && row < a.n;
+#pragma unroll
+        for (int u = 0; u < NKC; ++u) {
+            const int kc = 4 * u + gq;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = 4 * kc + q;
+                xpre[u][q] = (valid && i < D) ? __ldg(x + row * D + i) : ((valid && i == D) ? 1.0f : 0.0f);
+            }
+        }
+    };
+    auto stage_tile = [&](int64_t lt) {                         // local tile lt -> A stage lt & 1, from the prefetched registers
         float* Ah = As + (size_t)(lt & 1) * 2 * TF_TILE * KD;
         float* Al = Ah + TF_TILE * KD;
-        const bool valid = row < a.n;
 #pragma unroll
-        for (int kc0 = 0; kc0 < KCH; kc0 += 4) {
-            const int kc = kc0 + gq;
+        for (int u = 0; u < NKC; ++u) {
+            const int kc = 4 * u + gq;
             if (kc < KCH) {
                 float h[4], l[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int i = 4 * kc + q;
-                    const float v = (valid && i < D) ? __ldg(x + row * D + i) : ((valid && i == D) ? 1.0f : 0.0f);
-                    h[q] = tc::tf32_hi(v);
-                    l[q] = v - h[q];
+                    h[q] = tc::tf32_hi(xpre[u][q]);
+                    l[q] = xpre[u][q] - h[q];
                 }
                 const int o = tc::kmajor_off(rowt, 4 * kc, A_LBO, A_SBO);
                 *reinterpret_cast<float4*>(Ah + o) = make_float4(h[0], h[1], h[2], h[3]);
@@ -193,6 +214,7 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
 #pragma unroll
         for (int s = 0; s < 3; ++s) {                            // hi.hi, hi.lo, lo.hi
             const uint32_t aa = s == 2 ? al : ah, bb = s == 1 ? bl : bh;
+            if (dbg == 2 && s > 0) continue;                     // timing experiment: one product instead of three
 #pragma unroll
             for (int ks = 0; ks < KGR; ++ks) {
                 tc::mma_tf32(d_tmem, tc::make_smem_desc(aa + 2 * ks * a_lbo, a_lbo, a_sbo),
@@ -204,149 +226,160 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
     };
 
     float ent = 0.f;
-    int64_t next_g = 0;                                          // next chunk to issue (meaningful in thread 0)
-    if (my_tiles > 0) {
-        stage_tile(0);
-        tc::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            while (next_g < total_g && next_g < 2 && next_g / nchunks <= 0) issue_chunk(next_g++);
+    if (warp == TE_THREADS / 32) {
+        // =========================== MMA WARP ===========================
+        // chunk g (tile g / nchunks) goes to TMEM buffer g & 1 as soon as that buffer has been drained (tfree) and the tile's
+        // A stage is written (astaged); the whole warp walks the loop, one elected lane issues
+        for (int64_t g = 0; g < total_g; ++g) {
+            const int64_t lt = g / nchunks;
+            if (g - lt * nchunks == 0) mbar_wait(&astaged[lt & 1], (uint32_t)((lt >> 1) & 1));
+            if (g >= 2) mbar_wait(&tfree[g & 1], (uint32_t)(((g >> 1) - 1) & 1));
+            if ((tid & 31) == 0) issue_chunk(g);
+            __syncwarp();
         }
-    }
-    for (int64_t lt = 0; lt < my_tiles; ++lt) {
-        // stage the next tile now: its MMAs can then start as soon as a TMEM buffer frees up
-        if (lt + 1 < my_tiles) stage_tile(lt + 1);
-        tc::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            const int64_t g0 = lt * nchunks;                     // chunks g0, g0+1 may be in flight already
-            while (next_g < total_g && next_g < g0 + 2 && next_g / nchunks <= lt + 1) issue_chunk(next_g++);
+    } else {
+        // =========================== EPILOGUE / STAGING WARPS ===========================
+        const int qbar = 1 + (warp & 3);                         // named barrier of the four warps that share this row quarter
+        if (my_tiles > 0) {
+            fetch_tile(0);
+            stage_tile(0);
+            fetch_tile(1);
+            tc::fence_proxy_async();
+            mbar_arrive(&astaged[0]);
         }
-        const int64_t row = (blockIdx.x + lt * gridDim.x) * TF_TILE + rowt;
-        const bool valid = row < a.n;
-        // this thread's components: chunk ch, batch gq, u = 0 .. CPB-1  ->  component ch * cpc + gq * CPB + u  (local slot ch * CPB + u)
-        float l2[NL];
+        for (int64_t lt = 0; lt < my_tiles; ++lt) {
+            // stage the next tile now: its MMAs can start as soon as a TMEM buffer frees up.  (Its stage was last read by tile
+            // lt - 1, whose chunks this thread has already seen complete.)
+            if (lt + 1 < my_tiles) {
+                stage_tile(lt + 1);
+                fetch_tile(lt + 2);
+                tc::fence_proxy_async();
+                mbar_arrive(&astaged[(lt + 1) & 1]);
+            }
+            const int64_t row = (blockIdx.x + lt * gridDim.x) * TF_TILE + rowt;
+            const bool valid = row < a.n;
+            // this thread's components: chunk ch, batch gq, u = 0 .. CPB-1 -> component ch * cpc + gq * CPB + u (local slot ch * CPB + u)
+            float l2[NL];
 #pragma unroll
-        for (int c = 0; c < NL; ++c) l2[c] = -1.0e30f;
+            for (int c = 0; c < NL; ++c) l2[c] = -1.0e30f;
 #pragma unroll
-        for (int ch = 0; ch < NCHMAX; ++ch) {
-            if (ch < nchunks) {                                  // uniform
-                const int64_t g = lt * nchunks + ch;
-                if (warp == 0) mbar_wait(&mbar[g & 1], (uint32_t)((g >> 1) & 1));     // one warp polls, the block barrier releases the rest
-                __syncthreads();
-                tc::fence_after_sync();
-                const uint32_t t0 = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(g & 1) * TF_NMAX + 64 * gq;
-                if (gq * CPB < cpc) {                            // uniform per warp: this 64-column batch holds components
-                    uint32_t v[4][16];
+            for (int ch = 0; ch < NCHMAX; ++ch) {
+                if (ch < nchunks) {                              // uniform
+                    const int64_t g = lt * nchunks + ch;
+                    mbar_wait(&mbar[g & 1], (uint32_t)((g >> 1) & 1));
+                    tc::fence_after_sync();
+                    const uint32_t t0 = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(g & 1) * TF_NMAX + 64 * gq;
+                    if (gq * CPB < cpc && dbg != 1) {            // uniform per warp: this 64-column batch holds components
+                        uint32_t v[4][16];
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) tc::tmem_ld16_async(t0 + 16 * h, v[h]);
-                    tc::tmem_wait_ld();
-                    if constexpr (DP >= 16) {
+                        for (int h = 0; h < 4; ++h) tc::tmem_ld16_async(t0 + 16 * h, v[h]);
+                        tc::tmem_wait_ld();
+                        if constexpr (DP >= 16) {
 #pragma unroll
-                        for (int u = 0; u < CPB; ++u) {
-                            float q0 = 0.f, q1 = 0.f;
+                            for (int u = 0; u < CPB; ++u) {
+                                float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-                            for (int h = 0; h < DP / 16; ++h)
+                                for (int h = 0; h < DP / 16; ++h)
 #pragma unroll
-                                for (int j = 0; j < 16; j += 2) {
-                                    const float y0 = __uint_as_float(v[u * (DP / 16) + h][j]);
-                                    const float y1 = __uint_as_float(v[u * (DP / 16) + h][j + 1]);
-                                    q0 = fmaf(y0, y0, q0);
-                                    q1 = fmaf(y1, y1, q1);
-                                }
-                            l2[ch * CPB + u] = a2s[ch * cpc + gq * CPB + u] - (q0 + q1);
-                        }
-                    } else {
-                        constexpr int PER = 16 / DP;             // components per 16-column load
-#pragma unroll
-                        for (int h = 0; h < 4; ++h)
-#pragma unroll
-                            for (int u = 0; u < PER; ++u) {
-                                float q = 0.f;
-#pragma unroll
-                                for (int j = 0; j < DP; ++j) {
-                                    const float y = __uint_as_float(v[h][u * DP + j]);
-                                    q = fmaf(y, y, q);
-                                }
-                                l2[ch * CPB + h * PER + u] = a2s[ch * cpc + gq * CPB + h * PER + u] - q;
+                                    for (int j = 0; j < 16; j += 2) {
+                                        const float y0 = __uint_as_float(v[u * (DP / 16) + h][j]);
+                                        const float y1 = __uint_as_float(v[u * (DP / 16) + h][j + 1]);
+                                        q0 = fmaf(y0, y0, q0);
+                                        q1 = fmaf(y1, y1, q1);
+                                    }
+                                l2[ch * CPB + u] = a2s[ch * cpc + gq * CPB + u] - (q0 + q1);
                             }
+                        } else {
+                            constexpr int PER = 16 / DP;         // components per 16-column load
+#pragma unroll
+                            for (int h = 0; h < 4; ++h)
+#pragma unroll
+                                for (int u = 0; u < PER; ++u) {
+                                    float q = 0.f;
+#pragma unroll
+                                    for (int j = 0; j < DP; ++j) {
+                                        const float y = __uint_as_float(v[h][u * DP + j]);
+                                        q = fmaf(y, y, q);
+                                    }
+                                    l2[ch * CPB + h * PER + u] = a2s[ch * cpc + gq * CPB + h * PER + u] - q;
+                                }
+                        }
                     }
-                }
-                tc::fence_before_sync();
-                __syncthreads();                                 // every warp has drained TMEM buffer g & 1
-                if (tid == 0) {
-                    while (next_g < total_g && next_g <= g + 2 && next_g / nchunks <= lt + 1) issue_chunk(next_g++);
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if ((tid & 31) == 0) mbar_arrive(&tfree[g & 1]);      // this warp has drained TMEM buffer g & 1
                 }
             }
-        }
-        // ---- softmax over k: four threads per row, combined through shared memory ----
-        // component of local slot (ch, u): ch * cpc + gq * CPB + u; slots beyond KP hold -1e30 (a2 of padded components) or
-        // were never written (initial -1e30)
-        float mx = -3.0e38f;
+            // ---- softmax over k: four threads per row (one per column group), combined through shared memory; only the
+            //      four warps that share the row quarter synchronise (named barrier, 128 threads) ----
+            float mx = -3.0e38f;
 #pragma unroll
-        for (int c = 0; c < NL; ++c) mx = fmaxf(mx, l2[c]);
-        xch[gq * TF_TILE + rowt] = mx;
-        __syncthreads();
-        mx = fmaxf(fmaxf(xch[rowt], xch[TF_TILE + rowt]), fmaxf(xch[2 * TF_TILE + rowt], xch[3 * TF_TILE + rowt]));
-        float s = 0.f, dot = 0.f;
-#pragma unroll
-        for (int c = 0; c < NL; ++c) {
-            const float z = l2[c] - mx;
-            const float e = ex2f(z);                             // padded slots: z ~ -1e30 -> 0
-            if (OUT && a.lnrho_out != nullptr && valid) {
-                const int comp = (c / CPB) * cpc + gq * CPB + (c % CPB);
-                if ((c / CPB) < nchunks && gq * CPB < cpc && comp < K) a.lnrho_out[row * K + comp] = (double)l2[c] * 0.693147180559945309417232121458;
-            }
-            l2[c] = e;
-            s += e;
-            dot = fmaf(e, fmaxf(z, -1.0e4f), dot);               // e == 0 there: keep 0 * z finite
-        }
-        xch[(4 + gq) * TF_TILE + rowt] = s;
-        xch[(8 + gq) * TF_TILE + rowt] = dot;
-        __syncthreads();
-        s = (xch[4 * TF_TILE + rowt] + xch[5 * TF_TILE + rowt]) + (xch[6 * TF_TILE + rowt] + xch[7 * TF_TILE + rowt]);
-        dot = (xch[8 * TF_TILE + rowt] + xch[9 * TF_TILE + rowt]) + (xch[10 * TF_TILE + rowt] + xch[11 * TF_TILE + rowt]);
-        const float inv = valid ? 1.0f / s : 0.f;
-        if (valid && gq == 0) ent += 0.693147180559945309f * (dot * inv - lg2f(s));
-        // r: this thread's CPB consecutive components of every chunk (CPB >= 4 -> float4 stores; CPB == 2 at DP = 32)
-#pragma unroll
-        for (int ch = 0; ch < NCHMAX; ++ch) {
-            if (ch < nchunks && gq * CPB < cpc) {
-                const int c0 = ch * cpc + gq * CPB;
-#pragma unroll
-                for (int u = 0; u < CPB; ++u) {
-                    const float rv = l2[ch * CPB + u] * inv;
-                    if (c0 + u < KP) rst[rowt * RSP + c0 + u] = rv;
-                    if (OUT && a.r_out != nullptr && valid && c0 + u < K) a.r_out[row * K + c0 + u] = (double)rv;
-                    l2[ch * CPB + u] = rv;
-                }
-            }
-        }
-        __syncthreads();
-        {   // the tile's r rows are contiguous in r_f32 ([128][KP] floats): 16-byte stores, consecutive threads consecutive addresses
-            const int64_t row0 = (blockIdx.x + lt * gridDim.x) * TF_TILE;
-            const int rows_here = (int)min((int64_t)TF_TILE, a.n - row0);
-            const int q4 = KP / 4;
-            for (int e = tid; e < rows_here * q4; e += TE_THREADS) {
-                const int rr = e / q4, c4 = e - rr * q4;
-                *reinterpret_cast<float4*>(r_f32 + (row0 + rr) * KP + 4 * c4) = *reinterpret_cast<const float4*>(rst + rr * RSP + 4 * c4);
-            }
-        }
-        if (OUT && a.argmax_out != nullptr) {                    // final pass only: arg max over the four column groups
-            int best = 0x7fffffff;
-            float bestv = -1.f;
+            for (int c = 0; c < NL; ++c) mx = fmaxf(mx, l2[c]);
+            xch[gq * TF_TILE + rowt] = mx;
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+            mx = fmaxf(fmaxf(xch[rowt], xch[TF_TILE + rowt]), fmaxf(xch[2 * TF_TILE + rowt], xch[3 * TF_TILE + rowt]));
+            float s = 0.f, dot = 0.f;
 #pragma unroll
             for (int c = 0; c < NL; ++c) {
-                const int comp = (c / CPB) * cpc + gq * CPB + (c % CPB);
-                if ((c / CPB) < nchunks && gq * CPB < cpc && comp < K && (l2[c] > bestv || (l2[c] == bestv && comp < best))) {
-                    bestv = l2[c]; best = comp;
+                const float z = l2[c] - mx;
+                const float e = ex2f(z);                         // padded slots: z ~ -1e30 -> 0
+                if (OUT && a.lnrho_out != nullptr && valid) {
+                    const int comp = (c / CPB) * cpc + gq * CPB + (c % CPB);
+                    if ((c / CPB) < nchunks && gq * CPB < cpc && comp < K) a.lnrho_out[row * K + comp] = (double)l2[c] * 0.693147180559945309417232121458;
+                }
+                l2[c] = e;
+                s += e;
+                dot = fmaf(e, fmaxf(z, -1.0e4f), dot);           // e == 0 there: keep 0 * z finite
+            }
+            xch[(4 + gq) * TF_TILE + rowt] = s;
+            xch[(8 + gq) * TF_TILE + rowt] = dot;
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+            s = (xch[4 * TF_TILE + rowt] + xch[5 * TF_TILE + rowt]) + (xch[6 * TF_TILE + rowt] + xch[7 * TF_TILE + rowt]);
+            dot = (xch[8 * TF_TILE + rowt] + xch[9 * TF_TILE + rowt]) + (xch[10 * TF_TILE + rowt] + xch[11 * TF_TILE + rowt]);
+            const float inv = valid ? 1.0f / s : 0.f;
+            if (valid && gq == 0) ent += 0.693147180559945309f * (dot * inv - lg2f(s));
+            // r: this thread's CPB consecutive components of every chunk, staged for coalesced row stores
+#pragma unroll
+            for (int ch = 0; ch < NCHMAX; ++ch) {
+                if (ch < nchunks && gq * CPB < cpc) {
+                    const int c0 = ch * cpc + gq * CPB;
+#pragma unroll
+                    for (int u = 0; u < CPB; ++u) {
+                        const float rv = l2[ch * CPB + u] * inv;
+                        if (c0 + u < KP) rst[rowt * RSP + c0 + u] = rv;
+                        if (OUT && a.r_out != nullptr && valid && c0 + u < K) a.r_out[row * K + c0 + u] = (double)rv;
+                        l2[ch * CPB + u] = rv;
+                    }
                 }
             }
-            __syncthreads();
-            xch[gq * TF_TILE + rowt] = bestv;
-            xch[(4 + gq) * TF_TILE + rowt] = __int_as_float(best);
-            __syncthreads();
-            if (gq == 0 && valid) {
+            if (OUT && a.argmax_out != nullptr) {                // final pass only: arg max over the four column groups
+                int best = 0x7fffffff;
+                float bestv = -1.f;
+#pragma unroll
+                for (int c = 0; c < NL; ++c) {
+                    const int comp = (c / CPB) * cpc + gq * CPB + (c % CPB);
+                    if ((c / CPB) < nchunks && gq * CPB < cpc && comp < K && (l2[c] > bestv || (l2[c] == bestv && comp < best))) {
+                        bestv = l2[c]; best = comp;
+                    }
+                }
+                xch[gq * TF_TILE + rowt] = bestv;
+                xch[(4 + gq) * TF_TILE + rowt] = __int_as_float(best);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+            {   // this quarter's 32 rows of r are contiguous in r_f32 (32 x KP floats): 16-byte stores by its 128 threads
+                const int qtr = warp & 3, t128 = (tid & 31) + 32 * gq;
+                const int64_t row0 = (blockIdx.x + lt * gridDim.x) * TF_TILE + 32 * qtr;
+                const int rows_here = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
+                const int q4 = KP / 4;
+                for (int e = t128; e < rows_here * q4; e += 128) {
+                    const int rr = e / q4, c4 = e - rr * q4;
+                    *reinterpret_cast<float4*>(r_f32 + (row0 + rr) * KP + 4 * c4) =
+                        *reinterpret_cast<const float4*>(rst + (32 * qtr + rr) * RSP + 4 * c4);
+                }
+            }
+            if (OUT && a.argmax_out != nullptr && gq == 0 && valid) {
+                int best = __float_as_int(xch[4 * TF_TILE + rowt]);
+                float bestv = xch[rowt];
                 for (int o = 1; o < 4; ++o) {
                     const float ov = xch[o * TF_TILE + rowt];
                     const int ok = __float_as_int(xch[(4 + o) * TF_TILE + rowt]);
@@ -354,8 +387,8 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
                 }
                 a.argmax_out[row] = best;
             }
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");      // xch / rst rows of this quarter are reused by the next tile
         }
-        __syncthreads();                                         // xch is reused by the next tile
     }
     const double e_cta = block_sum((double)ent, red);
     if (tid == 0) ews[blockIdx.x] = e_cta;
@@ -631,7 +664,8 @@ static cudaError_t launch_e_t(const Tf32Plan& p, const PassArgs& a, const Layout
     auto kern = pass_tf32_e_kernel<DP, KD, OUT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_e);
     if (e != cudaSuccess) return e;
-    return launch_pdl(kern, dim3(grid), dim3(TE_THREADS), p.smem_e, stream, a, L, img, r_f32, ews, p.KP, p.cpc, p.nchunks, p.nmma);
+    static const int dbg = [] { const char* e = getenv("BGMM_TF32_DEBUG"); return e ? atoi(e) : 0; }();   // timing experiments only
+    return launch_pdl(kern, dim3(grid), dim3(TE_BLOCK), p.smem_e, stream, a, L, img, r_f32, ews, p.KP, p.cpc, p.nchunks, p.nmma, dbg);
 }
 template <int DP, int KD>
 static cudaError_t launch_e(const Tf32Plan& p, const PassArgs& a, const Layout& L, const float* img, float* r_f32, double* ews,

@@ -31,13 +31,32 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
     }
     if (tid == 0) mbar_init(&mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (warp == 0) tc::tmem_alloc<256>(&tmem_slot);
+    if (warp == 0) tc::tmem_alloc<512>(&tmem_slot);
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tbase = tmem_slot;
-    if (tid == 0) {
+    if (a_mn == 2) {
+        // A in TENSOR MEMORY: every thread stores its own row (lane = m) at columns 256 + k
+        for (int ks = 0; ks < kgr; ++ks) {
+            float v[8];
+            for (int j = 0; j < 8; ++j) v[j] = A[tid * Kd + 8 * ks + j];
+            tc::tmem_st8(tbase + ((uint32_t)(32 * warp) << 16) + 256 + 8 * ks, v);
+        }
+        tc::tmem_wait_st();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+    }
+    if (tid == 0 && a_mn == 2) {
+        const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, b_mn);
+        for (int ks = 0; ks < kgr; ++ks) {
+            const uint32_t b_addr = tc::smem_u32(Bs) + 4 * (b_mn ? ks * b_lbo : 2 * ks * b_lbo);
+            tc::mma_tf32_ts(tbase, tbase + 256 + 8 * ks, tc::make_smem_desc(b_addr, 4 * b_lbo, 4 * b_sbo), idesc, ks > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(&mbar);
+    } else if (tid == 0) {
         const uint32_t idesc = tc::make_idesc_tf32(128, N, a_mn, b_mn);
         for (int ks = 0; ks < kgr; ++ks) {
             // one MMA consumes 8 k: K-major -> two k-chunks (advance 2 * LBO), MN-major -> one k-group (advance LBO)
@@ -59,7 +78,7 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<256>(tbase);
+    if (warp == 0) tc::tmem_dealloc<512>(tbase);
 }
 
 }  // namespace bgmm

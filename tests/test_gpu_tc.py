@@ -13,7 +13,8 @@ def _tf32(a):
 
 # K-major operands only: with either operand MN-major in the no-swizzle layout the B200 returned an all-zero tile for
 # kind::tf32 (measured in round 2, scratch note in DESIGN.md §4.7), so the fp32-mode kernels stage every operand K-major.
-@pytest.mark.parametrize("a_mn,b_mn", [(0, 0)])
+# a_mn = 2: the A operand in tensor memory (tcgen05.st by the thread that owns the row, tcgen05.mma [d], [a], b-desc)
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (2, 0)])
 @pytest.mark.parametrize("n,kd", [(16, 8), (64, 24), (256, 32), (32, 64)])
 def test_tcgen05_tf32_matmul(n, kd, a_mn, b_mn):
     import torch
