@@ -397,29 +397,40 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
     if (warp == 0) tc::tmem_dealloc<512>(tbase);
 }
 
-// ---- statistics: raw[k][p] = sum_n r_nk phi_p(x'_n) as  D[feature][component] = Phi^T . R  on the tensor cores -------
-// Contraction over SAMPLES: a 64-sample sub-tile is 8 MMA k-steps.  A = Phi^T (rows = features, MT tiles of 128) and
-// B = R^T (rows = components) are both staged K-major, i.e. TRANSPOSED with respect to the thread that produces them
-// (a thread owns a sample): scalar 4-byte stores into the canonical layout, made conflict-free by a padded k-chunk pitch of
-// 144 bytes (LBO = 144 B: banks 4 (s / 4) + s % 4 are distinct for 32 consecutive samples).  Every value is split into
-// tf32 hi (round to nearest, unbiased) + lo; hi.hi + hi.lo + lo.hi accumulate in fp32 in tensor memory over TF_FLUSH
-// sub-tiles and are then added into float64 registers (thread = feature row), so the fp32 error of a partial sum never
-// exceeds that of 1024 samples.  Moments are about the global centre (format 0), reduced by reduce_partials_kernel.
+// ---- statistics: raw[k][p] = sum_n r_nk phi_p(x'_n) as  D[component][feature] = R^T . Phi  on the tensor cores -------
+// Contraction over SAMPLES: a 64-sample sub-tile is 8 MMA k-steps.  What bounds this GEMM is the tensor core's operand
+// bandwidth from shared memory (~64 B/clk measured: the first version, both operands in shared memory with the features on
+// M, spent 68 % of its time waiting for 48 small MMAs per sub-tile).  So:
+//   A = R^T lives in TENSOR MEMORY (lane = component, column = sample; written by the warp whose lanes are the components:
+//       lane c reads r[row][c], a coalesced 128-byte row per sample, and stores 8 samples per tcgen05.st) — no shared-memory
+//       traffic for A; rows K .. 127 of the M = 128 tile are zero;
+//   B = Phi (N = features, all of them in one MMA: P <= 256) is staged K-major, i.e. TRANSPOSED with respect to the thread
+//       that produces it (a thread owns a sample): scalar 4-byte stores, conflict-free through a padded k-chunk pitch of
+//       144 bytes; two stages, so the generation of sub-tile t + 1 overlaps the MMAs of sub-tile t.
+// Every value is split into tf32 hi (round to nearest, unbiased) + lo; hi.hi + hi.lo + lo.hi accumulate in fp32 in tensor
+// memory over TF_FLUSH sub-tiles and are then added into a float64 CTA-private array (feature-major, so a warp's lanes =
+// components are contiguous), so the fp32 error of a partial sum never exceeds that of 2048 samples.  Moments are about
+// the global centre (format 0), reduced over the CTAs by reduce_partials_kernel.
 constexpr int TM_SUB = 64;                   // samples per sub-tile
 constexpr int TM_LBO = 36;                   // floats: padded pitch of one 16-byte k-chunk column (144 B)
 constexpr int TM_SBO = (TM_SUB / 4) * TM_LBO;   // floats: one 8-row group = 16 k-chunks
-constexpr int TF_FLUSH = 16;                 // sub-tiles between TMEM -> fp64 flushes
+constexpr int TF_FLUSH = 32;                 // sub-tiles between TMEM -> fp64 flushes (2048 samples)
+constexpr int TM_GEN = 256;                  // generator threads: four per sample
+constexpr int TM_STG = 256;                  // staging threads: warps w with (w & 3) = 0 own TMEM lanes 0-31 (components 0-31),
+                                             // (w & 3) = 1 lanes 32-63; four warps per lane quarter, 16 samples each — ONE warp
+                                             // splitting all 64 samples of its component into hi / lo was the critical path
+constexpr int TM_BLOCK = TM_GEN + TM_STG + 32;   // warps 0-15 with (w & 3) >= 2 generate Phi; warp 16 only issues the MMAs
 
-// Phi^T rows of ONE sample into the hi / lo staging tiles, features with (p & 3) == Q only; D is a compile-time constant so
+// Phi rows of ONE sample into the hi / lo staging tiles, features with (p & 3) == Q only; D is a compile-time constant so
 // every product index and every shared-memory offset is static (5 instructions per feature: mul, cvt, sub, 2 stores)
 template <int DT, int Q>
-__device__ __forceinline__ void gen_features(const float (&xv)[DT > 0 ? DT : 1], float* __restrict__ Ah, float* __restrict__ Al,
+__device__ __forceinline__ void gen_features(const float (&xv)[DT > 0 ? DT : 1], float* __restrict__ Bh, float* __restrict__ Bl,
                                              const int sbase) {
     auto put = [&](int p, float v) {
         const float h = tc::tf32_hi(v);
         const int o = (p >> 3) * TM_SBO + (p & 7) * 4 + sbase;
-        Ah[o] = h;
-        Al[o] = v - h;
+        Bh[o] = h;
+        Bl[o] = v - h;
     };
     if (Q == 0) put(0, 1.0f);
 #pragma unroll
@@ -432,34 +443,33 @@ __device__ __forceinline__ void gen_features(const float (&xv)[DT > 0 ? DT : 1],
             if (((1 + DT + i * (i + 1) / 2 + j) & 3) == Q) put(1 + DT + i * (i + 1) / 2 + j, xv[i] * xv[j]);
 }
 
-constexpr int TM_THREADS = 256;              // four threads per sample of a 64-sample sub-tile
-
-// MT 128-feature tiles; NB = padded component count (multiple of 16); DT = compile-time D (0: run-time D through a table)
-template <int MT, int NB, int DT>
-__global__ void __launch_bounds__(TM_THREADS, 1)
-pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r_f32, const int KP,
-                   const double* __restrict__ ews, const int n_ews) {
+// DT = compile-time D (0: run-time D through a table); NF = features rounded up to 16 (the MMA N), passed at run time
+template <int DT>
+__global__ void __launch_bounds__(TM_BLOCK, 1)
+pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r_f32, const int KP, const int NF, const int nst,
+                   double* __restrict__ acct, const double* __restrict__ ews, const int n_ews) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     pdl_trigger();
     pdl_wait();
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
     if (pass_skip(ctrl, a.force, a.ignore_robust, a.crit_limit)) return;
-    const int K = L.K, D = DT > 0 ? DT : L.D, P = L.P, tid = threadIdx.x, warp = tid >> 5;
+    const int K = L.K, D = DT > 0 ? DT : L.D, P = L.P, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* __restrict__ x = static_cast<const float*>(a.x);
-    constexpr int RGA = MT * 16;                                // 8-row groups of A the descriptors can reach
-    float* Ah = reinterpret_cast<float*>(smem_raw);            // [RGA][16 chunks][36]
-    float* Al = Ah + RGA * TM_SBO;
-    float* Bh = Al + RGA * TM_SBO;                             // [NB / 8][16][36]
-    float* Bl = Bh + (NB / 8) * TM_SBO;
-    float* xs = Bl + (NB / 8) * TM_SBO;                        // [64][D + 2]: x', 1, 0   (run-time D only)
+    const int bpart = (NF / 8) * TM_SBO;                       // floats of one part (hi or lo) of one stage
+    float* Bs = reinterpret_cast<float*>(smem_raw);            // [nst stages][2 parts][NF / 8][16 chunks][36]
+    float* xs = Bs + 2 * nst * bpart;                                // [64][D + 2]: x', 1, 0   (run-time D only)
     unsigned short* ftab = reinterpret_cast<unsigned short*>(xs + (DT > 0 ? 0 : TM_SUB * (D + 2)));   // [P] (run-time D only)
     uint64_t* mbar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(ftab + (DT > 0 ? 0 : ((P + 7) & ~7))) + 15) & ~uintptr_t(15));
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 1);
-    constexpr int TCOLS = MT * NB <= 32 ? 32 : (MT * NB <= 64 ? 64 : 128);
+    uint64_t* mdone = mbar;                                    // [2] MMAs of sub-tile parity b complete (B stage + A buffer free)
+    uint64_t* bfull = mbar + 2;                                // [2] B stage b written (256 arrivals)
+    uint64_t* afull = mbar + 4;                                // [2] A buffer b written (one arrival per staging warp)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 6);
+    const int KW = (KP + 31) / 32;                             // component warps with real rows (1 or 2)
+    double* acc = acct + (int64_t)blockIdx.x * 256 * 64;      // CTA-private [NF][64] float64, feature-major
 
     if (DT == 0) {
         // feature table: phi_p = xs[.][i] * xs[.][j] with the constant columns xs[.][D] = 1, xs[.][D + 1] = 0
-        for (int p = tid; p < P; p += TM_THREADS) {
+        for (int p = tid; p < P; p += TM_BLOCK) {
             int i, j;
             if (p == 0) { i = D; j = D; }
             else if (p <= D) { i = p - 1; j = D; }
@@ -473,151 +483,184 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
             ftab[p] = (unsigned short)((i << 8) | j);
         }
     }
-    for (int e = tid; e < 2 * (RGA + NB / 8) * TM_SBO; e += TM_THREADS) Ah[e] = 0.f;      // rows never written must be finite
-    if (tid == 0) mbar_init(mbar, 1);
+    for (int e = tid; e < 2 * nst * bpart; e += TM_BLOCK) Bs[e] = 0.f;    // feature rows P .. NF-1 are never written
+    for (int e = tid; e < NF * 64; e += TM_BLOCK) acc[e] = 0.0;
+    if (tid == 0) {
+        mbar_init(&mdone[0], 1); mbar_init(&mdone[1], 1);
+        mbar_init(&bfull[0], TM_GEN); mbar_init(&bfull[1], TM_GEN);
+        mbar_init(&afull[0], TM_STG / 32); mbar_init(&afull[1], TM_STG / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (warp == 0) tc::tmem_alloc<TCOLS>(tslot);
+    if (warp == 0) tc::tmem_alloc<512>(tslot);
     tc::fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tbase = *tslot;
-    const uint32_t idesc = tc::make_idesc_tf32(128, NB, 0, 0);
-
-    // fp64 accumulators: warps 0-3 only (thread = feature row of every M tile)
-    double acc[MT][NB];
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-        for (int c = 0; c < NB; ++c) acc[mt][c] = 0.0;
-
-    auto flush = [&]() {                                        // TMEM accumulators -> fp64 registers
-        if (warp < 4) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-                for (int c0 = 0; c0 < NB; c0 += 16) {
-                    float v[16];
-                    tc::tmem_ld16(tbase + ((uint32_t)(32 * warp) << 16) + mt * NB + c0, v);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[mt][c0 + j] += (double)v[j];
-                }
-        }
-    };
-
+    // TMEM columns: A stage s hi at 128 s, lo at 128 s + 64; D at 256 .. 256 + NF
+    if (warp < 4) {                                             // rows K .. 127 of A stay zero: clear all 128 lanes once
+        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < 256; c += 8) tc::tmem_st8(tbase + ((uint32_t)(32 * warp) << 16) + c, z);
+        tc::tmem_wait_st();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t idesc = tc::make_idesc_tf32(128, NF, 0, 0);
     const int64_t nsub = (a.n + TM_SUB - 1) / TM_SUB;
-    const int s_loc = tid & 63, qd = tid >> 6;                  // four threads per sample: features / components by index mod 4
-    const int sbase = (s_loc >> 2) * TM_LBO + (s_loc & 3);
-    uint32_t phase = 0;
-    int since_flush = 0;
-    bool pending = false;                                       // MMAs in flight reading the staging buffers
-    for (int64_t sb = blockIdx.x; sb < nsub; sb += gridDim.x) {
-        const int64_t row = sb * TM_SUB + s_loc;
-        const bool valid = row < a.n;
-        // this sample's row: global loads issued before the wait on the tensor core
-        float xv[DT > 0 ? DT : 1];
-        if (DT > 0) {
-#pragma unroll
-            for (int i = 0; i < DT; ++i) xv[i] = valid ? __ldg(x + row * DT + i) : 0.f;
-        }
-        float4 rv[(NB / 4 + 3) / 4];
-#pragma unroll
-        for (int u = 0; u < (NB / 4 + 3) / 4; ++u) {
-            const int c4 = qd + 4 * u;
-            rv[u] = (valid && c4 < KP / 4) ? *reinterpret_cast<const float4*>(r_f32 + row * KP + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (pending) {                                          // the tensor core is done with the previous sub-tile's operands
-            if (warp == 0) mbar_wait(mbar, phase);              // one warp polls, the block barrier releases the rest
-            __syncthreads();
-            phase ^= 1u;
+    const int64_t my_sub = blockIdx.x < nsub ? (nsub - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == TM_BLOCK / 32 - 1) {
+        // =========================== ISSUER: one thread feeds the tensor core and nothing else ===========================
+        int since_flush = 0;
+        for (int64_t t = 0; t < my_sub; ++t) {
+            if (since_flush == TF_FLUSH) since_flush = 0;       // the staging warps flushed before they signalled afull
+            mbar_wait(&afull[t & 1], (uint32_t)((t >> 1) & 1));
+            mbar_wait(&bfull[t & 1], (uint32_t)((t >> 1) & 1));
             tc::fence_after_sync();
-            pending = false;
-            if (since_flush == TF_FLUSH) { flush(); since_flush = 0; tc::fence_before_sync(); }
-        }
-        __syncthreads();
-        // R^T: component rows, this thread's sample column
-#pragma unroll
-        for (int u = 0; u < (NB / 4 + 3) / 4; ++u) {
-            const int c4 = qd + 4 * u;
-            if (c4 < KP / 4) {
-                const float rr[4] = {rv[u].x, rv[u].y, rv[u].z, rv[u].w};
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const int c = 4 * c4 + w;
-                    const float h = tc::tf32_hi(rr[w]);
-                    const int o = (c >> 3) * TM_SBO + (c & 7) * 4 + sbase;
-                    Bh[o] = h;
-                    Bl[o] = rr[w] - h;
-                }
-            }
-        }
-        // Phi^T: this thread's quarter of the feature rows
-        if (DT > 0) {
-            if (qd == 0) gen_features<DT, 0>(xv, Ah, Al, sbase);
-            else if (qd == 1) gen_features<DT, 1>(xv, Ah, Al, sbase);
-            else if (qd == 2) gen_features<DT, 2>(xv, Ah, Al, sbase);
-            else gen_features<DT, 3>(xv, Ah, Al, sbase);
-        } else {
-            for (int e = tid; e < TM_SUB * (D + 2); e += TM_THREADS) {
-                const int sr = e / (D + 2), c = e - sr * (D + 2);
-                const int64_t rr = sb * TM_SUB + sr;
-                xs[e] = c < D ? (rr < a.n ? __ldg(x + rr * D + c) : 0.f) : (c == D ? 1.f : 0.f);
-            }
-            __syncthreads();
-            const float* xr = xs + s_loc * (D + 2);
-            for (int p = qd; p < P; p += 4) {
-                const unsigned int code = ftab[p];
-                const float v = xr[code >> 8] * xr[code & 0xFF];
-                const float h = tc::tf32_hi(v);
-                const int o = (p >> 3) * TM_SBO + (p & 7) * 4 + sbase;
-                Ah[o] = h;
-                Al[o] = v - h;
-            }
-        }
-        tc::fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint32_t ah = tc::smem_u32(Ah), al = tc::smem_u32(Al), bh = tc::smem_u32(Bh), bl = tc::smem_u32(Bl);
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
+            if (lane == 0) {
+                const uint32_t bh = tc::smem_u32(Bs + (size_t)(nst == 2 ? (t & 1) : 0) * 2 * bpart), bl = bh + 4 * (uint32_t)bpart;
+                const uint32_t ah = tbase + 128 * (uint32_t)(t & 1), al = ah + 64;
                 uint32_t accum = since_flush > 0 ? 1u : 0u;
 #pragma unroll
-                for (int sp = 0; sp < 3; ++sp) {
-                    const uint32_t aa = (sp == 2 ? al : ah) + 4 * (uint32_t)(mt * 16 * TM_SBO), bb = sp == 1 ? bl : bh;
+                for (int sp = 0; sp < 3; ++sp) {                // hi.hi, hi.lo, lo.hi
+                    const uint32_t aa = sp == 2 ? al : ah, bb = sp == 1 ? bl : bh;
 #pragma unroll
                     for (int ks = 0; ks < TM_SUB / 8; ++ks) {
-                        tc::mma_tf32(tbase + mt * NB, tc::make_smem_desc(aa + 4 * 2 * ks * TM_LBO, 4 * TM_LBO, 4 * TM_SBO),
-                                     tc::make_smem_desc(bb + 4 * 2 * ks * TM_LBO, 4 * TM_LBO, 4 * TM_SBO), idesc, accum);
+                        tc::mma_tf32_ts(tbase + 256, aa + 8 * ks,
+                                        tc::make_smem_desc(bb + 4 * 2 * ks * TM_LBO, 4 * TM_LBO, 4 * TM_SBO), idesc, accum);
                         accum = 1u;
                     }
                 }
+                tc::mma_commit(&mdone[t & 1]);
             }
-            tc::mma_commit(mbar);
+            __syncwarp();
+            ++since_flush;
         }
-        pending = true;
-        ++since_flush;
+    } else if ((warp & 3) >= 2) {
+        // =========================== GENERATOR WARPS: Phi of sub-tile t into B stage t & 1 ===========================
+        const int gtid = (((warp >> 2) << 1) + (warp & 3) - 2) * 32 + lane;     // 0 .. 255 over the generator warps
+        const int s_loc = gtid & 63, qd = gtid >> 6;            // four threads per sample: features by index mod 4
+        const int sbase = (s_loc >> 2) * TM_LBO + (s_loc & 3);
+        for (int64_t t = 0; t < my_sub; ++t) {
+            const int64_t sb = blockIdx.x + t * gridDim.x;
+            const int64_t row = sb * TM_SUB + s_loc;
+            const bool valid = row < a.n;
+            float xv[DT > 0 ? DT : 1];
+            if (DT > 0) {
+#pragma unroll
+                for (int i = 0; i < DT; ++i) xv[i] = valid ? __ldg(x + row * DT + i) : 0.f;
+            }
+            // the MMAs that read this stage are done: sub-tile t - 2 with two stages, t - 1 with one (large feature counts)
+            if (nst == 2) { if (t >= 2) mbar_wait(&mdone[t & 1], (uint32_t)(((t >> 1) - 1) & 1)); }
+            else if (t >= 1) mbar_wait(&mdone[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
+            float* Bh = Bs + (size_t)(nst == 2 ? (t & 1) : 0) * 2 * bpart;
+            float* Bl = Bh + bpart;
+            if (DT > 0) {
+                if (qd == 0) gen_features<DT, 0>(xv, Bh, Bl, sbase);
+                else if (qd == 1) gen_features<DT, 1>(xv, Bh, Bl, sbase);
+                else if (qd == 2) gen_features<DT, 2>(xv, Bh, Bl, sbase);
+                else gen_features<DT, 3>(xv, Bh, Bl, sbase);
+            } else {
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // xs free (previous sub-tile's products formed)
+                for (int e = gtid; e < TM_SUB * (D + 2); e += TM_GEN) {
+                    const int sr = e / (D + 2), c = e - sr * (D + 2);
+                    const int64_t rr = sb * TM_SUB + sr;
+                    xs[e] = c < D ? (rr < a.n ? __ldg(x + rr * D + c) : 0.f) : (c == D ? 1.f : 0.f);
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float* xr = xs + s_loc * (D + 2);
+                for (int p = qd; p < P; p += 4) {
+                    const unsigned int code = ftab[p];
+                    const float v = xr[code >> 8] * xr[code & 0xFF];
+                    const float h = tc::tf32_hi(v);
+                    const int o = (p >> 3) * TM_SBO + (p & 7) * 4 + sbase;
+                    Bh[o] = h;
+                    Bl[o] = v - h;
+                }
+            }
+            tc::fence_proxy_async();
+            mbar_arrive(&bfull[t & 1]);
+        }
+    } else {
+        // =========================== STAGING WARPS: R^T into TMEM, MMA issue, flushes ===========================
+        const int cw = warp & 3;                                // 0: components 0-31 (TMEM lanes 0-31), 1: components 32-63
+        const int sq = warp >> 2;                               // which 16 of the 64 samples (and which features of a flush)
+        const int c = 32 * cw + lane;
+        const uint32_t lane_base = tbase + ((uint32_t)(32 * cw) << 16);
+        int since_flush = 0;
+        auto flush = [&]() {                                    // D rows (lane = component) -> float64, feature-major
+            if (cw < KW) {
+                for (int p0 = 16 * sq; p0 < NF; p0 += 64) {
+                    float v[16];
+                    double o[16];
+                    double* ap = acc + (int64_t)p0 * 64 + c;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = __ldcg(ap + j * 64);     // 16 independent loads in flight
+                    tc::tmem_ld16(lane_base + 256 + p0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) __stcg(ap + j * 64, o[j] + (double)v[j]);
+                }
+            }
+        };
+        // this component's responsibilities of 16 samples (a warp reads one 128-byte row of r per sample), one sub-tile ahead
+        float rv[2][8];
+        auto load_r = [&](int64_t t) {
+            const int64_t row0 = (blockIdx.x + t * gridDim.x) * TM_SUB + 16 * sq;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t row = row0 + 8 * j + u;
+                    rv[j][u] = (t < my_sub && row < a.n && c < KP) ? __ldg(r_f32 + row * KP + c) : 0.f;
+                }
+        };
+        if (cw < KW) load_r(0);
+        for (int64_t t = 0; t < my_sub; ++t) {
+            if (t >= 2) mbar_wait(&mdone[t & 1], (uint32_t)(((t >> 1) - 1) & 1));     // A buffer t & 1 free
+            tc::fence_after_sync();
+            if (since_flush == TF_FLUSH) {
+                // every MMA issued so far has completed?  sub-tile t - 1 must be waited for explicitly
+                mbar_wait(&mdone[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
+                tc::fence_after_sync();
+                flush();
+                since_flush = 0;
+                tc::fence_before_sync();
+            }
+            if (cw < KW) {
+                const uint32_t abase = lane_base + 128 * (uint32_t)(t & 1);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    float h[8], l[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { h[u] = tc::tf32_hi(rv[j][u]); l[u] = rv[j][u] - h[u]; }
+                    tc::tmem_st8(abase + 16 * sq + 8 * j, h);
+                    tc::tmem_st8(abase + 64 + 16 * sq + 8 * j, l);
+                }
+                load_r(t + 1);
+                tc::tmem_wait_st();
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&afull[t & 1]);          // this warp's part of A is in place (and its flush is done)
+            ++since_flush;
+        }
+        if (my_sub > 0) {
+            mbar_wait(&mdone[(my_sub - 1) & 1], (uint32_t)(((my_sub - 1) >> 1) & 1));
+            tc::fence_after_sync();
+            if (since_flush > 0) flush();
+        }
     }
-    if (pending) {
-        mbar_wait(mbar, phase);
-        tc::fence_after_sync();
-    }
-    if (since_flush > 0) flush();
+    __threadfence_block();
+    __syncthreads();
     // ---- per-CTA partial (logical layout [K][pitch] float64) ----
     const int64_t len = L.stats_len;
     double* part = a.workspace + (int64_t)blockIdx.x * len;
-    for (int64_t o = tid; o < len; o += TM_THREADS) part[o] = 0.0;
+    for (int64_t o = tid; o < len; o += TM_BLOCK) part[o] = 0.0;
     __syncthreads();
-    if (warp < 4) {
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-            const int p = mt * 128 + tid;
-            if (p < P) {
-#pragma unroll
-                for (int c = 0; c < NB; ++c)
-                    if (c < K) part[(int64_t)c * L.pitch + p] = acc[mt][c];
-            }
-        }
+    for (int e = tid; e < K * P; e += TM_BLOCK) {
+        const int k = e / P, p = e - k * P;
+        part[(int64_t)k * L.pitch + p] = acc[(int64_t)p * 64 + k];
     }
     if (blockIdx.x == 0 && tid == 0) {
         double v = 0.0;
@@ -626,7 +669,7 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<TCOLS>(tbase);
+    if (warp == 0) tc::tmem_dealloc<512>(tbase);
 }
 
 // ---- host side ----
@@ -636,26 +679,32 @@ static int tf32_grid(int64_t units) {
     return (int)(units < 1 ? 1 : (units < sms ? units : sms));
 }
 
-struct Tf32MPlan { bool ok; int MT, NB; size_t smem; };
+struct Tf32MPlan { bool ok; int NF, nst; size_t smem; };
 static Tf32MPlan plan_tf32_m(int K, int D) {
     Tf32MPlan m{};
     const int P = feat_count(D);
-    m.MT = (P + 127) / 128;
-    m.NB = (K + 15) & ~15;
-    m.smem = sizeof(float) * ((size_t)2 * (m.MT * 16 + m.NB / 8) * TM_SBO + (size_t)TM_SUB * (D + 2)) +
-             sizeof(unsigned short) * ((P + 7) & ~7) + 64;
-    m.ok = m.MT >= 1 && m.MT <= 2 && m.MT * m.NB <= 64 && m.smem <= 220 * 1024;
+    m.NF = (P + 15) & ~15;
+    auto bytes = [&](int nst) {
+        return sizeof(float) * ((size_t)2 * nst * (m.NF / 8) * TM_SBO + (size_t)TM_SUB * (D + 2)) +
+               sizeof(unsigned short) * ((P + 7) & ~7) + 96;
+    };
+    m.nst = bytes(2) <= 220 * 1024 ? 2 : 1;                    // two Phi stages when they fit (P <= ~190), else one
+    m.smem = bytes(m.nst);
+    m.ok = m.NF <= 256 && K <= 64 && m.smem <= 220 * 1024;
     return m;
 }
 
 bool tf32_pass_supported(int K, int D, int dtype) { return tf32_supported(K, D, dtype) && plan_tf32_m(K, D).ok && K >= 2; }
 
-// doubles of workspace: per-CTA partial statistics + entropy partials + the operand image + r (float32 [n][KP])
+// doubles of workspace: per-CTA partial statistics + entropy partials + the operand image + the CTA-private float64
+// accumulators of the statistics kernel + r (float32 [n][KP])
+static int64_t tf32_fixed_doubles(int K, int D) {
+    return (int64_t)160 * ((int64_t)K * feat_pitch(D) + 8) + 160 + (tf32_image_floats(K, D) + 1) / 2 + 8 + (int64_t)160 * 256 * 64;
+}
 int64_t tf32_workspace_doubles(int K, int D, int64_t n) {
     if (!tf32_pass_supported(K, D, BGMM_F32)) return 0;
     const Tf32Plan p = plan_tf32(K, D);
-    return (int64_t)160 * ((int64_t)K * feat_pitch(D) + 8) + 160 + (tf32_image_floats(K, D) + 1) / 2 + 8 +
-           (n * p.KP + 1) / 2 + 8;
+    return tf32_fixed_doubles(K, D) + (n * p.KP + 1) / 2 + 8;
 }
 
 template <int DP, int KD, bool OUT>
@@ -675,22 +724,13 @@ static cudaError_t launch_e(const Tf32Plan& p, const PassArgs& a, const Layout& 
                : launch_e_t<DP, KD, false>(p, a, L, img, r_f32, ews, grid, stream);
 }
 
-template <int MT, int NB, int DT>
-static cudaError_t launch_m_t(const Tf32MPlan& m, const PassArgs& a, const Layout& L, const float* r_f32, int KP, const double* ews,
-                              int n_ews, int grid, cudaStream_t stream) {
-    auto kern = pass_tf32_m_kernel<MT, NB, DT>;
+template <int DT>
+static cudaError_t launch_m_t(const Tf32MPlan& m, const PassArgs& a, const Layout& L, const float* r_f32, int KP, double* acct,
+                              const double* ews, int n_ews, int grid, cudaStream_t stream) {
+    auto kern = pass_tf32_m_kernel<DT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m.smem);
     if (e != cudaSuccess) return e;
-    return launch_pdl(kern, dim3(grid), dim3(TM_THREADS), m.smem, stream, a, L, r_f32, KP, ews, n_ews);
-}
-// compile-time D for the common dimensions (static feature indices), the table-driven instantiation otherwise
-template <int MT, int NB>
-static cudaError_t launch_m(const Tf32MPlan& m, const PassArgs& a, const Layout& L, const float* r_f32, int KP, const double* ews,
-                            int n_ews, int grid, cudaStream_t stream) {
-    if (MT == 2 && L.D == 16) return launch_m_t<MT, NB, (MT == 2 ? 16 : 0)>(m, a, L, r_f32, KP, ews, n_ews, grid, stream);
-    if (MT == 1 && L.D == 8) return launch_m_t<MT, NB, (MT == 1 ? 8 : 0)>(m, a, L, r_f32, KP, ews, n_ews, grid, stream);
-    if (MT == 1 && L.D == 4) return launch_m_t<MT, NB, (MT == 1 ? 4 : 0)>(m, a, L, r_f32, KP, ews, n_ews, grid, stream);
-    return launch_m_t<MT, NB, 0>(m, a, L, r_f32, KP, ews, n_ews, grid, stream);
+    return launch_pdl(kern, dim3(grid), dim3(TM_BLOCK), m.smem, stream, a, L, r_f32, KP, m.NF, m.nst, acct, ews, n_ews);
 }
 
 int launch_pass_tf32(const PassArgs& a, int K, int D, int dtype, cudaStream_t stream) {
@@ -705,7 +745,8 @@ int launch_pass_tf32(const PassArgs& a, int K, int D, int dtype, cudaStream_t st
     const int64_t len = L.stats_len;
     double* ews = a.workspace + (int64_t)160 * len;
     float* img = reinterpret_cast<float*>(ews + 160);
-    float* r_f32 = reinterpret_cast<float*>(ews + 160 + (tf32_image_floats(K, D) + 1) / 2 + 8);
+    double* acct = ews + 160 + (tf32_image_floats(K, D) + 1) / 2 + 8;
+    float* r_f32 = reinterpret_cast<float*>(a.workspace + tf32_fixed_doubles(K, D));
     const int grid_e = tf32_grid((a.n + TF_TILE - 1) / TF_TILE), grid_m = tf32_grid((a.n + TM_SUB - 1) / TM_SUB);
     cudaError_t e = launch_pdl(tf32_prep_kernel, dim3(32), dim3(256), 0, stream, (const double*)a.state, L, img, p.DP, p.KD,
                                p.KP, p.cpc, p.nchunks, p.nmma, a.force, a.crit_limit);
@@ -716,10 +757,11 @@ int launch_pass_tf32(const PassArgs& a, int K, int D, int dtype, cudaStream_t st
     else { set_error("bgmm_pass(tf32): no E instantiation for DP=%d KD=%d", p.DP, p.KD); return BGMM_ENOSUP; }
 #undef BGMM_TF_E
     if (e != cudaSuccess) return check_cuda(e, "pass_tf32_e_kernel launch");
-#define BGMM_TF_M(mt, nb) if (m.MT == mt && m.NB == nb) e = launch_m<mt, nb>(m, a, L, r_f32, p.KP, ews, grid_e, grid_m, stream);
-    BGMM_TF_M(1, 16) else BGMM_TF_M(1, 32) else BGMM_TF_M(1, 48) else BGMM_TF_M(1, 64) else BGMM_TF_M(2, 16) else BGMM_TF_M(2, 32)
-    else { set_error("bgmm_pass(tf32): no M instantiation for MT=%d NB=%d", m.MT, m.NB); return BGMM_ENOSUP; }
-#undef BGMM_TF_M
+    // compile-time D for the common dimensions (static feature indices), the table-driven instantiation otherwise
+    if (D == 16) e = launch_m_t<16>(m, a, L, r_f32, p.KP, acct, ews, grid_e, grid_m, stream);
+    else if (D == 8) e = launch_m_t<8>(m, a, L, r_f32, p.KP, acct, ews, grid_e, grid_m, stream);
+    else if (D == 4) e = launch_m_t<4>(m, a, L, r_f32, p.KP, acct, ews, grid_e, grid_m, stream);
+    else e = launch_m_t<0>(m, a, L, r_f32, p.KP, acct, ews, grid_e, grid_m, stream);
     if (e != cudaSuccess) return check_cuda(e, "pass_tf32_m_kernel launch");
     launch_reduce_partials(a, L, grid_m, stream);
     return check_cuda(cudaGetLastError(), "pass_tf32 launch");
