@@ -142,7 +142,7 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
     const int RSP = KP + 4;                                    // pitch: 16-byte aligned, rows 4 banks apart
     uint64_t* mbar = reinterpret_cast<uint64_t*>(rst + TF_TILE * (64 + 4));  // [2] MMAs of TMEM buffer b complete
     uint64_t* tfree = mbar + 2;                                // [2] TMEM buffer b drained by all 16 epilogue warps
-    uint64_t* astaged = mbar + 4;                              // [2] A stage s written (512 arrivals)
+    uint64_t* astaged = mbar + 4;                              // [2] A stage s written (one arrival per staging warp)
     uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 6);
     __shared__ double red[40];
 
@@ -151,7 +151,7 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
     if (tid == 0) {
         mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
         mbar_init(&tfree[0], TE_THREADS / 32); mbar_init(&tfree[1], TE_THREADS / 32);
-        mbar_init(&astaged[0], TE_THREADS); mbar_init(&astaged[1], TE_THREADS);
+        mbar_init(&astaged[0], TE_THREADS / 32); mbar_init(&astaged[1], TE_THREADS / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (warp == 0) tc::tmem_alloc<512>(tslot);
@@ -161,6 +161,10 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
     tc::fence_after_sync();
     const uint32_t tbase = *tslot;
     const uint32_t idesc = tc::make_idesc_tf32(128, nmma, 0, 0);
+    // the last chunk may hold fewer components: its MMAs cover only their columns (C2: 8 of 16 -> N = 128, a quarter less
+    // tensor-core time per tile)
+    const int n_last = (((KP - (nchunks - 1) * cpc) * DP) + 15) & ~15;
+    const uint32_t idesc_last = tc::make_idesc_tf32(128, n_last < nmma ? n_last : nmma, 0, 0);
     const uint32_t b_lbo = 4 * 32, b_sbo = 4 * KCH * 32, a_lbo = 4 * A_LBO, a_sbo = 4 * A_SBO;    // bytes
 
     const int64_t ntiles = (a.n + TF_TILE - 1) / TF_TILE;
@@ -218,7 +222,7 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
 #pragma unroll
             for (int ks = 0; ks < KGR; ++ks) {
                 tc::mma_tf32(d_tmem, tc::make_smem_desc(aa + 2 * ks * a_lbo, a_lbo, a_sbo),
-                             tc::make_smem_desc(bb + 2 * ks * b_lbo, b_lbo, b_sbo), idesc, accum);
+                             tc::make_smem_desc(bb + 2 * ks * b_lbo, b_lbo, b_sbo), ch == nchunks - 1 ? idesc_last : idesc, accum);
                 accum = 1;
             }
         }
@@ -245,7 +249,8 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
             stage_tile(0);
             fetch_tile(1);
             tc::fence_proxy_async();
-            mbar_arrive(&astaged[0]);
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&astaged[0]);
         }
         for (int64_t lt = 0; lt < my_tiles; ++lt) {
             // stage the next tile now: its MMAs can start as soon as a TMEM buffer frees up.  (Its stage was last read by tile
@@ -254,7 +259,8 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
                 stage_tile(lt + 1);
                 fetch_tile(lt + 2);
                 tc::fence_proxy_async();
-                mbar_arrive(&astaged[(lt + 1) & 1]);
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&astaged[(lt + 1) & 1]);
             }
             const int64_t row = (blockIdx.x + lt * gridDim.x) * TF_TILE + rowt;
             const bool valid = row < a.n;
@@ -269,7 +275,7 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
                     mbar_wait(&mbar[g & 1], (uint32_t)((g >> 1) & 1));
                     tc::fence_after_sync();
                     const uint32_t t0 = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(g & 1) * TF_NMAX + 64 * gq;
-                    if (gq * CPB < cpc && dbg != 1) {            // uniform per warp: this 64-column batch holds components
+                    if (gq * CPB < cpc && ch * cpc + gq * CPB < KP && dbg != 1) {   // uniform per warp: this 64-column batch holds components
                         uint32_t v[4][16];
 #pragma unroll
                         for (int h = 0; h < 4; ++h) tc::tmem_ld16_async(t0 + 16 * h, v[h]);
@@ -412,8 +418,6 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
 // components are contiguous), so the fp32 error of a partial sum never exceeds that of 2048 samples.  Moments are about
 // the global centre (format 0), reduced over the CTAs by reduce_partials_kernel.
 constexpr int TM_SUB = 64;                   // samples per sub-tile
-constexpr int TM_LBO = 36;                   // floats: padded pitch of one 16-byte k-chunk column (144 B)
-constexpr int TM_SBO = (TM_SUB / 4) * TM_LBO;   // floats: one 8-row group = 16 k-chunks
 constexpr int TF_FLUSH = 32;                 // sub-tiles between TMEM -> fp64 flushes (2048 samples)
 constexpr int TM_GEN = 256;                  // generator threads: four per sample
 constexpr int TM_STG = 256;                  // staging threads: warps w with (w & 3) = 0 own TMEM lanes 0-31 (components 0-31),
@@ -423,24 +427,27 @@ constexpr int TM_BLOCK = TM_GEN + TM_STG + 32;   // warps 0-15 with (w & 3) >= 2
 
 // Phi rows of ONE sample into the hi / lo staging tiles, features with (p & 3) == Q only; D is a compile-time constant so
 // every product index and every shared-memory offset is static (5 instructions per feature: mul, cvt, sub, 2 stores)
-template <int DT, int Q>
-__device__ __forceinline__ void gen_features(const float (&xv)[DT > 0 ? DT : 1], float* __restrict__ Bh, float* __restrict__ Bl,
-                                             const int sbase) {
-    auto put = [&](int p, float v) {
-        const float h = tc::tf32_hi(v);
-        const int o = (p >> 3) * TM_SBO + (p & 7) * 4 + sbase;
-        Bh[o] = h;
-        Bl[o] = v - h;
+// A generator warp owns the features p = FG (mod 8) — one row of every swizzled 8-row atom, so the XOR of the chunk index is
+// a per-thread constant — and a lane two consecutive samples: 8-byte stores, 4 instructions per (sample, feature).
+// o0 = float offset of (row FG of atom row-group 0, this lane's sample pair).
+template <int DT, int FG>
+__device__ __forceinline__ void gen_features(const float (&xa)[DT > 0 ? DT : 1], const float (&xb)[DT > 0 ? DT : 1],
+                                             float* __restrict__ Bh, float* __restrict__ Bl, const int o0) {
+    auto put = [&](int p, float va, float vb) {
+        const float ha = tc::tf32_trunc(va), hb = tc::tf32_trunc(vb);
+        const int o = (p >> 3) * 256 + o0;
+        *reinterpret_cast<float2*>(Bh + o) = make_float2(ha, hb);
+        *reinterpret_cast<float2*>(Bl + o) = make_float2(va - ha, vb - hb);
     };
-    if (Q == 0) put(0, 1.0f);
+    if (FG == 0) put(0, 1.0f, 1.0f);
 #pragma unroll
     for (int i = 0; i < DT; ++i)
-        if (((1 + i) & 3) == Q) put(1 + i, xv[i]);
+        if (((1 + i) & 7) == FG) put(1 + i, xa[i], xb[i]);
 #pragma unroll
     for (int i = 0; i < DT; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j)
-            if (((1 + DT + i * (i + 1) / 2 + j) & 3) == Q) put(1 + DT + i * (i + 1) / 2 + j, xv[i] * xv[j]);
+            if (((1 + DT + i * (i + 1) / 2 + j) & 7) == FG) put(1 + DT + i * (i + 1) / 2 + j, xa[i] * xa[j], xb[i] * xb[j]);
 }
 
 // DT = compile-time D (0: run-time D through a table); NF = features rounded up to 16 (the MMA N), passed at run time
@@ -448,20 +455,22 @@ template <int DT>
 __global__ void __launch_bounds__(TM_BLOCK, 1)
 pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r_f32, const int KP, const int NF, const int nst,
                    double* __restrict__ acct, const double* __restrict__ ews, const int n_ews) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw_m[];
     pdl_trigger();
     pdl_wait();
     volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
     if (pass_skip(ctrl, a.force, a.ignore_robust, a.crit_limit)) return;
     const int K = L.K, D = DT > 0 ? DT : L.D, P = L.P, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* __restrict__ x = static_cast<const float*>(a.x);
-    const int bpart = (NF / 8) * TM_SBO;                       // floats of one part (hi or lo) of one stage
-    float* Bs = reinterpret_cast<float*>(smem_raw);            // [nst stages][2 parts][NF / 8][16 chunks][36]
+    const int bpart = NF * TM_SUB;                             // floats of one part (hi or lo) of one stage
+    // [nst stages][2 parts][2 k-atoms of 32 samples][NF / 8 row groups][8 features][128 bytes, chunks swizzled]
+    float* Bs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw_m) + 1023) & ~uintptr_t(1023));
     float* xs = Bs + 2 * nst * bpart;                                // [64][D + 2]: x', 1, 0   (run-time D only)
     unsigned short* ftab = reinterpret_cast<unsigned short*>(xs + (DT > 0 ? 0 : TM_SUB * (D + 2)));   // [P] (run-time D only)
     uint64_t* mbar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(ftab + (DT > 0 ? 0 : ((P + 7) & ~7))) + 15) & ~uintptr_t(15));
     uint64_t* mdone = mbar;                                    // [2] MMAs of sub-tile parity b complete (B stage + A buffer free)
-    uint64_t* bfull = mbar + 2;                                // [2] B stage b written (256 arrivals)
+    uint64_t* bfull = mbar + 2;                                // [2] B stage b written (one arrival per generator warp: 256
+                                                               //     per-thread arrivals on one mbarrier cost ~1000 cycles a sub-tile)
     uint64_t* afull = mbar + 4;                                // [2] A buffer b written (one arrival per staging warp)
     uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 6);
     const int KW = (KP + 31) / 32;                             // component warps with real rows (1 or 2)
@@ -487,7 +496,7 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
     for (int e = tid; e < NF * 64; e += TM_BLOCK) acc[e] = 0.0;
     if (tid == 0) {
         mbar_init(&mdone[0], 1); mbar_init(&mdone[1], 1);
-        mbar_init(&bfull[0], TM_GEN); mbar_init(&bfull[1], TM_GEN);
+        mbar_init(&bfull[0], TM_GEN / 32); mbar_init(&bfull[1], TM_GEN / 32);
         mbar_init(&afull[0], TM_STG / 32); mbar_init(&afull[1], TM_STG / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -509,6 +518,12 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
     const uint32_t idesc = tc::make_idesc_tf32(128, NF, 0, 0);
     const int64_t nsub = (a.n + TM_SUB - 1) / TM_SUB;
     const int64_t my_sub = blockIdx.x < nsub ? (nsub - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // K <= 32: the hi parts of R^T sit in TMEM lanes 0-31 and the lo parts in lanes 64-95 of the SAME columns, so one MMA
+    // against Phi_hi yields r_hi.Phi_hi and r_lo.Phi_hi in different accumulator rows, one against Phi_lo the other two
+    // products: two MMAs per k-step instead of three (and r_lo.Phi_lo comes for free).  Staging warps are then the even
+    // ones (lane quarters 0 and 2), generators the odd ones.  K > 32: components 32-63 need lanes 32-63, three MMAs.
+    const bool two = KW == 1;
+    const int wq = warp & 3;
 
     if (warp == TM_BLOCK / 32 - 1) {
         // =========================== ISSUER: one thread feeds the tensor core and nothing else ===========================
@@ -524,11 +539,12 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
                 uint32_t accum = since_flush > 0 ? 1u : 0u;
 #pragma unroll
                 for (int sp = 0; sp < 3; ++sp) {                // hi.hi, hi.lo, lo.hi
+                    if (two && sp == 2) break;
                     const uint32_t aa = sp == 2 ? al : ah, bb = sp == 1 ? bl : bh;
 #pragma unroll
                     for (int ks = 0; ks < TM_SUB / 8; ++ks) {
                         tc::mma_tf32_ts(tbase + 256, aa + 8 * ks,
-                                        tc::make_smem_desc(bb + 4 * 2 * ks * TM_LBO, 4 * TM_LBO, 4 * TM_SBO), idesc, accum);
+                                        tc::make_smem_desc_sw128(bb + (ks >> 2) * (NF * 128) + (ks & 3) * 32, 1024), idesc, accum);
                         accum = 1u;
                     }
                 }
@@ -537,19 +553,46 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
             __syncwarp();
             ++since_flush;
         }
-    } else if ((warp & 3) >= 2) {
+    } else if (two ? (wq & 1) : wq >= 2) {
         // =========================== GENERATOR WARPS: Phi of sub-tile t into B stage t & 1 ===========================
-        const int gtid = (((warp >> 2) << 1) + (warp & 3) - 2) * 32 + lane;     // 0 .. 255 over the generator warps
-        const int s_loc = gtid & 63, qd = gtid >> 6;            // four threads per sample: features by index mod 4
-        const int sbase = (s_loc >> 2) * TM_LBO + (s_loc & 3);
+        const int gtid = (((warp >> 2) << 1) + (two ? wq >> 1 : wq - 2)) * 32 + lane;     // 0 .. 255 over the generator warps
+        // run-time D: four threads per sample, features by index mod 4; xo[r] = the sample's word offset inside row r of a
+        // swizzled atom.  Compile-time D: warp gw owns the features p = gw (mod 8), lane l the samples 2 l and 2 l + 1.
+        const int s_loc = DT > 0 ? 2 * lane : (gtid & 63), qd = gtid >> 6, gw = gtid >> 5;
+        int xo[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) xo[r] = (s_loc >> 5) * (NF * 32) + (((((s_loc & 31) >> 2) ^ r)) << 2) + (s_loc & 3);
+        const int o0 = (s_loc >> 5) * (NF * 32) + gw * 32 + (((((s_loc & 31) >> 2) ^ gw)) << 2) + (s_loc & 3);
         for (int64_t t = 0; t < my_sub; ++t) {
             const int64_t sb = blockIdx.x + t * gridDim.x;
             const int64_t row = sb * TM_SUB + s_loc;
-            const bool valid = row < a.n;
-            float xv[DT > 0 ? DT : 1];
+            float xa[DT > 0 ? DT : 1], xb[DT > 0 ? DT : 1];
+            if (DT > 0 && gw == (int)(t & 7)) {
+                // the x rows of the NEXT sub-tile into L1 (one warp covers the 64 rows): the loads below were 60 % of the
+                // generators' stall samples (long scoreboard) when they went to L2 / HBM
+                const char* nx = reinterpret_cast<const char*>(x + (sb + gridDim.x) * TM_SUB * DT);
+                const char* endx = reinterpret_cast<const char*>(x + a.n * DT);
+                for (int o = 128 * lane; o < TM_SUB * DT * 4; o += 128 * 32)
+                    if (t + 1 < my_sub && nx + o < endx) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + o));
+            }
             if (DT > 0) {
+                const bool va = row < a.n, vb = row + 1 < a.n;
+                if (DT % 4 == 0) {
+                    const float4* pa = reinterpret_cast<const float4*>(x + row * DT);
 #pragma unroll
-                for (int i = 0; i < DT; ++i) xv[i] = valid ? __ldg(x + row * DT + i) : 0.f;
+                    for (int i = 0; i < DT / 4; ++i) {
+                        const float4 fa = va ? __ldg(pa + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 fb = vb ? __ldg(pa + DT / 4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xa[4 * i] = fa.x; xa[4 * i + 1] = fa.y; xa[4 * i + 2] = fa.z; xa[4 * i + 3] = fa.w;
+                        xb[4 * i] = fb.x; xb[4 * i + 1] = fb.y; xb[4 * i + 2] = fb.z; xb[4 * i + 3] = fb.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < DT; ++i) {
+                        xa[i] = va ? __ldg(x + row * DT + i) : 0.f;
+                        xb[i] = vb ? __ldg(x + (row + 1) * DT + i) : 0.f;
+                    }
+                }
             }
             // the MMAs that read this stage are done: sub-tile t - 2 with two stages, t - 1 with one (large feature counts)
             if (nst == 2) { if (t >= 2) mbar_wait(&mdone[t & 1], (uint32_t)(((t >> 1) - 1) & 1)); }
@@ -557,10 +600,16 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
             float* Bh = Bs + (size_t)(nst == 2 ? (t & 1) : 0) * 2 * bpart;
             float* Bl = Bh + bpart;
             if (DT > 0) {
-                if (qd == 0) gen_features<DT, 0>(xv, Bh, Bl, sbase);
-                else if (qd == 1) gen_features<DT, 1>(xv, Bh, Bl, sbase);
-                else if (qd == 2) gen_features<DT, 2>(xv, Bh, Bl, sbase);
-                else gen_features<DT, 3>(xv, Bh, Bl, sbase);
+                switch (gw) {                     // warp-uniform
+                    case 0: gen_features<DT, 0>(xa, xb, Bh, Bl, o0); break;
+                    case 1: gen_features<DT, 1>(xa, xb, Bh, Bl, o0); break;
+                    case 2: gen_features<DT, 2>(xa, xb, Bh, Bl, o0); break;
+                    case 3: gen_features<DT, 3>(xa, xb, Bh, Bl, o0); break;
+                    case 4: gen_features<DT, 4>(xa, xb, Bh, Bl, o0); break;
+                    case 5: gen_features<DT, 5>(xa, xb, Bh, Bl, o0); break;
+                    case 6: gen_features<DT, 6>(xa, xb, Bh, Bl, o0); break;
+                    default: gen_features<DT, 7>(xa, xb, Bh, Bl, o0); break;
+                }
             } else {
                 asm volatile("bar.sync 1, 256;" ::: "memory");  // xs free (previous sub-tile's products formed)
                 for (int e = gtid; e < TM_SUB * (D + 2); e += TM_GEN) {
@@ -573,28 +622,30 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
                 for (int p = qd; p < P; p += 4) {
                     const unsigned int code = ftab[p];
                     const float v = xr[code >> 8] * xr[code & 0xFF];
-                    const float h = tc::tf32_hi(v);
-                    const int o = (p >> 3) * TM_SBO + (p & 7) * 4 + sbase;
+                    const float h = tc::tf32_trunc(v);
+                    const int o = (p >> 3) * 256 + (p & 7) * 32 + xo[p & 7];
                     Bh[o] = h;
                     Bl[o] = v - h;
                 }
             }
             tc::fence_proxy_async();
-            mbar_arrive(&bfull[t & 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bfull[t & 1]);
         }
     } else {
         // =========================== STAGING WARPS: R^T into TMEM, MMA issue, flushes ===========================
-        const int cw = warp & 3;                                // 0: components 0-31 (TMEM lanes 0-31), 1: components 32-63
         const int sq = warp >> 2;                               // which 16 of the 64 samples (and which features of a flush)
-        const int c = 32 * cw + lane;
-        const uint32_t lane_base = tbase + ((uint32_t)(32 * cw) << 16);
+        const int c = two ? lane : 32 * wq + lane;              // the component of this lane
+        const bool lo_part = two && wq == 2;                    // this warp stages (and flushes) the lo parts
+        const int acol = two ? 32 * (wq >> 1) + lane : c;       // column of the float64 accumulator array
+        const uint32_t lane_base = tbase + ((uint32_t)(32 * wq) << 16);
         int since_flush = 0;
         auto flush = [&]() {                                    // D rows (lane = component) -> float64, feature-major
-            if (cw < KW) {
+            {
                 for (int p0 = 16 * sq; p0 < NF; p0 += 64) {
                     float v[16];
                     double o[16];
-                    double* ap = acc + (int64_t)p0 * 64 + c;
+                    double* ap = acc + (int64_t)p0 * 64 + acol;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) o[j] = __ldcg(ap + j * 64);     // 16 independent loads in flight
                     tc::tmem_ld16(lane_base + 256 + p0, v);
@@ -615,8 +666,15 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
                     rv[j][u] = (t < my_sub && row < a.n && c < KP) ? __ldg(r_f32 + row * KP + c) : 0.f;
                 }
         };
-        if (cw < KW) load_r(0);
+        load_r(0);
         for (int64_t t = 0; t < my_sub; ++t) {
+            if (!lo_part && t + 2 < my_sub) {
+                // r rows of sub-tile t + 2 (this warp's 16 rows = 64 KP bytes, contiguous) towards L1
+                const int64_t r0 = (blockIdx.x + (t + 2) * gridDim.x) * TM_SUB + 16 * sq;
+                const int rows_here = (int)max((int64_t)0, min((int64_t)16, a.n - r0));
+                const char* pr = reinterpret_cast<const char*>(r_f32 + r0 * KP);
+                if (128 * lane < rows_here * KP * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 128 * lane));
+            }
             if (t >= 2) mbar_wait(&mdone[t & 1], (uint32_t)(((t >> 1) - 1) & 1));     // A buffer t & 1 free
             tc::fence_after_sync();
             if (since_flush == TF_FLUSH) {
@@ -627,15 +685,19 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
                 since_flush = 0;
                 tc::fence_before_sync();
             }
-            if (cw < KW) {
+            {
                 const uint32_t abase = lane_base + 128 * (uint32_t)(t & 1);
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     float h[8], l[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { h[u] = tc::tf32_hi(rv[j][u]); l[u] = rv[j][u] - h[u]; }
-                    tc::tmem_st8(abase + 16 * sq + 8 * j, h);
-                    tc::tmem_st8(abase + 64 + 16 * sq + 8 * j, l);
+                    for (int u = 0; u < 8; ++u) { h[u] = tc::tf32_trunc(rv[j][u]); l[u] = rv[j][u] - h[u]; }
+                    if (two) {
+                        tc::tmem_st8(abase + 16 * sq + 8 * j, lo_part ? l : h);
+                    } else {
+                        tc::tmem_st8(abase + 16 * sq + 8 * j, h);
+                        tc::tmem_st8(abase + 64 + 16 * sq + 8 * j, l);
+                    }
                 }
                 load_r(t + 1);
                 tc::tmem_wait_st();
@@ -660,7 +722,7 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
     __syncthreads();
     for (int e = tid; e < K * P; e += TM_BLOCK) {
         const int k = e / P, p = e - k * P;
-        part[(int64_t)k * L.pitch + p] = acc[(int64_t)p * 64 + k];
+        part[(int64_t)k * L.pitch + p] = acc[(int64_t)p * 64 + k] + (two ? acc[(int64_t)p * 64 + 32 + k] : 0.0);
     }
     if (blockIdx.x == 0 && tid == 0) {
         double v = 0.0;
@@ -685,8 +747,8 @@ static Tf32MPlan plan_tf32_m(int K, int D) {
     const int P = feat_count(D);
     m.NF = (P + 15) & ~15;
     auto bytes = [&](int nst) {
-        return sizeof(float) * ((size_t)2 * nst * (m.NF / 8) * TM_SBO + (size_t)TM_SUB * (D + 2)) +
-               sizeof(unsigned short) * ((P + 7) & ~7) + 96;
+        return sizeof(float) * ((size_t)2 * nst * m.NF * TM_SUB + (size_t)TM_SUB * (D + 2)) +
+               sizeof(unsigned short) * ((P + 7) & ~7) + 96 + 1024;
     };
     m.nst = bytes(2) <= 220 * 1024 ? 2 : 1;                    // two Phi stages when they fit (P <= ~190), else one
     m.smem = bytes(m.nst);

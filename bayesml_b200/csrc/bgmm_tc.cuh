@@ -41,6 +41,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
     return d;                                 // base offset 0, lbo mode 0, layout type 0 (no swizzle)
 }
+// K-major operand in the 128-byte-swizzle layout: a row (M or N index) holds 32 consecutive k (128 bytes), 8 rows form a
+// 1024-byte atom (1024-byte aligned) whose 16-byte chunks are XOR-ed with the row index (chunk ^ (row & 7)); SBO = byte
+// distance between 8-row groups; one MMA (8 k) starts 32 bytes further along the row.  The tensor core fetches whole
+// 128-byte rows: measured twice the operand rate of the no-swizzle layout (whose core matrices it fetches one by one).
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                   // LBO: unused for a swizzled K-major operand
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                   // layout type: SWIZZLE_128B
+    return d;
+}
+// float offset of element (row, k) of a [rows][32 k] swizzled atom column (atoms of 8 rows stacked every 256 floats)
+__device__ __forceinline__ int sw128_off(int row, int k) {
+    return (row >> 3) * 256 + (row & 7) * 32 + ((((k >> 2) & 7) ^ (row & 7)) << 2) + (k & 3);
+}
 // Instruction descriptor for kind::tf32: fp32 accumulate, A and B tf32, M x N tile, K-major (0) or MN-major (1) operands.
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -117,6 +134,11 @@ __device__ __forceinline__ float tf32_hi(float v) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
 }
+
+// the cheap split of the streaming kernels: hi = the top 19 bits (one LOP3 instead of the four instructions cvt.rna
+// compiles to), lo = v - hi exact with <= 13 significant bits of which the MMA reads 11: 2^-21 |v| per term, one bit worse
+// than the rounded split
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 // canonical no-swizzle offsets (in floats) of element (row, col) of a tile whose row groups / chunks are laid out as stated
 //   K-major tile [rows][kcols]: core (row / 8, col / 4) at (row / 8) * sbo_f + (col / 4) * lbo_f

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
     __shared__ uint32_t tmem_slot;
     float* As = reinterpret_cast<float*>(smem_raw);            // 128 x Kd
     float* Bs = As + 128 * Kd;                                 // N x Kd
+    const bool b_sw = b_mn == 3;                               // B K-major in the 128-byte-swizzle layout (Kd % 32 == 0)
+    if (b_sw) Bs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Bs) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, warp = tid >> 5;
     const int kch = Kd / 4, kgr = Kd / 8;
     // K-major: row-group major, k-chunks contiguous -> LBO = 128 B, SBO = kch * 128 B
@@ -27,7 +29,8 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
     }
     for (int e = tid; e < N * Kd; e += 128) {
         const int r = e / Kd, c = e - r * Kd;
-        Bs[b_mn ? tc::mnmajor_off(c, r, b_lbo, b_sbo) : tc::kmajor_off(r, c, b_lbo, b_sbo)] = B[e];
+        if (b_sw) Bs[(c >> 5) * (N / 8) * 256 + tc::sw128_off(r, c & 31)] = B[e];
+        else Bs[b_mn ? tc::mnmajor_off(c, r, b_lbo, b_sbo) : tc::kmajor_off(r, c, b_lbo, b_sbo)] = B[e];
     }
     if (tid == 0) mbar_init(&mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -50,10 +53,12 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
         tc::fence_after_sync();
     }
     if (tid == 0 && a_mn == 2) {
-        const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, b_mn);
+        const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, b_sw ? 0 : b_mn);
         for (int ks = 0; ks < kgr; ++ks) {
             const uint32_t b_addr = tc::smem_u32(Bs) + 4 * (b_mn ? ks * b_lbo : 2 * ks * b_lbo);
-            tc::mma_tf32_ts(tbase, tbase + 256 + 8 * ks, tc::make_smem_desc(b_addr, 4 * b_lbo, 4 * b_sbo), idesc, ks > 0 ? 1u : 0u);
+            const uint64_t bd = b_sw ? tc::make_smem_desc_sw128(tc::smem_u32(Bs) + (ks >> 2) * (N / 8) * 1024 + (ks & 3) * 32, 1024)
+                                     : tc::make_smem_desc(b_addr, 4 * b_lbo, 4 * b_sbo);
+            tc::mma_tf32_ts(tbase, tbase + 256 + 8 * ks, bd, idesc, ks > 0 ? 1u : 0u);
         }
         tc::mma_commit(&mbar);
     } else if (tid == 0) {
@@ -91,7 +96,11 @@ extern "C" int bgmm_tc_selftest(const float* A, const float* B, float* D, int N,
         set_error("bgmm_tc_selftest: bad argument (N=%d multiple of 16 in [16, 256], Kd=%d multiple of 8 in [8, 64])", N, Kd);
         return BGMM_EINVAL;
     }
-    const size_t smem = sizeof(float) * (size_t)(128 + N) * Kd + 128;
+    if (b_mn_major == 3 && (a_mn_major != 2 || (Kd % 32) != 0)) {
+        set_error("bgmm_tc_selftest: the swizzled B layout (3) needs A in tensor memory (2) and Kd a multiple of 32");
+        return BGMM_EINVAL;
+    }
+    const size_t smem = sizeof(float) * (size_t)(128 + N) * Kd + 128 + 1024;
     cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tc_selftest)");
     tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, B, D, N, Kd, a_mn_major, b_mn_major);
