@@ -648,10 +648,11 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tracked = load_peaks()
     fp64_peak = tracked["fp64_tflops"]
-    traffic = None
+    traffic, pipe_active = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         traffic = tr.get(f"{args.config}_n{world}")
+        pipe_active = tr.get("tensor_pipe_active_pct", {}).get(f"{args.config}_n{world}")
     except Exception:
         pass
     kname = {_lib.PASS_DMMA: "bgmm::pass_dmma_kernel", _lib.PASS_F32: "bgmm::pass_f32_kernel",
@@ -665,6 +666,9 @@ def main():
         "kernel": kname,
         "kernel_ms": pass_ms, "kernel_share_of_step": pass_ms / ms_per_step,
         "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": x_bytes,
+        # frac can exceed 1: SURVEY §8d's algorithmic count charges the full D x D quadratic form, the kernels contract the
+        # packed symmetric feature map (about half the flops); the ncu capture of the same kernel gives the pipe's duty cycle
+        "tensor_pipe_active_pct_ncu": pipe_active,
         "peak_source": "FP64 tensor pipe (DMMA.8x8x4), " + tracked["source"],
         "hbm": {"achieved_gbs": x_bytes / (pass_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": x_bytes / (pass_ms * 1e-3) / 1e9 / hbm_peak,
@@ -679,7 +683,10 @@ def main():
         tf32_peak = float(peaks.get("bf16_tflops", 1640.0)) / 2.0
         kd, dp, kp = (d + 1 + 7) // 8 * 8, (4 if d <= 4 else 8 if d <= 8 else 16 if d <= 16 else 32), (k + 3) // 4 * 4
         p_feat = 1 + d + d * (d + 1) // 2
-        executed = n_local * 2.0 * 3.0 * (kd * kp * dp + ((p_feat + 127) // 128 * 128) * ((k + 15) // 16 * 16))
+        # executed: E = 3 split products of [128 x kd] . [kd x kp dp]; statistics = 128-row (component) tiles against
+        # nf features, 2 products when the lo parts ride in spare tensor-memory lanes (K <= 32), else 3
+        nf = (p_feat + 15) // 16 * 16
+        executed = n_local * 2.0 * (3.0 * kd * kp * dp + (2.0 if k <= 32 else 3.0) * 128 * nf)
         roofline.update({"bound": "tensor", "achieved": ach_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": ach_tflops / tf32_peak,
                          "peak_source": "kind::tf32 dense = MEASURED_PEAKS.json bf16_tflops / 2 (no measured tf32 entry)",
