@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
 #pragma unroll
         for (int i = 0; i < D; ++i) { xv[i] = xn1[i]; xn1[i] = xn2[i]; }
         load_row(n + 2 * stride, xn2);
+        // the register rotation above touches the row loaded ONE iteration ago (22 % of the stall samples in the round-2 C3
+        // profile when it came from HBM): pull the rows of six iterations ahead into L2 so that load is a ~300-cycle hit
+        if (n + 6 * stride < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (n + 6 * stride) * D));
         // statistics features about the global centre: phi = [1, x, x_i x_j (i >= j)] (also the E-step's in the feature form)
         float phi[P];
         phi[0] = 1.f;
