@@ -523,6 +523,145 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
     }
 }
 
+// Phase A / A' on the FP64 tensor pipe (K > 8).  The K basis runs of a chunk are ONE matrix recursion: with row j0 of S the
+// message vector started from unit vector j0,
+//     forward :  S <- (S . A~) o rho_i          (column scaling; `_hiddenmarkovnormal.py` :999-1004 applied to K vectors)
+//     backward:  S <- ((S o rho_i) . A~^T) / chat_i                                              (:1010-1011)
+// i.e. a right-multiplication by a CONSTANT matrix per step.  One warp owns one chunk and keeps S in DMMA accumulator
+// fragments (m8n8k4: lane (r, q) holds S[8 mb + r][8 nb + 2 q + e], e = 0, 1).  The same registers are the A operand of
+// the next step: for fixed (kb, e) they form an 8 x 4 tile over the columns k = 8 kb + 2 q + e, a permuted k-block, and the
+// sum over k does not care about the order as long as the constant B fragments use the same rows — so there is no
+// layout conversion, no shuffle and no shared memory in the step: (KP/8)^3 * 2 DMMAs (128 at K = 32) + KP scalings.
+// The vector form above does the same 2 K^3 flops per element as K dependent mat-vec chains through shared memory
+// (12.4 of h2's 16.6 ms); this one is bound by the DMMA pipe.  Rows are renormalised every 8 steps (and at the end of a
+// forward chunk: phase B relies on rows summing to one), with the same zero-row rule as the vector kernels.
+template <int KP, bool FWD>
+__global__ void __launch_bounds__(HT, 1) hmm_basis_mma_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+                                                              const double* __restrict__ hst, const HmmLayout H,
+                                                              const int force, const ScanBufs B) {
+    constexpr int NB = KP / 8;
+    const volatile int* ctrl = reinterpret_cast<const volatile int*>(st + L.ctrl);
+    if (!force && ctrl[BGMM_CTRL_DONE]) return;
+    if (hmm_window(st, L, hst, H, sp) > 0) return;
+    const int K = sp.K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, r = lane >> 2, q = lane & 3;
+    const int64_t item = (int64_t)blockIdx.x * HW + warp;
+    if (item >= sp.nch - 1) return;                               // whole warps only: no block barrier below
+    const int c = FWD ? (int)item : 1 + (int)item;                // forward: chunks 0 .. nch-2, backward: 1 .. nch-1
+    const double* at = current_at(st, L, hst, H);
+    const double* __restrict__ rhohat = B.rhohat;
+    const double* __restrict__ ichat = B.ichat;
+    // constant B fragments: R[k][n] with k = 8 kb + 2 q + e, n = 8 nb + r;  R = A~ (forward) or A~^T (backward)
+    double bc[NB][2][NB];
+#pragma unroll
+    for (int kb = 0; kb < NB; ++kb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                const int k = 8 * kb + 2 * q + e, n = 8 * nb + r;
+                bc[kb][e][nb] = (k < K && n < K) ? (FWD ? at[k * K + n] : at[n * K + k]) : 0.0;
+            }
+    double sm[NB][NB][2], slog[NB];
+#pragma unroll
+    for (int mb = 0; mb < NB; ++mb) {
+        slog[mb] = 0.0;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = 8 * mb + r, col = 8 * nb + 2 * q + e;
+                sm[mb][nb][e] = (row == col && row < K) ? 1.0 : 0.0;
+            }
+    }
+    const int64_t i0 = (int64_t)c * sp.L;
+    const int64_t i1 = (i0 + sp.L < sp.n ? i0 + sp.L : sp.n) - 1;
+    const int nsteps = (int)(i1 - i0 + 1);
+    // emission values (this lane's 2 NB columns) two steps ahead of the dependent chain
+    auto load_rho = [&](int s, double (&dst)[NB][2]) {
+        const int64_t i = FWD ? i0 + s : i1 - s;
+        const bool ok = s < nsteps;
+        const double sc = FWD ? 1.0 : (ok ? ichat[i] : 0.0);
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int col = 8 * nb + 2 * q + e;
+                dst[nb][e] = (ok && col < K) ? rhohat[i * K + col] * sc : 0.0;
+            }
+    };
+    double rc[NB][2], rn[NB][2];
+    load_rho(0, rc);
+    load_rho(1, rn);
+    for (int s = 0; s < nsteps; ++s) {
+        double rho[NB][2];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) { rho[nb][e] = rc[nb][e]; rc[nb][e] = rn[nb][e]; }
+        load_rho(s + 2, rn);
+        const bool no_transition = FWD && i0 + s == 0;            // :1000 — the first element has no transition
+#pragma unroll
+        for (int mb = 0; mb < NB; ++mb) {
+            if (!FWD) {
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { sm[mb][nb][0] *= rho[nb][0]; sm[mb][nb][1] *= rho[nb][1]; }
+            }
+            if (!no_transition) {
+                double o[NB][2];
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { o[nb][0] = 0.0; o[nb][1] = 0.0; }
+#pragma unroll
+                for (int kb = 0; kb < NB; ++kb)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb) dmma(o[nb][0], o[nb][1], sm[mb][kb][e], bc[kb][e][nb]);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { sm[mb][nb][0] = o[nb][0]; sm[mb][nb][1] = o[nb][1]; }
+            }
+            if (FWD) {
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { sm[mb][nb][0] *= rho[nb][0]; sm[mb][nb][1] *= rho[nb][1]; }
+            }
+        }
+        if ((s & 7) == 7 || (FWD && s == nsteps - 1)) {
+#pragma unroll
+            for (int mb = 0; mb < NB; ++mb) {
+                double sum = 0.0;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) sum += sm[mb][nb][0] + sm[mb][nb][1];
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                if (sum > 0.0) {
+                    const double inv = 1.0 / sum;
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) { sm[mb][nb][0] *= inv; sm[mb][nb][1] *= inv; }
+                    slog[mb] += log(sum);
+                } else {
+                    // impossible start (forward) / end (backward) state: exactly zero response, log scale -inf
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) { sm[mb][nb][0] = 0.0; sm[mb][nb][1] = 0.0; }
+                    slog[mb] = -INFINITY;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < NB; ++mb) {
+        const int j0 = 8 * mb + r;
+        if (j0 < K) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = 8 * nb + 2 * q + e;
+                    if (col < K) B.tf[((int64_t)c * K + j0) * K + col] = sm[mb][nb][e];
+                }
+            if (q == 0) B.ls[(int64_t)c * K + j0] = slog[mb];
+        }
+    }
+}
+
 // Mixing mode: the boundary vector of every chunk from a warm-up window of W elements (see hmm_window).
 //   FWD : v[c] = normalised alpha at element cL-1, run over [cL-W, cL-1] from a flat vector (from pi~ when the window
 //         reaches element 0, where the first element has no transition: then it is the exact recursion);
@@ -696,12 +835,21 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
     }
     // boundary vectors: either {basis runs, sequential sweep} or {one warm-up window per chunk}; the device decides
     // (hmm_window) from the current A~, the kernels of the other branch return at once
-    if (sp.nch > 1) hmm_fwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    const char* env_mma = getenv("BGMM_HMM_BASIS_MMA");                    // 0: the vector basis runs (tests compare the two)
+    const int basis_mma = (env_mma == nullptr || atoi(env_mma) != 0) ? 1 : 0;
+    const unsigned gm = (unsigned)((sp.nch - 1 + HW - 1) / HW);          // tensor-pipe basis runs: one warp per chunk
+    if (sp.nch > 1) {
+        if (KP >= 16 && basis_mma) hmm_basis_mma_kernel<(KP >= 16 ? KP : 16), true><<<gm, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+        else hmm_fwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    }
     launch_seq<KP, true>(sp, st, L, hst, H, force, B, smem_seq, stream);
     hmm_window_kernel<KP, true><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_fwd_kernel<KP, 0><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_cs_kernel<<<sp.nch, 128, 0, stream>>>(sp, st, L, force, B);
-    if (sp.nch > 1) hmm_bwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    if (sp.nch > 1) {
+        if (KP >= 16 && basis_mma) hmm_basis_mma_kernel<(KP >= 16 ? KP : 16), false><<<gm, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+        else hmm_bwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+    }
     launch_seq<KP, false>(sp, st, L, hst, H, force, B, smem_seq, stream);
     hmm_window_kernel<KP, false><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_bwd_kernel<KP, 0><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
