@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(HT) hmm_bwd_kernel(const ScanPlan sp, const do
 // (12.4 of h2's 16.6 ms); this one is bound by the DMMA pipe.  Rows are renormalised every 8 steps (and at the end of a
 // forward chunk: phase B relies on rows summing to one), with the same zero-row rule as the vector kernels.
 template <int KP, bool FWD>
-__global__ void __launch_bounds__(HT, 1) hmm_basis_mma_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
+__global__ void __launch_bounds__(HT, KP >= 32 ? 1 : 4) hmm_basis_mma_kernel(const ScanPlan sp, const double* __restrict__ st, const Layout L,
                                                               const double* __restrict__ hst, const HmmLayout H,
                                                               const int force, const ScanBufs B) {
     constexpr int NB = KP / 8;
@@ -839,7 +839,7 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
     const int basis_mma = (env_mma == nullptr || atoi(env_mma) != 0) ? 1 : 0;
     const unsigned gm = (unsigned)((sp.nch - 1 + HW - 1) / HW);          // tensor-pipe basis runs: one warp per chunk
     if (sp.nch > 1) {
-        if (KP >= 16 && basis_mma) hmm_basis_mma_kernel<(KP >= 16 ? KP : 16), true><<<gm, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+        if (KP >= 2 && basis_mma) hmm_basis_mma_kernel<(KP >= 8 ? KP : 8), true><<<gm, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
         else hmm_fwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     }
     launch_seq<KP, true>(sp, st, L, hst, H, force, B, smem_seq, stream);
@@ -847,7 +847,7 @@ static int launch_scan(const ScanPlan& sp, double* st, const Layout& L, double* 
     hmm_fwd_kernel<KP, 0><<<gc, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     hmm_cs_kernel<<<sp.nch, 128, 0, stream>>>(sp, st, L, force, B);
     if (sp.nch > 1) {
-        if (KP >= 16 && basis_mma) hmm_basis_mma_kernel<(KP >= 16 ? KP : 16), false><<<gm, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
+        if (KP >= 2 && basis_mma) hmm_basis_mma_kernel<(KP >= 8 ? KP : 8), false><<<gm, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
         else hmm_bwd_kernel<KP, 1><<<gb, HT, 0, stream>>>(sp, st, L, hst, H, force, B);
     }
     launch_seq<KP, false>(sp, st, L, hst, H, force, B, smem_seq, stream);

@@ -203,7 +203,7 @@ def test_window_and_basis_paths_agree(lib_built, monkeypatch):
     assert np.allclose(out["0"][3], out["16384"][3], rtol=1e-11)
 
 
-@pytest.mark.parametrize("K,D,n", [(32, 3, 120_000), (12, 2, 90_000), (17, 4, 40_000)])
+@pytest.mark.parametrize("K,D,n", [(32, 3, 120_000), (12, 2, 90_000), (17, 4, 40_000), (8, 2, 200_000), (3, 2, 100_000), (5, 3, 60_000)])
 def test_tensor_pipe_basis_runs_match_the_vector_basis_runs(K, D, n, lib_built, monkeypatch):
     """Phase A / A' as one DMMA matrix recursion per chunk (hmm_basis_mma_kernel, K > 8) against the K vector recursions
     per chunk it replaces, and against the oracle: same fit.  The window shortcut is disabled so the basis path runs."""
