@@ -12,7 +12,7 @@ def _tf32(a):
 
 
 # K-major operands only: with either operand MN-major in the no-swizzle layout the B200 returned an all-zero tile for
-# kind::tf32 (measured in round 2, scratch note in DESIGN.md §4.7), so the fp32-mode kernels stage every operand K-major.
+# kind::tf32 (measured in round 2), so the fp32-mode kernels stage every operand K-major.
 # a_mn = 2: the A operand in tensor memory (tcgen05.st by the thread that owns the row, tcgen05.mma [d], [a], b-desc)
 # b_mn = 3: B K-major in the 128-byte-swizzle layout (what the statistics kernel stages), needs Kd % 32 == 0
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (2, 0), (2, 3)])
