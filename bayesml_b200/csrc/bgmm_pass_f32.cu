@@ -18,6 +18,7 @@
 // bar 1e-4 relative against the fp64 oracle fed the same fp32-rounded X.
 #include "bgmm_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace bgmm {
 
@@ -41,6 +42,58 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// per-CTA partial from the per-warp float64 accumulators, then the last CTA (atomic ticket) reduces the partials in CTA
+// order and publishes them to the peers of a row-sharded fit
+template <int P>
+__device__ __forceinline__ void f32_epilogue(const PassArgs& a, const Layout& L, volatile int* ctrl,
+                                             double (&wsum)[F32_THREADS / 32][F32_KMAX * P + 1], int& is_last) {
+    constexpr int NW = F32_THREADS / 32;
+    const int K = L.K, tid = threadIdx.x;
+    // ---- per-CTA partial (fp64, logical layout [K][pitch]) ----
+    const int64_t len = L.stats_len;
+    double* part = a.workspace + (int64_t)blockIdx.x * len;
+    for (int64_t o = tid; o < len; o += F32_THREADS) part[o] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < K * P; i += F32_THREADS) {
+        const int k = i / P, p = i - k * P;
+        double v = 0.0;
+        for (int w = 0; w < NW; ++w) v += wsum[w][k * P + p];
+        part[(int64_t)k * L.pitch + p] = v;
+    }
+    if (tid == 0) {
+        double v = 0.0;
+        for (int w = 0; w < NW; ++w) v += wsum[w][F32_KMAX * P];
+        part[(int64_t)K * L.pitch] = v;
+    }
+
+    // ---- last CTA reduces the partials in CTA order ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int tk = atomicAdd(const_cast<int*>(&ctrl[BGMM_CTRL_PASS_TICKET]), 1);
+        is_last = (tk == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double* out = a.state + L.stats;
+    const double* ws = a.workspace;
+    for (int64_t o = tid; o < len; o += F32_THREADS) {
+        double s0 = 0.0;
+        for (int b = 0; b < (int)gridDim.x; ++b) s0 += __ldcg(&ws[(int64_t)b * len + o]);
+        if (o == (int64_t)K * L.pitch + 1) s0 = (double)a.n;
+        if (o == (int64_t)K * L.pitch + 2) { out[o] = 0.0; continue; }      // format marker: moments about the centre
+        out[o] = a.accumulate ? out[o] + s0 : s0;
+    }
+    if (tid == 0) ctrl[BGMM_CTRL_PASS_TICKET] = 0;
+    const CommDesc* cd = a.no_publish ? nullptr : comm_of(ctrl);
+    if (cd != nullptr) {                  // row-sharded fit: hand the reduced statistics to the peers (bgmm_comm.cu)
+        __threadfence();
+        __syncthreads();
+        publish_block(a.state, L, cd);
+    }
+}
+
 template <int D>
 struct F32Params {                   // per component, fp32, in shared memory
     float m[D];
@@ -51,7 +104,7 @@ struct F32Params {                   // per component, fp32, in shared memory
 constexpr int F32_FEAT_CRIT = 128;   // feature-map E-step up to this value of ctrl.CRIT
 
 template <int D, bool OUT>
-__global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a, const Layout L) {
+__global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a, const Layout L, const int skip_if_feat) {
     constexpr int P = 1 + D + D * (D + 1) / 2;
     constexpr int NW = F32_THREADS / 32;
     __shared__ F32Params<D> prm[F32_KMAX];
@@ -64,6 +117,7 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
     const double* Pc = a.state + L.params[ctrl[BGMM_CTRL_CUR]];
     const float* __restrict__ x = static_cast<const float*>(a.x);
     const bool feat = ctrl[BGMM_CTRL_CRIT] <= F32_FEAT_CRIT;   // uniform: which E-step form this launch uses
+    if (skip_if_feat && feat) return;                           // pass_f32x2_kernel (launched just before) did this pass
 
     // ---- prologue: whitening factors of Lambda_k = nu_k W_k (fp64 Cholesky of a D x D matrix per component) ----
     if (tid < F32_KMAX) {
@@ -261,50 +315,141 @@ __global__ void __launch_bounds__(F32_THREADS) pass_f32_kernel(const PassArgs a,
     flush();
     __syncthreads();
 
-    // ---- per-CTA partial (fp64, logical layout [K][pitch]) ----
-    const int64_t len = L.stats_len;
-    double* part = a.workspace + (int64_t)blockIdx.x * len;
-    for (int64_t o = tid; o < len; o += F32_THREADS) part[o] = 0.0;
-    __syncthreads();
-    for (int i = tid; i < K * P; i += F32_THREADS) {
-        const int k = i / P, p = i - k * P;
-        double v = 0.0;
-        for (int w = 0; w < NW; ++w) v += wsum[w][k * P + p];
-        part[(int64_t)k * L.pitch + p] = v;
-    }
-    if (tid == 0) {
-        double v = 0.0;
-        for (int w = 0; w < NW; ++w) v += wsum[w][F32_KMAX * P];
-        part[(int64_t)K * L.pitch] = v;
-    }
-
-    // ---- last CTA reduces the partials in CTA order ----
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const int tk = atomicAdd(const_cast<int*>(&ctrl[BGMM_CTRL_PASS_TICKET]), 1);
-        is_last = (tk == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    double* out = a.state + L.stats;
-    const double* ws = a.workspace;
-    for (int64_t o = tid; o < len; o += F32_THREADS) {
-        double s0 = 0.0;
-        for (int b = 0; b < (int)gridDim.x; ++b) s0 += __ldcg(&ws[(int64_t)b * len + o]);
-        if (o == (int64_t)K * L.pitch + 1) s0 = (double)a.n;
-        if (o == (int64_t)K * L.pitch + 2) { out[o] = 0.0; continue; }      // format marker: moments about the centre
-        out[o] = a.accumulate ? out[o] + s0 : s0;
-    }
-    if (tid == 0) ctrl[BGMM_CTRL_PASS_TICKET] = 0;
-    const CommDesc* cd = a.no_publish ? nullptr : comm_of(ctrl);
-    if (cd != nullptr) {                  // row-sharded fit: hand the reduced statistics to the peers (bgmm_comm.cu)
-        __threadfence();
-        __syncthreads();
-        publish_block(a.state, L, cd);
-    }
+    f32_epilogue<P>(a, L, ctrl, wsum, is_last);
     (void)red;
+}
+
+// ---- D = 2, feature-map form, loop instantiation: two samples per thread in packed f32x2 arithmetic ----
+// BASELINE C3's shape.  The scalar kernel above issues ~155 instructions per sample; here everything except the E-step dot
+// products (whose coefficients are per-component scalars held in registers) works on PAIRS of consecutive samples in
+// 64-bit registers: phi, the softmax subtraction / sum / entropy dot product, r and the 48 statistics accumulators (FFMA2 /
+// FADD2 / FMUL2: ~107 instructions per sample).  Launched before pass_f32_kernel<2, false>, which returns at once when this
+// kernel took the pass (and does the pass itself when the conditioning criterion asks for the whitened form).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+__global__ void __launch_bounds__(F32_THREADS, 2) pass_f32x2_kernel(const PassArgs a, const Layout L) {
+    constexpr int D = 2, P = 6, NW = F32_THREADS / 32;
+    __shared__ float cf[F32_KMAX][P];
+    __shared__ double wsum[NW][F32_KMAX * P + 1];
+    __shared__ int is_last;
+    const int K = L.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    volatile int* ctrl = reinterpret_cast<volatile int*>(a.state + L.ctrl);
+    if (pass_skip(ctrl, a.force, a.ignore_robust)) return;
+    if (!(ctrl[BGMM_CTRL_CRIT] <= F32_FEAT_CRIT)) return;       // whitened form: the scalar kernel does this pass
+    const double* Pc = a.state + L.params[ctrl[BGMM_CTRL_CUR]];
+    const float* __restrict__ x = static_cast<const float*>(a.x);
+    if (tid < F32_KMAX * P) {
+        const int k = tid / P, p = tid - k * P;
+        // base-2 feature-map coefficients [const, x, y, xx, xy, yy]; padded components sit at -1e30 (r == 0 exactly)
+        cf[k][p] = k < K ? (float)(Pc[L.p_coef + (int64_t)k * L.pitch + p] * 1.4426950408889634074) : (p == 0 ? -1.0e30f : 0.f);
+    }
+    for (int i = lane; i < F32_KMAX * P + 1; i += 32) wsum[warp][i] = 0.0;
+    __syncthreads();
+    // the E-step stays scalar: (coefficient, coefficient) pairs for a packed E-step would need 96 more registers; measured
+    // with them the compiler rebuilds the pairs per use and the kernel is 11 % slower
+    float c[F32_KMAX][P];
+#pragma unroll
+    for (int k = 0; k < F32_KMAX; ++k)
+#pragma unroll
+        for (int p = 0; p < P; ++p) c[k][p] = cf[k][p];
+    f32x2 acc[F32_KMAX][P];
+#pragma unroll
+    for (int k = 0; k < F32_KMAX; ++k)
+#pragma unroll
+        for (int p = 0; p < P; ++p) acc[k][p] = 0ull;
+    float ent = 0.f;
+    int pending = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int k = 0; k < F32_KMAX; ++k)
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                float lo, hi;
+                upk(acc[k][p], lo, hi);
+                float v = lo + hi;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) wsum[warp][k * P + p] += (double)v;
+                acc[k][p] = 0ull;
+            }
+        float v = ent;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) wsum[warp][F32_KMAX * P] += (double)v;
+        ent = 0.f;
+        pending = 0;
+    };
+    // a thread owns the samples 2 q and 2 q + 1 of pair q: one 16-byte load, a warp reads 512 contiguous bytes
+    const int64_t npairs = (a.n + 1) >> 1, stride = (int64_t)gridDim.x * F32_THREADS;
+    auto load_pair = [&](int64_t q) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (2 * q + 1 < a.n) v = __ldg(reinterpret_cast<const float4*>(x) + q);
+        else if (2 * q < a.n) { const float2 h = __ldg(reinterpret_cast<const float2*>(x) + 2 * q); v.x = h.x; v.y = h.y; }
+        return v;
+    };
+    const int64_t q0 = (int64_t)blockIdx.x * F32_THREADS + warp * 32 + lane;
+    float4 xn1 = load_pair(q0), xn2 = load_pair(q0 + stride);
+    for (int64_t base = (int64_t)blockIdx.x * F32_THREADS + warp * 32; base < npairs; base += stride) {
+        const int64_t q = base + lane;
+        const bool va = 2 * q < a.n, vb = 2 * q + 1 < a.n;
+        const float4 xv = xn1;
+        xn1 = xn2;
+        xn2 = load_pair(q + 2 * stride);
+        if (q + 6 * stride < npairs) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (q + 6 * stride) * 4));
+        const f32x2 X = pk(xv.x, xv.z), Y = pk(xv.y, xv.w);
+        const f32x2 XX = mul2(X, X), XY = mul2(X, Y), YY = mul2(Y, Y);
+        float xxa, xxb, xya, xyb, yya, yyb;
+        upk(XX, xxa, xxb); upk(XY, xya, xyb); upk(YY, yya, yyb);
+        float la[F32_KMAX], lb[F32_KMAX];
+        float mxa = -3.0e38f, mxb = -3.0e38f;
+#pragma unroll
+        for (int k = 0; k < F32_KMAX; ++k) {
+            float u = fmaf(c[k][1], xv.x, c[k][0]), w = fmaf(c[k][1], xv.z, c[k][0]);
+            u = fmaf(c[k][2], xv.y, u);  w = fmaf(c[k][2], xv.w, w);
+            u = fmaf(c[k][3], xxa, u);   w = fmaf(c[k][3], xxb, w);
+            u = fmaf(c[k][4], xya, u);   w = fmaf(c[k][4], xyb, w);
+            u = fmaf(c[k][5], yya, u);   w = fmaf(c[k][5], yyb, w);
+            la[k] = u; lb[k] = w;
+            mxa = fmaxf(mxa, u); mxb = fmaxf(mxb, w);
+        }
+        const f32x2 NMX = pk(-mxa, -mxb);
+        f32x2 E[F32_KMAX], S = 0ull, DOT = 0ull;
+#pragma unroll
+        for (int k = 0; k < F32_KMAX; ++k) {
+            const f32x2 Z = add2(pk(la[k], lb[k]), NMX);        // finite: padded components sit at -1e30
+            float za, zb;
+            upk(Z, za, zb);
+            E[k] = pk(ex2_approx(za), ex2_approx(zb));
+            S = add2(S, E[k]);
+            DOT = fma2(E[k], Z, DOT);
+        }
+        float sa, sb, da, db;
+        upk(S, sa, sb); upk(DOT, da, db);
+        const float inva = va ? rcp_approx(sa) : 0.f, invb = vb ? rcp_approx(sb) : 0.f;       // 1 <= s <= K
+        if (va) ent += 0.693147180559945309f * (da * inva - lg2_approx(sa));
+        if (vb) ent += 0.693147180559945309f * (db * invb - lg2_approx(sb));
+        const f32x2 INV = pk(inva, invb);
+#pragma unroll
+        for (int k = 0; k < F32_KMAX; ++k) {
+            const f32x2 R = mul2(E[k], INV);
+            acc[k][0] = add2(acc[k][0], R);
+            acc[k][1] = fma2(R, X, acc[k][1]);
+            acc[k][2] = fma2(R, Y, acc[k][2]);
+            acc[k][3] = fma2(R, XX, acc[k][3]);
+            acc[k][4] = fma2(R, XY, acc[k][4]);
+            acc[k][5] = fma2(R, YY, acc[k][5]);
+        }
+        if (++pending == F32_FLUSH / 2) flush();
+    }
+    flush();
+    __syncthreads();
+    f32_epilogue<P>(a, L, ctrl, wsum, is_last);
+    (void)D;
 }
 
 bool f32_supported(int K, int D, int dtype) { return dtype == BGMM_F32 && D >= 1 && D <= 3 && K <= F32_KMAX; }
@@ -333,7 +478,21 @@ int launch_pass_f32(const PassArgs& a, int K, int D, int dtype, cudaStream_t str
     }
     const Layout L = make_layout(K, D, 1);
     const bool out = a.r_out != nullptr || a.lnrho_out != nullptr || a.argmax_out != nullptr;
-#define BGMM_F32_CASE(d, o) if (D == d && out == o) pass_f32_kernel<d, o><<<f32_grid<d, o>(a.n), F32_THREADS, 0, stream>>>(a, L);
+    // C3's shape in the loop: the packed two-samples-per-thread kernel first; the scalar kernel then returns at once unless the
+    // conditioning criterion asked for the whitened form (BGMM_F32_PACKED=0 keeps the scalar kernel alone)
+    static const int packed_on = [] { const char* e = getenv("BGMM_F32_PACKED"); return (e == nullptr || atoi(e) != 0) ? 1 : 0; }();
+    const int packed = (D == 2 && !out && packed_on) ? 1 : 0;
+    if (packed) {
+        int dev = 0, sms = 148, occ = 1;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pass_f32x2_kernel, F32_THREADS, 0);
+        if (occ < 1) occ = 1;
+        const int64_t want = ((a.n + 1) / 2 + F32_THREADS - 1) / F32_THREADS;
+        int64_t cap = (int64_t)sms * occ;
+        if (cap > 1024) cap = 1024;
+        pass_f32x2_kernel<<<(int)(want < 1 ? 1 : (want < cap ? want : cap)), F32_THREADS, 0, stream>>>(a, L);
+    }
+#define BGMM_F32_CASE(d, o) if (D == d && out == o) pass_f32_kernel<d, o><<<f32_grid<d, o>(a.n), F32_THREADS, 0, stream>>>(a, L, packed);
     BGMM_F32_CASE(1, false) BGMM_F32_CASE(1, true) BGMM_F32_CASE(2, false) BGMM_F32_CASE(2, true)
     BGMM_F32_CASE(3, false) BGMM_F32_CASE(3, true)
 #undef BGMM_F32_CASE
