@@ -246,13 +246,19 @@ def test_larger_shapes_against_oracle_and_elbo_monotone(shape, variant, monkeypa
     assert np.isclose(m.ns.sum(), n, rtol=1e-12)
 
 
-@pytest.mark.parametrize("shape", [(60000, 2, 8), (30000, 3, 5), (20000, 1, 3), (4097, 2, 2)])
-def test_fp32_mode_against_fp64_oracle(shape):
+@pytest.mark.parametrize("packed", ["1", "0"])
+@pytest.mark.parametrize("shape", [(60000, 2, 8), (30000, 3, 5), (20000, 1, 3), (4097, 2, 2), (12345, 2, 5)])
+def test_fp32_mode_against_fp64_oracle(shape, packed, monkeypatch):
     """precision='float32' (BASELINE config C3's mode): X is rounded to fp32 once and the SAME rounded X is fed to the
-    fp64 oracle (the reference promotes float32 input to float64, :780); bar 1e-4 relative, assignments exact."""
+    fp64 oracle (the reference promotes float32 input to float64, :780); bar 1e-4 relative, assignments exact.
+    packed = 1: D = 2 runs the two-samples-per-thread f32x2 kernel in the loop (odd N: a half-filled last pair);
+    packed = 0: the scalar kernel alone."""
     from bayesml_b200 import _lib, gaussianmixture
     from oracle.gmm_vb_oracle import OracleGMM, fit
     n, d, k = shape
+    if packed == "0" and d != 2:
+        pytest.skip("the packed kernel exists for D = 2 only")
+    monkeypatch.setenv("BGMM_F32_PACKED", packed)
     assert _lib.load().bgmm_pass_supported(k, d, _lib.F32, _lib.PASS_F32)
     rng = np.random.default_rng(n + d + k)
     mu = rng.normal(0, 5.0, size=(k, d))
