@@ -356,7 +356,9 @@ def test_fp32_mode_on_tensor_cores_against_fp64_oracle(shape):
     assert np.array_equal(np.argmax(m.r_vecs, axis=1)[clear], np.argmax(o.r_vecs, axis=1)[clear])
 
 
-@pytest.mark.parametrize("shape", [(20000, 16, 32), (30000, 8, 6), (10000, 5, 3), (9000, 20, 12), (7001, 12, 40)])
+# the last four: fewer rows than one 128-sample tile / 64-sample sub-tile, a single row, one row more than a tile
+@pytest.mark.parametrize("shape", [(20000, 16, 32), (30000, 8, 6), (10000, 5, 3), (9000, 20, 12), (7001, 12, 40),
+                                   (63, 16, 4), (1, 4, 3), (129, 8, 33), (50, 21, 2)])
 def test_fp32_tensor_core_pass_from_identical_state(shape):
     """One E-step + statistics sweep of the tcgen05 kernels from a GIVEN parameter set against the fp64 oracle's E-step from the
     same set on the same fp32-rounded X (north_star: 'identical inputs and identical initial state'): ln rho, r, N_k and the
