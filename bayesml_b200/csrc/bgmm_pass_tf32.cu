@@ -528,25 +528,34 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
     if (warp == TM_BLOCK / 32 - 1) {
         // =========================== ISSUER: one thread feeds the tensor core and nothing else ===========================
         int since_flush = 0;
+        // descriptor low words (address field | LBO) of stage 0, per part and k-step; the high word (SBO = 1024 B, version,
+        // SWIZZLE_128B) is constant and the other stage is a constant offset in the address field
+        uint32_t blo[2][TM_SUB / 8];
+#pragma unroll
+        for (int pt = 0; pt < 2; ++pt)
+#pragma unroll
+            for (int ks = 0; ks < TM_SUB / 8; ++ks) {
+                const uint32_t addr = tc::smem_u32(Bs + (size_t)pt * bpart) + (uint32_t)((ks >> 2) * (NF * 128) + (ks & 3) * 32);
+                blo[pt][ks] = ((addr >> 4) & 0x3FFFu) | 0x10000u;
+            }
+        const uint32_t bhi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t stage_step = nst == 2 ? (uint32_t)((2 * bpart * 4) >> 4) : 0u;
         for (int64_t t = 0; t < my_sub; ++t) {
             if (since_flush == TF_FLUSH) since_flush = 0;       // the staging warps flushed before they signalled afull
             mbar_wait(&afull[t & 1], (uint32_t)((t >> 1) & 1));
             mbar_wait(&bfull[t & 1], (uint32_t)((t >> 1) & 1));
             tc::fence_after_sync();
             if (lane == 0) {
-                const uint32_t bh = tc::smem_u32(Bs + (size_t)(nst == 2 ? (t & 1) : 0) * 2 * bpart), bl = bh + 4 * (uint32_t)bpart;
-                const uint32_t ah = tbase + 128 * (uint32_t)(t & 1), al = ah + 64;
-                uint32_t accum = since_flush > 0 ? 1u : 0u;
+                const uint32_t soff = (t & 1) ? stage_step : 0u;
+                const uint32_t ah = tbase + 128 * (uint32_t)(t & 1), al = ah + 64, dt = tbase + 256;
+                tc::mma_tf32_ts_w(dt, ah, blo[0][0] + soff, bhi, idesc, since_flush > 0 ? 1u : 0u);
 #pragma unroll
-                for (int sp = 0; sp < 3; ++sp) {                // hi.hi, hi.lo, lo.hi
-                    if (two && sp == 2) break;
-                    const uint32_t aa = sp == 2 ? al : ah, bb = sp == 1 ? bl : bh;
+                for (int ks = 1; ks < TM_SUB / 8; ++ks) tc::mma_tf32_ts_w(dt, ah + 8 * ks, blo[0][ks] + soff, bhi, idesc, 1u);
 #pragma unroll
-                    for (int ks = 0; ks < TM_SUB / 8; ++ks) {
-                        tc::mma_tf32_ts(tbase + 256, aa + 8 * ks,
-                                        tc::make_smem_desc_sw128(bb + (ks >> 2) * (NF * 128) + (ks & 3) * 32, 1024), idesc, accum);
-                        accum = 1u;
-                    }
+                for (int ks = 0; ks < TM_SUB / 8; ++ks) tc::mma_tf32_ts_w(dt, ah + 8 * ks, blo[1][ks] + soff, bhi, idesc, 1u);   // hi.lo
+                if (!two) {
+#pragma unroll
+                    for (int ks = 0; ks < TM_SUB / 8; ++ks) tc::mma_tf32_ts_w(dt, al + 8 * ks, blo[0][ks] + soff, bhi, idesc, 1u);   // lo.hi
                 }
                 tc::mma_commit(&mdone[t & 1]);
             }

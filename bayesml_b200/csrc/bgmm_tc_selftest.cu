@@ -9,12 +9,13 @@ namespace bgmm {
 
 __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                           float* __restrict__ Dout, const int N, const int Kd,
-                                                          const int a_mn, const int b_mn) {
+                                                          const int a_mn, const int b_mn_arg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_slot;
     float* As = reinterpret_cast<float*>(smem_raw);            // 128 x Kd
     float* Bs = As + 128 * Kd;                                 // N x Kd
+    const int b_mn = b_mn_arg >= 4 ? 0 : b_mn_arg;             // 4 / 5: the latency / throughput probes, K-major no-swizzle B
     const bool b_sw = b_mn == 3;                               // B K-major in the 128-byte-swizzle layout (Kd % 32 == 0)
     if (b_sw) Bs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Bs) + 1023) & ~uintptr_t(1023));
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -74,6 +75,30 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(const float* __restric
     }
     mbar_wait(&mbar, 0);
     tc::fence_after_sync();
+    if (a_mn == 2 && b_mn_arg >= 4) {
+        // latency probe (tests/test_gpu_tc.py::test_tcgen05_round_trip_latency): ONE thread issues one MMA, commits and waits for
+        // the mbarrier, 256 times back to back; Dout[0] = cycles per round trip (issue -> complete -> commit -> arrival seen)
+        if (tid == 0) {
+            const uint32_t idesc = tc::make_idesc_tf32(128, N, 0, 0);
+            const uint64_t bd = tc::make_smem_desc(tc::smem_u32(Bs), 4 * 32, 4 * (Kd / 4) * 32);
+            uint32_t phase = 1;
+            const long long t0 = clock64();
+            const int per_commit = b_mn_arg == 5 ? 16 : 1;     // 5: sixteen MMAs back to back per commit (throughput)
+            for (int it = 0; it < 256; ++it) {
+                for (int j = 0; j < per_commit; ++j) tc::mma_tf32_ts(tbase, tbase + 256, bd, idesc, 1u);
+                tc::mma_commit(&mbar);
+                mbar_wait(&mbar, phase);
+                phase ^= 1u;
+            }
+            const long long t1 = clock64();
+            Dout[0] = (float)((t1 - t0) / 256.0);
+        }
+        __syncthreads();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tc::tmem_dealloc<512>(tbase);
+        return;
+    }
     for (int c0 = 0; c0 < N; c0 += 16) {
         float v[16];
         tc::tmem_ld16(tbase + ((uint32_t)(32 * warp) << 16) + c0, v);

@@ -34,3 +34,23 @@ def test_tcgen05_tf32_matmul(n, kd, a_mn, b_mn):
     want = _tf32(a).astype(np.float64) @ _tf32(b).astype(np.float64).T       # the tensor core reads the top 19 bits
     got = dd.cpu().numpy()
     assert np.allclose(got, want, rtol=0, atol=2e-5 * np.sqrt(kd)), np.max(np.abs(got - want))
+
+
+def test_tcgen05_round_trip_latency():
+    """Issue -> execute -> tcgen05.commit -> mbarrier arrival observed by the issuing thread, one 128 x N x 8 tf32 MMA at a time:
+    the latency that bounds a pipeline with few stages in flight.  Reported, and sanity-bounded."""
+    import torch
+    from bayesml_b200 import _lib
+    lib = _lib.load()
+    for mode, what in ((4, "round trip, one MMA per commit"), (5, "sixteen MMAs per commit, cycles per group")):
+        out = {}
+        for n in (16, 32, 64, 96, 128, 144, 160, 192, 224, 256):
+            a = torch.zeros((128, 8), dtype=torch.float32, device="cuda")
+            b = torch.zeros((n, 8), dtype=torch.float32, device="cuda")
+            d = torch.zeros((128, n), dtype=torch.float32, device="cuda")
+            _lib.check(lib.bgmm_tc_selftest(a.data_ptr(), b.data_ptr(), d.data_ptr(), n, 8, 2, mode,
+                                            torch.cuda.current_stream().cuda_stream), "bgmm_tc_selftest")
+            torch.cuda.synchronize()
+            out[n] = float(d[0, 0].item())
+        print(f"tcgen05 kind::tf32 M=128 K=8, A in tensor memory ({what}):", out)
+        assert all(50.0 < v < 50000.0 for v in out.values()), out
