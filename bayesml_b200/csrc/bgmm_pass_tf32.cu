@@ -466,7 +466,9 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
     // [nst stages][2 parts][2 k-atoms of 32 samples][NF / 8 row groups][8 features][128 bytes, chunks swizzled]
     float* Bs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw_m) + 1023) & ~uintptr_t(1023));
     float* xs = Bs + 2 * nst * bpart;                                // [64][D + 2]: x', 1, 0   (run-time D only)
-    unsigned short* ftab = reinterpret_cast<unsigned short*>(xs + (DT > 0 ? 0 : TM_SUB * (D + 2)));   // [P] (run-time D only)
+    // compile-time D: xs = two buffers of 32 row PAIRS, pitch 2 D + 4 floats (16-byte aligned, conflict-free for LDS.128)
+    constexpr int XPP = DT > 0 ? 2 * DT + 4 : 0;
+    unsigned short* ftab = reinterpret_cast<unsigned short*>(xs + (DT > 0 ? 2 * 32 * XPP : TM_SUB * (D + 2)));   // [P] (run-time D only)
     uint64_t* mbar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(ftab + (DT > 0 ? 0 : ((P + 7) & ~7))) + 15) & ~uintptr_t(15));
     uint64_t* mdone = mbar;                                    // [2] MMAs of sub-tile parity b complete (B stage + A buffer free)
     uint64_t* bfull = mbar + 2;                                // [2] B stage b written (one arrival per generator warp: 256
@@ -572,36 +574,40 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
 #pragma unroll
         for (int r = 0; r < 8; ++r) xo[r] = (s_loc >> 5) * (NF * 32) + (((((s_loc & 31) >> 2) ^ r)) << 2) + (s_loc & 3);
         const int o0 = (s_loc >> 5) * (NF * 32) + gw * 32 + (((((s_loc & 31) >> 2) ^ gw)) << 2) + (s_loc & 3);
+        // compile-time D (a multiple of 4): the 64 x rows of a sub-tile (256 D contiguous bytes) come in by cp.async one whole
+        // sub-tile ahead — global loads issued at the top of the iteration that consumes them were 60 % of the generators'
+        // stall samples, and an L1 prefetch did not remove them.  Chunk c (16 bytes) of the tile goes to pair c / (D/2).
+        auto fetch_x = [&](int64_t tt) {
+            if (DT > 0) {
+                constexpr int CPP = DT > 0 ? DT / 2 : 1;            // 16-byte chunks per row pair
+                float* dstb = xs + (size_t)(tt & 1) * 32 * XPP;
+                const int64_t row0 = (blockIdx.x + tt * gridDim.x) * TM_SUB;
+                for (int c = gtid; c < 32 * CPP; c += TM_GEN) {
+                    const int pr = c / CPP, w = c - pr * CPP;
+                    const int64_t e0 = row0 * DT + (int64_t)c * 4;              // first float of the chunk
+                    const int nbytes = (tt < my_sub && e0 < a.n * DT) ? 16 : 0;  // rows past the end: zero fill
+                    const float* src = nbytes ? x + e0 : x;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dstb + pr * XPP + 4 * w)),
+                                 "l"(src), "r"(nbytes) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+        };
+        fetch_x(0);
         for (int64_t t = 0; t < my_sub; ++t) {
             const int64_t sb = blockIdx.x + t * gridDim.x;
-            const int64_t row = sb * TM_SUB + s_loc;
             float xa[DT > 0 ? DT : 1], xb[DT > 0 ? DT : 1];
-            if (DT > 0 && gw == (int)(t & 7)) {
-                // the x rows of the NEXT sub-tile into L1 (one warp covers the 64 rows): the loads below were 60 % of the
-                // generators' stall samples (long scoreboard) when they went to L2 / HBM
-                const char* nx = reinterpret_cast<const char*>(x + (sb + gridDim.x) * TM_SUB * DT);
-                const char* endx = reinterpret_cast<const char*>(x + a.n * DT);
-                for (int o = 128 * lane; o < TM_SUB * DT * 4; o += 128 * 32)
-                    if (t + 1 < my_sub && nx + o < endx) asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + o));
-            }
             if (DT > 0) {
-                const bool va = row < a.n, vb = row + 1 < a.n;
-                if (DT % 4 == 0) {
-                    const float4* pa = reinterpret_cast<const float4*>(x + row * DT);
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");          // every generator thread's chunk of tile t has landed
+                const float4* pp = reinterpret_cast<const float4*>(xs + (size_t)(t & 1) * 32 * XPP + lane * XPP);
 #pragma unroll
-                    for (int i = 0; i < DT / 4; ++i) {
-                        const float4 fa = va ? __ldg(pa + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 fb = vb ? __ldg(pa + DT / 4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        xa[4 * i] = fa.x; xa[4 * i + 1] = fa.y; xa[4 * i + 2] = fa.z; xa[4 * i + 3] = fa.w;
-                        xb[4 * i] = fb.x; xb[4 * i + 1] = fb.y; xb[4 * i + 2] = fb.z; xb[4 * i + 3] = fb.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < DT; ++i) {
-                        xa[i] = va ? __ldg(x + row * DT + i) : 0.f;
-                        xb[i] = vb ? __ldg(x + (row + 1) * DT + i) : 0.f;
-                    }
+                for (int i = 0; i < DT / 4; ++i) {
+                    const float4 fa = pp[i], fb = pp[DT / 4 + i];
+                    xa[4 * i] = fa.x; xa[4 * i + 1] = fa.y; xa[4 * i + 2] = fa.z; xa[4 * i + 3] = fa.w;
+                    xb[4 * i] = fb.x; xb[4 * i + 1] = fb.y; xb[4 * i + 2] = fb.z; xb[4 * i + 3] = fb.w;
                 }
+                fetch_x(t + 1);                                         // the other buffer: last read in iteration t - 1
             }
             // the MMAs that read this stage are done: sub-tile t - 2 with two stages, t - 1 with one (large feature counts)
             if (nst == 2) { if (t >= 2) mbar_wait(&mdone[t & 1], (uint32_t)(((t >> 1) - 1) & 1)); }
@@ -756,7 +762,7 @@ static Tf32MPlan plan_tf32_m(int K, int D) {
     const int P = feat_count(D);
     m.NF = (P + 15) & ~15;
     auto bytes = [&](int nst) {
-        return sizeof(float) * ((size_t)2 * nst * m.NF * TM_SUB + (size_t)TM_SUB * (D + 2)) +
+        return sizeof(float) * ((size_t)2 * nst * m.NF * TM_SUB + (size_t)TM_SUB * (D + 2) + 2 * 32 * (2 * 32 + 4)) +
                sizeof(unsigned short) * ((P + 7) & ~7) + 96 + 1024;
     };
     m.nst = bytes(2) <= 220 * 1024 ? 2 : 1;                    // two Phi stages when they fit (P <= ~190), else one
