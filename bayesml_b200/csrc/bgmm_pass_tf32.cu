@@ -430,14 +430,27 @@ constexpr int TM_BLOCK = TM_GEN + TM_STG + 32;   // warps 0-15 with (w & 3) >= 2
 // A generator warp owns the features p = FG (mod 8) — one row of every swizzled 8-row atom, so the XOR of the chunk index is
 // a per-thread constant — and a lane two consecutive samples: 8-byte stores, 4 instructions per (sample, feature).
 // o0 = float offset of (row FG of atom row-group 0, this lane's sample pair).
+// explicit shared-space accesses: the staging pointers come out of a 1024-byte round-up of the dynamic shared memory base,
+// through which the compiler loses the address space and emits generic LD / ST (4.5 % of the executed instructions)
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float a) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
+// Bh / Bl: 32-bit shared addresses of the hi / lo staging tiles
 template <int DT, int FG>
 __device__ __forceinline__ void gen_features(const float (&xa)[DT > 0 ? DT : 1], const float (&xb)[DT > 0 ? DT : 1],
-                                             float* __restrict__ Bh, float* __restrict__ Bl, const int o0) {
+                                             const uint32_t Bh, const uint32_t Bl, const int o0) {
     auto put = [&](int p, float va, float vb) {
         const float ha = tc::tf32_trunc(va), hb = tc::tf32_trunc(vb);
-        const int o = (p >> 3) * 256 + o0;
-        *reinterpret_cast<float2*>(Bh + o) = make_float2(ha, hb);
-        *reinterpret_cast<float2*>(Bl + o) = make_float2(va - ha, vb - hb);
+        const uint32_t o = 4u * (uint32_t)((p >> 3) * 256 + o0);
+        sts64(Bh + o, ha, hb);
+        sts64(Bl + o, va - ha, vb - hb);
     };
     if (FG == 0) put(0, 1.0f, 1.0f);
 #pragma unroll
@@ -600,10 +613,10 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
             if (DT > 0) {
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
                 asm volatile("bar.sync 1, 256;" ::: "memory");          // every generator thread's chunk of tile t has landed
-                const float4* pp = reinterpret_cast<const float4*>(xs + (size_t)(t & 1) * 32 * XPP + lane * XPP);
+                const uint32_t pp = tc::smem_u32(xs + (size_t)(t & 1) * 32 * XPP + lane * XPP);
 #pragma unroll
                 for (int i = 0; i < DT / 4; ++i) {
-                    const float4 fa = pp[i], fb = pp[DT / 4 + i];
+                    const float4 fa = lds128(pp + 16 * i), fb = lds128(pp + 16 * (DT / 4 + i));
                     xa[4 * i] = fa.x; xa[4 * i + 1] = fa.y; xa[4 * i + 2] = fa.z; xa[4 * i + 3] = fa.w;
                     xb[4 * i] = fb.x; xb[4 * i + 1] = fb.y; xb[4 * i + 2] = fb.z; xb[4 * i + 3] = fb.w;
                 }
@@ -612,8 +625,7 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
             // the MMAs that read this stage are done: sub-tile t - 2 with two stages, t - 1 with one (large feature counts)
             if (nst == 2) { if (t >= 2) mbar_wait(&mdone[t & 1], (uint32_t)(((t >> 1) - 1) & 1)); }
             else if (t >= 1) mbar_wait(&mdone[(t - 1) & 1], (uint32_t)(((t - 1) >> 1) & 1));
-            float* Bh = Bs + (size_t)(nst == 2 ? (t & 1) : 0) * 2 * bpart;
-            float* Bl = Bh + bpart;
+            const uint32_t Bh = tc::smem_u32(Bs + (size_t)(nst == 2 ? (t & 1) : 0) * 2 * bpart), Bl = Bh + 4u * (uint32_t)bpart;
             if (DT > 0) {
                 switch (gw) {                     // warp-uniform
                     case 0: gen_features<DT, 0>(xa, xb, Bh, Bl, o0); break;
@@ -638,9 +650,9 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
                     const unsigned int code = ftab[p];
                     const float v = xr[code >> 8] * xr[code & 0xFF];
                     const float h = tc::tf32_trunc(v);
-                    const int o = (p >> 3) * 256 + (p & 7) * 32 + xo[p & 7];
-                    Bh[o] = h;
-                    Bl[o] = v - h;
+                    const uint32_t o = 4u * (uint32_t)((p >> 3) * 256 + (p & 7) * 32 + xo[p & 7]);
+                    sts32(Bh + o, h);
+                    sts32(Bl + o, v - h);
                 }
             }
             tc::fence_proxy_async();
