@@ -276,11 +276,32 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
                     tc::fence_after_sync();
                     const uint32_t t0 = tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(g & 1) * TF_NMAX + 64 * gq;
                     if (gq * CPB < cpc && ch * cpc + gq * CPB < KP && dbg != 1) {   // uniform per warp: this 64-column batch holds components
-                        uint32_t v[4][16];
+                        if constexpr (DP == 16) {
+                            // two 32-column halves: 32 live accumulator registers instead of 64 (the 120-register cap of a
+                            // 544-thread CTA made the one-batch form spill)
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) tc::tmem_ld16_async(t0 + 16 * h, v[h]);
-                        tc::tmem_wait_ld();
-                        if constexpr (DP >= 16) {
+                            for (int hb = 0; hb < 2; ++hb) {
+                                uint32_t v[2][16];
+                                tc::tmem_ld16_async(t0 + 32 * hb, v[0]);
+                                tc::tmem_ld16_async(t0 + 32 * hb + 16, v[1]);
+                                tc::tmem_wait_ld();
+#pragma unroll
+                                for (int u = 0; u < 2; ++u) {
+                                    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                                    for (int j = 0; j < 16; j += 2) {
+                                        const float y0 = __uint_as_float(v[u][j]), y1 = __uint_as_float(v[u][j + 1]);
+                                        q0 = fmaf(y0, y0, q0);
+                                        q1 = fmaf(y1, y1, q1);
+                                    }
+                                    l2[ch * CPB + 2 * hb + u] = a2s[ch * cpc + gq * CPB + 2 * hb + u] - (q0 + q1);
+                                }
+                            }
+                        } else if constexpr (DP >= 16) {
+                            uint32_t v[4][16];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) tc::tmem_ld16_async(t0 + 16 * h, v[h]);
+                            tc::tmem_wait_ld();
 #pragma unroll
                             for (int u = 0; u < CPB; ++u) {
                                 float q0 = 0.f, q1 = 0.f;
@@ -296,6 +317,10 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
                                 l2[ch * CPB + u] = a2s[ch * cpc + gq * CPB + u] - (q0 + q1);
                             }
                         } else {
+                            uint32_t v[4][16];
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) tc::tmem_ld16_async(t0 + 16 * h, v[h]);
+                            tc::tmem_wait_ld();
                             constexpr int PER = 16 / DP;         // components per 16-column load
 #pragma unroll
                             for (int h = 0; h < 4; ++h)
