@@ -181,10 +181,15 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
 #pragma unroll
         for (int u = 0; u < NKC; ++u) {
             const int kc = 4 * u + gq;
+            if (valid && (D & 3) == 0 && 4 * kc + 3 < D) {         // a whole 16-byte chunk of the row: one load
+                const float4 f = __ldg(reinterpret_cast<const float4*>(x + row * D) + kc);
+                xpre[u][0] = f.x; xpre[u][1] = f.y; xpre[u][2] = f.z; xpre[u][3] = f.w;
+            } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = 4 * kc + q;
-                xpre[u][q] = (valid && i < D) ? __ldg(x + row * D + i) : ((valid && i == D) ? 1.0f : 0.0f);
+                for (int q = 0; q < 4; ++q) {
+                    const int i = 4 * kc + q;
+                    xpre[u][q] = (valid && i < D) ? __ldg(x + row * D + i) : ((valid && i == D) ? 1.0f : 0.0f);
+                }
             }
         }
     };
@@ -377,10 +382,13 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
 #pragma unroll
                     for (int u = 0; u < CPB; ++u) {
                         const float rv = l2[ch * CPB + u] * inv;
-                        if (c0 + u < KP) rst[rowt * RSP + c0 + u] = rv;
+                        if (CPB != 4 && c0 + u < KP) rst[rowt * RSP + c0 + u] = rv;
                         if (OUT && a.r_out != nullptr && valid && c0 + u < K) a.r_out[row * K + c0 + u] = (double)rv;
                         l2[ch * CPB + u] = rv;
                     }
+                    if (CPB == 4 && c0 < KP)                     // KP, c0 and the pitch are multiples of 4: one 16-byte store
+                        *reinterpret_cast<float4*>(rst + rowt * RSP + c0) =
+                            make_float4(l2[ch * CPB], l2[ch * CPB + 1], l2[ch * CPB + 2], l2[ch * CPB + 3]);
                 }
             }
             if (OUT && a.argmax_out != nullptr) {                // final pass only: arg max over the four column groups
