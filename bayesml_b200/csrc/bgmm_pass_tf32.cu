@@ -249,6 +249,8 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
     } else {
         // =========================== EPILOGUE / STAGING WARPS ===========================
         const int qbar = 1 + (warp & 3);                         // named barrier of the four warps that share this row quarter
+        const int st_t128 = (tid & 31) + 32 * gq, st_q4 = KP / 4;
+        const int st_rr0 = st_t128 / st_q4, st_c40 = st_t128 - st_rr0 * st_q4, st_drr = 128 / st_q4, st_dc4 = 128 - st_drr * st_q4;
         if (my_tiles > 0) {
             fetch_tile(0);
             stage_tile(0);
@@ -349,19 +351,26 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
             // ---- softmax over k: four threads per row (one per column group), combined through shared memory; only the
             //      four warps that share the row quarter synchronise (named barrier, 128 threads) ----
             float mx = -3.0e38f;
+            // slots of chunks this launch does not have (ch >= nchunks, uniform) are skipped, not carried as -1e30 padding: at
+            // C2 that is half of the exponentials
 #pragma unroll
-            for (int c = 0; c < NL; ++c) mx = fmaxf(mx, l2[c]);
+            for (int ch = 0; ch < NCHMAX; ++ch)
+                if (ch < nchunks) {
+#pragma unroll
+                    for (int u = 0; u < CPB; ++u) mx = fmaxf(mx, l2[ch * CPB + u]);
+                }
             xch[gq * TF_TILE + rowt] = mx;
             asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
             mx = fmaxf(fmaxf(xch[rowt], xch[TF_TILE + rowt]), fmaxf(xch[2 * TF_TILE + rowt], xch[3 * TF_TILE + rowt]));
             float s = 0.f, dot = 0.f;
 #pragma unroll
             for (int c = 0; c < NL; ++c) {
+                if ((c / CPB) >= nchunks) { l2[c] = 0.f; continue; }   // uniform
                 const float z = l2[c] - mx;
                 const float e = ex2f(z);                         // padded slots: z ~ -1e30 -> 0
                 if (OUT && a.lnrho_out != nullptr && valid) {
                     const int comp = (c / CPB) * cpc + gq * CPB + (c % CPB);
-                    if ((c / CPB) < nchunks && gq * CPB < cpc && comp < K) a.lnrho_out[row * K + comp] = (double)l2[c] * 0.693147180559945309417232121458;
+                    if (gq * CPB < cpc && comp < K) a.lnrho_out[row * K + comp] = (double)l2[c] * 0.693147180559945309417232121458;
                 }
                 l2[c] = e;
                 s += e;
@@ -410,10 +419,12 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
                 const int64_t row0 = (blockIdx.x + lt * gridDim.x) * TF_TILE + 32 * qtr;
                 const int rows_here = (int)max((int64_t)0, min((int64_t)32, a.n - row0));
                 const int q4 = KP / 4;
+                int rr = st_rr0, c4 = st_c40;                    // (t128 / q4, t128 % q4), advanced by (128 / q4, 128 % q4)
                 for (int e = t128; e < rows_here * q4; e += 128) {
-                    const int rr = e / q4, c4 = e - rr * q4;
                     *reinterpret_cast<float4*>(r_f32 + (row0 + rr) * KP + 4 * c4) =
                         *reinterpret_cast<const float4*>(rst + (32 * qtr + rr) * RSP + 4 * c4);
+                    rr += st_drr; c4 += st_dc4;
+                    if (c4 >= q4) { c4 -= q4; ++rr; }
                 }
             }
             if (OUT && a.argmax_out != nullptr && gq == 0 && valid) {
