@@ -729,13 +729,21 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
         float rv[2][8];
         auto load_r = [&](int64_t t) {
             const int64_t row0 = (blockIdx.x + t * gridDim.x) * TM_SUB + 16 * sq;
+            if (t < my_sub && row0 + 16 <= a.n && c < KP) {            // all 16 rows exist: no per-row 64-bit compares
+                const float* p = r_f32 + row0 * KP + c;
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int64_t row = row0 + 8 * j + u;
-                    rv[j][u] = (t < my_sub && row < a.n && c < KP) ? __ldg(r_f32 + row * KP + c) : 0.f;
-                }
+                    for (int u = 0; u < 8; ++u) rv[j][u] = __ldg(p + (8 * j + u) * KP);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t row = row0 + 8 * j + u;
+                        rv[j][u] = (t < my_sub && row < a.n && c < KP) ? __ldg(r_f32 + row * KP + c) : 0.f;
+                    }
+            }
         };
         load_r(0);
         for (int64_t t = 0; t < my_sub; ++t) {
