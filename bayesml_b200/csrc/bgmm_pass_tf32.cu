@@ -747,12 +747,11 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
         };
         load_r(0);
         for (int64_t t = 0; t < my_sub; ++t) {
-            if (!lo_part && t + 2 < my_sub) {
-                // r rows of sub-tile t + 2 (this warp's 16 rows = 64 KP bytes, contiguous) towards L1
-                const int64_t r0 = (blockIdx.x + (t + 2) * gridDim.x) * TM_SUB + 16 * sq;
-                const int rows_here = (int)max((int64_t)0, min((int64_t)16, a.n - r0));
-                const char* pr = reinterpret_cast<const char*>(r_f32 + r0 * KP);
-                if (128 * lane < rows_here * KP * 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 128 * lane));
+            if (!lo_part && t + 3 < my_sub && 128 * lane < 16 * KP * 4) {
+                // r rows of sub-tile t + 2 (this warp's 16 rows = 64 KP bytes, contiguous) towards L2 / L1; sub-tile t + 2 is
+                // not the CTA's last, so all of its rows exist
+                const char* pr = reinterpret_cast<const char*>(r_f32 + ((blockIdx.x + (t + 2) * gridDim.x) * TM_SUB + 16 * sq) * KP);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pr + 128 * lane));
             }
             if (t >= 2) mbar_wait(&mdone[t & 1], (uint32_t)(((t >> 1) - 1) & 1));     // A buffer t & 1 free
             tc::fence_after_sync();
