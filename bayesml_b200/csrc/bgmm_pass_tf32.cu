@@ -639,10 +639,11 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
                 constexpr int CPP = DT > 0 ? DT / 2 : 1;            // 16-byte chunks per row pair
                 float* dstb = xs + (size_t)(tt & 1) * 32 * XPP;
                 const int64_t row0 = (blockIdx.x + tt * gridDim.x) * TM_SUB;
+                const bool full = tt + 1 < my_sub;                  // not this CTA's last sub-tile: every row exists
                 for (int c = gtid; c < 32 * CPP; c += TM_GEN) {
                     const int pr = c / CPP, w = c - pr * CPP;
                     const int64_t e0 = row0 * DT + (int64_t)c * 4;              // first float of the chunk
-                    const int nbytes = (tt < my_sub && e0 < a.n * DT) ? 16 : 0;  // rows past the end: zero fill
+                    const int nbytes = (full || (tt < my_sub && e0 < a.n * DT)) ? 16 : 0;  // rows past the end: zero fill
                     const float* src = nbytes ? x + e0 : x;
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dstb + pr * XPP + 4 * w)),
                                  "l"(src), "r"(nbytes) : "memory");
