@@ -212,22 +212,33 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
             }
         }
     };
+    // descriptor low words (address | LBO) of A stage 0 / B chunk 0 per part and k-step; stage, chunk are address offsets
+    uint32_t alo[2][KGR], blo[2][KGR];
+#pragma unroll
+    for (int pt = 0; pt < 2; ++pt)
+#pragma unroll
+        for (int ks = 0; ks < KGR; ++ks) {
+            const uint32_t aaddr = tc::smem_u32(As + (size_t)pt * TF_TILE * KD) + 2 * ks * a_lbo;
+            const uint32_t baddr = tc::smem_u32(Bs) + (pt ? 4 * (uint32_t)bpart : 0u) + 2 * ks * b_lbo;
+            alo[pt][ks] = ((aaddr >> 4) & 0x3FFFu) | (((a_lbo >> 4) & 0x3FFFu) << 16);
+            blo[pt][ks] = ((baddr >> 4) & 0x3FFFu) | (((b_lbo >> 4) & 0x3FFFu) << 16);
+        }
+    const uint32_t ahi = ((a_sbo >> 4) & 0x3FFFu) | (1u << 14), bhi = ((b_sbo >> 4) & 0x3FFFu) | (1u << 14);
+    const uint32_t a_stage_step = (uint32_t)(2 * TF_TILE * KD * 4) >> 4, b_chunk_step = (uint32_t)(nmma * KD * 4) >> 4;
     auto issue_chunk = [&](int64_t g) {                          // thread 0 only
         tc::fence_after_sync();
         const int64_t lt = g / nchunks;
         const int ch = (int)(g - lt * nchunks);
         const uint32_t d_tmem = tbase + (uint32_t)(g & 1) * TF_NMAX;
-        const uint32_t ah = tc::smem_u32(As + (size_t)(lt & 1) * 2 * TF_TILE * KD), al = ah + 4 * TF_TILE * KD;
-        const uint32_t bh = tc::smem_u32(Bs + (size_t)ch * nmma * KD), bl = bh + 4 * (uint32_t)bpart;
+        const uint32_t aoff = (lt & 1) ? a_stage_step : 0u, boff = (uint32_t)ch * b_chunk_step;
+        const uint32_t id = ch == nchunks - 1 ? idesc_last : idesc;
         uint32_t accum = 0;
 #pragma unroll
         for (int s = 0; s < 3; ++s) {                            // hi.hi, hi.lo, lo.hi
-            const uint32_t aa = s == 2 ? al : ah, bb = s == 1 ? bl : bh;
             if (dbg == 2 && s > 0) continue;                     // timing experiment: one product instead of three
 #pragma unroll
             for (int ks = 0; ks < KGR; ++ks) {
-                tc::mma_tf32(d_tmem, tc::make_smem_desc(aa + 2 * ks * a_lbo, a_lbo, a_sbo),
-                             tc::make_smem_desc(bb + 2 * ks * b_lbo, b_lbo, b_sbo), ch == nchunks - 1 ? idesc_last : idesc, accum);
+                tc::mma_tf32_w(d_tmem, alo[s == 2 ? 1 : 0][ks] + aoff, ahi, blo[s == 1 ? 1 : 0][ks] + boff, bhi, id, accum);
                 accum = 1;
             }
         }
