@@ -534,15 +534,20 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
     // [nst stages][2 parts][2 k-atoms of 32 samples][NF / 8 row groups][8 features][128 bytes, chunks swizzled]
     float* Bs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw_m) + 1023) & ~uintptr_t(1023));
     float* xs = Bs + 2 * nst * bpart;                                // [64][D + 2]: x', 1, 0   (run-time D only)
-    // compile-time D: xs = two buffers of 32 row PAIRS, pitch 2 D + 4 floats (16-byte aligned, conflict-free for LDS.128)
+    // compile-time D: xs = XNB buffers of 32 row PAIRS, pitch 2 D + 4 floats (16-byte aligned, conflict-free for LDS.128).
+    // Five buffers, filled two sub-tiles ahead: a generator warp can be up to two iterations behind the fastest one (each
+    // waits for the MMAs of sub-tile t - 2 only), so the tiles t - 2 .. t + 2 must be distinct buffers — then no block
+    // barrier is needed around the tile (the 256-thread barrier of the two-buffer form cost ~500 cycles of skew per sub-tile).
     constexpr int XPP = DT > 0 ? 2 * DT + 4 : 0;
-    unsigned short* ftab = reinterpret_cast<unsigned short*>(xs + (DT > 0 ? 2 * 32 * XPP : TM_SUB * (D + 2)));   // [P] (run-time D only)
+    constexpr int XNB = 5;
+    unsigned short* ftab = reinterpret_cast<unsigned short*>(xs + (DT > 0 ? XNB * 32 * XPP : TM_SUB * (D + 2)));   // [P] (run-time D only)
     uint64_t* mbar = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(ftab + (DT > 0 ? 0 : ((P + 7) & ~7))) + 15) & ~uintptr_t(15));
     uint64_t* mdone = mbar;                                    // [2] MMAs of sub-tile parity b complete (B stage + A buffer free)
     uint64_t* bfull = mbar + 2;                                // [2] B stage b written (one arrival per generator warp: 256
                                                                //     per-thread arrivals on one mbarrier cost ~1000 cycles a sub-tile)
     uint64_t* afull = mbar + 4;                                // [2] A buffer b written (one arrival per staging warp)
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 6);
+    uint64_t* xfull = mbar + 6;                                // [5] x tile buffer filled (cp.async arrivals of the 256 generator threads)
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(mbar + 11);
     const int KW = (KP + 31) / 32;                             // component warps with real rows (1 or 2)
     double* acc = acct + (int64_t)blockIdx.x * 256 * 64;      // CTA-private [NF][64] float64, feature-major
 
@@ -568,6 +573,7 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
         mbar_init(&mdone[0], 1); mbar_init(&mdone[1], 1);
         mbar_init(&bfull[0], TM_GEN / 32); mbar_init(&bfull[1], TM_GEN / 32);
         mbar_init(&afull[0], TM_STG / 32); mbar_init(&afull[1], TM_STG / 32);
+        for (int i = 0; i < 5; ++i) mbar_init(&xfull[i], TM_GEN);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     if (warp == 0) tc::tmem_alloc<512>(tslot);
@@ -642,13 +648,13 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
 #pragma unroll
         for (int r = 0; r < 8; ++r) xo[r] = (s_loc >> 5) * (NF * 32) + (((((s_loc & 31) >> 2) ^ r)) << 2) + (s_loc & 3);
         const int o0 = (s_loc >> 5) * (NF * 32) + gw * 32 + (((((s_loc & 31) >> 2) ^ gw)) << 2) + (s_loc & 3);
-        // compile-time D (a multiple of 4): the 64 x rows of a sub-tile (256 D contiguous bytes) come in by cp.async one whole
-        // sub-tile ahead — global loads issued at the top of the iteration that consumes them were 60 % of the generators'
+        // compile-time D (a multiple of 4): the 64 x rows of a sub-tile (256 D contiguous bytes) come in by cp.async TWO
+        // sub-tiles ahead (three buffers; one ahead still left ~500 cycles of wait per sub-tile in the generators' timeline) — global loads issued at the top of the iteration that consumes them were 60 % of the generators'
         // stall samples, and an L1 prefetch did not remove them.  Chunk c (16 bytes) of the tile goes to pair c / (D/2).
         auto fetch_x = [&](int64_t tt) {
             if (DT > 0) {
                 constexpr int CPP = DT > 0 ? DT / 2 : 1;            // 16-byte chunks per row pair
-                float* dstb = xs + (size_t)(tt & 1) * 32 * XPP;
+                float* dstb = xs + (size_t)(tt % XNB) * 32 * XPP;
                 const int64_t row0 = (blockIdx.x + tt * gridDim.x) * TM_SUB;
                 const bool full = tt + 1 < my_sub;                  // not this CTA's last sub-tile: every row exists
                 for (int c = gtid; c < 32 * CPP; c += TM_GEN) {
@@ -659,24 +665,25 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dstb + pr * XPP + 4 * w)),
                                  "l"(src), "r"(nbytes) : "memory");
                 }
-                asm volatile("cp.async.commit_group;" ::: "memory");
+                // arrives on the buffer's barrier when this thread's copies have landed (threads without a chunk at once)
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(tc::smem_u32(&xfull[tt % XNB])) : "memory");
             }
         };
         fetch_x(0);
+        fetch_x(1);
         for (int64_t t = 0; t < my_sub; ++t) {
             const int64_t sb = blockIdx.x + t * gridDim.x;
             float xa[DT > 0 ? DT : 1], xb[DT > 0 ? DT : 1];
             if (DT > 0) {
-                asm volatile("cp.async.wait_group 0;" ::: "memory");
-                asm volatile("bar.sync 1, 256;" ::: "memory");          // every generator thread's chunk of tile t has landed
-                const uint32_t pp = tc::smem_u32(xs + (size_t)(t & 1) * 32 * XPP + lane * XPP);
+                mbar_wait(&xfull[t % XNB], (uint32_t)((t / XNB) & 1));   // every generator thread's chunk of tile t has landed
+                const uint32_t pp = tc::smem_u32(xs + (size_t)(t % XNB) * 32 * XPP + lane * XPP);
 #pragma unroll
                 for (int i = 0; i < DT / 4; ++i) {
                     const float4 fa = lds128(pp + 16 * i), fb = lds128(pp + 16 * (DT / 4 + i));
                     xa[4 * i] = fa.x; xa[4 * i + 1] = fa.y; xa[4 * i + 2] = fa.z; xa[4 * i + 3] = fa.w;
                     xb[4 * i] = fb.x; xb[4 * i + 1] = fb.y; xb[4 * i + 2] = fb.z; xb[4 * i + 3] = fb.w;
                 }
-                fetch_x(t + 1);                                         // the other buffer: last read in iteration t - 1
+                fetch_x(t + 2);                                         // buffer (t + 2) % 5: last read (tile t - 3) by every warp
             }
             // the MMAs that read this stage are done: sub-tile t - 2 with two stages, t - 1 with one (large feature counts)
             if (nst == 2) { if (t >= 2) mbar_wait(&mdone[t & 1], (uint32_t)(((t >> 1) - 1) & 1)); }
@@ -837,8 +844,8 @@ static Tf32MPlan plan_tf32_m(int K, int D) {
     const int P = feat_count(D);
     m.NF = (P + 15) & ~15;
     auto bytes = [&](int nst) {
-        return sizeof(float) * ((size_t)2 * nst * m.NF * TM_SUB + (size_t)TM_SUB * (D + 2) + 2 * 32 * (2 * 32 + 4)) +
-               sizeof(unsigned short) * ((P + 7) & ~7) + 96 + 1024;
+        return sizeof(float) * ((size_t)2 * nst * m.NF * TM_SUB + (size_t)TM_SUB * (D + 2) + 5 * 32 * (2 * 16 + 4)) +
+               sizeof(unsigned short) * ((P + 7) & ~7) + 128 + 1024;
     };
     m.nst = bytes(2) <= 220 * 1024 ? 2 : 1;                    // two Phi stages when they fit (P <= ~190), else one
     m.smem = bytes(m.nst);
