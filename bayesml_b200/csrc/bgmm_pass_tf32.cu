@@ -651,26 +651,33 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
         // compile-time D (a multiple of 4): the 64 x rows of a sub-tile (256 D contiguous bytes) come in by cp.async TWO
         // sub-tiles ahead (three buffers; one ahead still left ~500 cycles of wait per sub-tile in the generators' timeline) — global loads issued at the top of the iteration that consumes them were 60 % of the generators'
         // stall samples, and an L1 prefetch did not remove them.  Chunk c (16 bytes) of the tile goes to pair c / (D/2).
-        auto fetch_x = [&](int64_t tt) {
+        // per-thread constants of the tile fetch: at most one 16-byte chunk per generator thread (32 D/2 <= 256 chunks)
+        constexpr int CPP = DT > 0 ? DT / 2 : 1;                // 16-byte chunks per row pair
+        const bool has_chunk = DT > 0 && gtid < 32 * CPP;
+        const uint32_t xdst0 = tc::smem_u32(xs + (gtid / CPP) * XPP + 4 * (gtid % CPP));
+        const float* xsrc = x + (int64_t)blockIdx.x * TM_SUB * DT + (int64_t)gtid * 4;   // this thread's chunk of the next tile
+        const int64_t xsrc_step = (int64_t)gridDim.x * TM_SUB * DT;
+        uint32_t xbuf = 0, xbar = tc::smem_u32(xfull);          // next tile's buffer (byte offset) and its barrier
+        int64_t xtt = 0;                                        // index of the next tile to fetch
+        auto fetch_x = [&]() {
             if (DT > 0) {
-                constexpr int CPP = DT > 0 ? DT / 2 : 1;            // 16-byte chunks per row pair
-                float* dstb = xs + (size_t)(tt % XNB) * 32 * XPP;
-                const int64_t row0 = (blockIdx.x + tt * gridDim.x) * TM_SUB;
-                const bool full = tt + 1 < my_sub;                  // not this CTA's last sub-tile: every row exists
-                for (int c = gtid; c < 32 * CPP; c += TM_GEN) {
-                    const int pr = c / CPP, w = c - pr * CPP;
-                    const int64_t e0 = row0 * DT + (int64_t)c * 4;              // first float of the chunk
-                    const int nbytes = (full || (tt < my_sub && e0 < a.n * DT)) ? 16 : 0;  // rows past the end: zero fill
-                    const float* src = nbytes ? x + e0 : x;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dstb + pr * XPP + 4 * w)),
-                                 "l"(src), "r"(nbytes) : "memory");
+                if (has_chunk) {
+                    // every row of a tile exists unless it is this CTA's last one: then test the chunk (rows past the end: zero fill)
+                    const int nbytes = (xtt + 1 < my_sub || (xtt < my_sub && xsrc < x + a.n * DT)) ? 16 : 0;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(xdst0 + xbuf), "l"(nbytes ? xsrc : x), "r"(nbytes)
+                                 : "memory");
                 }
                 // arrives on the buffer's barrier when this thread's copies have landed (threads without a chunk at once)
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(tc::smem_u32(&xfull[tt % XNB])) : "memory");
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];" ::"r"(xbar) : "memory");
+                xsrc += xsrc_step;
+                ++xtt;
+                xbuf += 32u * XPP * 4u;
+                xbar += 8u;
+                if (xbuf == XNB * 32u * XPP * 4u) { xbuf = 0; xbar -= 8u * XNB; }
             }
         };
-        fetch_x(0);
-        fetch_x(1);
+        fetch_x();
+        fetch_x();
         for (int64_t t = 0; t < my_sub; ++t) {
             const int64_t sb = blockIdx.x + t * gridDim.x;
             float xa[DT > 0 ? DT : 1], xb[DT > 0 ? DT : 1];
@@ -683,7 +690,7 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
                     xa[4 * i] = fa.x; xa[4 * i + 1] = fa.y; xa[4 * i + 2] = fa.z; xa[4 * i + 3] = fa.w;
                     xb[4 * i] = fb.x; xb[4 * i + 1] = fb.y; xb[4 * i + 2] = fb.z; xb[4 * i + 3] = fb.w;
                 }
-                fetch_x(t + 2);                                         // buffer (t + 2) % 5: last read (tile t - 3) by every warp
+                fetch_x();                                                 // buffer (t + 2) % 5: last read (tile t - 3) by every warp
             }
             // the MMAs that read this stage are done: sub-tile t - 2 with two stages, t - 1 with one (large feature counts)
             if (nst == 2) { if (t >= 2) mbar_wait(&mdone[t & 1], (uint32_t)(((t >> 1) - 1) & 1)); }
