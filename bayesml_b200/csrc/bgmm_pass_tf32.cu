@@ -648,9 +648,10 @@ pass_tf32_m_kernel(const PassArgs a, const Layout L, const float* __restrict__ r
 #pragma unroll
         for (int r = 0; r < 8; ++r) xo[r] = (s_loc >> 5) * (NF * 32) + (((((s_loc & 31) >> 2) ^ r)) << 2) + (s_loc & 3);
         const int o0 = (s_loc >> 5) * (NF * 32) + gw * 32 + (((((s_loc & 31) >> 2) ^ gw)) << 2) + (s_loc & 3);
-        // compile-time D (a multiple of 4): the 64 x rows of a sub-tile (256 D contiguous bytes) come in by cp.async TWO
-        // sub-tiles ahead (three buffers; one ahead still left ~500 cycles of wait per sub-tile in the generators' timeline) — global loads issued at the top of the iteration that consumes them were 60 % of the generators'
-        // stall samples, and an L1 prefetch did not remove them.  Chunk c (16 bytes) of the tile goes to pair c / (D/2).
+        // compile-time D (a multiple of 4): the 64 x rows of a sub-tile (256 D contiguous bytes) come in by cp.async TWO sub-tiles
+        // ahead into one of five buffers (see XNB above).  Global loads issued at the top of the iteration that consumes them
+        // were 60 % of the generators' stall samples, and an L1 prefetch did not remove them.  Chunk c (16 bytes) of the tile
+        // goes to row pair c / (D / 2).
         // per-thread constants of the tile fetch: at most one 16-byte chunk per generator thread (32 D/2 <= 256 chunks)
         constexpr int CPP = DT > 0 ? DT / 2 : 1;                // 16-byte chunks per row pair
         const bool has_chunk = DT > 0 && gtid < 32 * CPP;
