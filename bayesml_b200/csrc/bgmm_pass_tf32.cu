@@ -10,14 +10,18 @@
 //
 //   tf32_prep_kernel    per iteration: B (hi / lo parts, already in the shared-memory operand layout) and a2 from the
 //                       parameter set (Linv comes from bgmm_small: BGMM_P_LINV);
-//   pass_tf32_e_kernel  persistent, one CTA (128 threads) per SM, 128-sample tiles: the [x, 1] tile is split into
-//                       tf32 hi + lo and staged K-major in shared memory (two stages); ONE thread issues, per 256-column
-//                       chunk of (component, dimension) pairs, the three products hi.hi + hi.lo + lo.hi into one of two
-//                       TMEM buffers and commits to an mbarrier; all four warps read the chunk back (tcgen05.ld, lane =
-//                       sample), accumulate |y|^2 per component, and the next chunk's MMAs run meanwhile;
-//                       r (float32, [n][KP]) goes to HBM for the statistics kernel — 4 KP bytes per sample.
-// Operands are staged K-major in the no-swizzle canonical layout (bgmm_tc.cuh; verified on the B200 by
-// tests/test_gpu_tc.py).  Replaces `_update_q_z` :772-783 of the reference GMM file in fp32 mode; bar 1e-4.
+//   pass_tf32_e_kernel  persistent, one CTA (544 threads) per SM, 128-sample tiles: 16 epilogue / staging warps split the
+//                       [x, 1] tile into tf32 hi + lo and stage it K-major in shared memory (two stages, x prefetched one
+//                       tile ahead); a 17th warp issues, per 256-column chunk of (component, dimension) pairs, the three
+//                       products hi.hi + hi.lo + lo.hi into one of two TMEM buffers and commits to an mbarrier; the four
+//                       warps of a TMEM lane quarter split the chunk's columns (tcgen05.ld, lane = sample), accumulate |y|^2
+//                       per component and combine max / sum / entropy through shared memory; the next chunk's MMAs run
+//                       meanwhile; r (float32, [n][KP]) goes to HBM for the statistics kernel — 4 KP bytes per sample.
+//   pass_tf32_m_kernel  persistent, 544 threads: raw = R^T . Phi with R^T in TENSOR MEMORY (staging warps), Phi generated
+//                       into 128-byte-swizzled shared-memory stages (generator warps), one issuing warp; see its header.
+// E-kernel operands are staged K-major in the no-swizzle canonical layout, Phi in the SWIZZLE_128B layout (bgmm_tc.cuh; both
+// verified on the B200 by tests/test_gpu_tc.py).  Replaces `_update_q_z` :772-783 and `_calc_n_x_bar_s` :725-732 of the
+// reference GMM file in fp32 mode; bar 1e-4.
 #include "bgmm_common.cuh"
 #include "bgmm_mma.cuh"
 #include "bgmm_tc.cuh"
