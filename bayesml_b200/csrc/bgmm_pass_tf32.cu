@@ -469,10 +469,14 @@ pass_tf32_e_kernel(const PassArgs a, const Layout L, const float* __restrict__ i
 //   A = R^T lives in TENSOR MEMORY (lane = component, column = sample; written by the warp whose lanes are the components:
 //       lane c reads r[row][c], a coalesced 128-byte row per sample, and stores 8 samples per tcgen05.st) — no shared-memory
 //       traffic for A; rows K .. 127 of the M = 128 tile are zero;
-//   B = Phi (N = features, all of them in one MMA: P <= 256) is staged K-major, i.e. TRANSPOSED with respect to the thread
-//       that produces it (a thread owns a sample): scalar 4-byte stores, conflict-free through a padded k-chunk pitch of
-//       144 bytes; two stages, so the generation of sub-tile t + 1 overlaps the MMAs of sub-tile t.
-// Every value is split into tf32 hi (round to nearest, unbiased) + lo; hi.hi + hi.lo + lo.hi accumulate in fp32 in tensor
+//   B = Phi (N = features, all of them in one MMA: P <= 256) is staged K-major in the 128-byte-swizzle layout (a feature
+//       row holds 32 samples; bgmm_tc.cuh), i.e. TRANSPOSED with respect to the thread that produces it: generator warp g
+//       owns the features p = g (mod 8) — one row of every 8-row swizzle atom — and a lane two consecutive samples:
+//       conflict-free 8-byte stores; two stages, so the generation of sub-tile t + 1 overlaps the MMAs of sub-tile t;
+//       the x rows arrive by cp.async two sub-tiles ahead (five buffers, one mbarrier each).
+//   K <= 32: the hi parts of R^T sit in TMEM lanes 0-31, the lo parts in lanes 64-95 of the same columns: two MMAs per
+//       k-step (against Phi_hi and Phi_lo) give all four split products.
+// Every value is split into tf32 hi (truncated: one LOP3) + the exact remainder lo; the split products accumulate in fp32 in tensor
 // memory over TF_FLUSH sub-tiles and are then added into a float64 CTA-private array (feature-major, so a warp's lanes =
 // components are contiguous), so the fp32 error of a partial sum never exceeds that of 2048 samples.  Moments are about
 // the global centre (format 0), reduced over the CTAs by reduce_partials_kernel.
